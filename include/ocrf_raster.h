@@ -1,0 +1,174 @@
+/*
+ * ocrf_raster.h -- C ABI of the B200-native OcRF Gaussian render path (libocrf_raster.so).
+ *
+ * This is the drop-in boundary for the reference's pybind module `diff_gaussian_rasterization._C`
+ * (reference paths relative to
+ *  /root/reference/mmdet3d/models/necks/MVSGaussian/lib/submodules/diff-gaussian-rasterization/):
+ *
+ *   _C.rasterize_gaussians           ext.cpp:16, rasterize_points.cu:36-115
+ *        -> ocrf_preprocess_forward + ocrf_bin_forward + ocrf_render_forward
+ *   _C.rasterize_gaussians_backward  ext.cpp:17, rasterize_points.cu:118-196
+ *        -> ocrf_render_backward + ocrf_preprocess_backward
+ *   _C.mark_visible                  ext.cpp:18, rasterize_points.cu:198-217
+ *        -> ocrf_mark_visible
+ *   ObatinOpacityMask + apply        /root/reference/mmdet3d/models/necks/view_transformer_ocrf.py:230-242,1197-1199
+ *        -> ocrf_opacity_mask_forward / ocrf_opacity_mask_backward
+ *
+ * Conventions
+ *   - plain C types only: device pointers, sizes, an explicit cudaStream_t passed as void*.
+ *   - every entry point returns 0 on success, a positive cudaError_t on a CUDA failure, or a
+ *     negative OCRF_E* code for an argument error.  No C++ exception crosses the boundary.
+ *   - the caller owns ALL memory (as the reference's torch-owned buffers, rasterize_points.cu:27-33,
+ *     68-78); the library never allocates.  Workspace sizes and layouts come from ocrf_*_layout.
+ *   - a call renders a BATCH of V views (camera v looks at sample v / views_per_sample); V = 1,
+ *     S = 1 is exactly the reference's single call.  4x4 matrices are the reference's transposed
+ *     (column-major) layout, auxiliary.h:58-77.
+ */
+#ifndef OCRF_RASTER_H
+#define OCRF_RASTER_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OCRF_ABI_VERSION 1
+
+#define OCRF_EINVAL (-1)    /* bad argument (null pointer, non-positive size, unsupported channel count) */
+#define OCRF_ECAPACITY (-2) /* workspace too small for the request */
+
+/* floats per camera record: view[16] proj[16] campos[3] tanfovx tanfovy pad[3] */
+#define OCRF_CAM_STRIDE 40
+/* bytes per packed (tile, Gaussian) record consumed by the blend kernels */
+#define OCRF_RECORD_BYTES 48
+/* floats per (view, Gaussian) screen-space gradient record: dmean2D.xy, dconic.ABC, dopacity, pad[2] */
+#define OCRF_GGRAD_STRIDE 8
+
+typedef struct OcrfShape {
+  int32_t S;                /* samples (independent Gaussian sets) */
+  int32_t P;                /* Gaussians per sample */
+  int32_t V;                /* views in this batch; V % views_per_sample == 0 */
+  int32_t views_per_sample; /* view v renders sample v / views_per_sample */
+  int32_t W, H;             /* image size in pixels (all views) */
+  int32_t C;                /* feature channels per Gaussian (3 for RGB) */
+  int32_t sh_degree;        /* active SH degree (only read when shs != NULL) */
+  int32_t sh_M;             /* SH coefficients per Gaussian (shs is [S,P,M,3]) */
+} OcrfShape;
+
+/* Byte offsets of the arrays inside the three caller-allocated workspaces.  All offsets are
+ * multiples of 128.  geom: per (view, Gaussian) state kept for backward (the reference's
+ * GeometryState, rasterizer_impl.cu:155-170); binning: per (tile, Gaussian) pair (BinningState,
+ * :182-194); image: per pixel / per tile (ImageState, :172-179). */
+typedef struct OcrfGeomLayout {
+  size_t total;
+  size_t header;        /* uint32[32]: [0] num_pairs, [1] error flags, [2] block ticket, ... */
+  size_t depths;        /* float  [V*P] */
+  size_t xy;            /* float2 [V*P] */
+  size_t conic_opacity; /* float4 [V*P] */
+  size_t tiles_touched; /* uint32 [V*P] */
+  size_t offsets;       /* uint32 [V*P] inclusive scan of tiles_touched over the whole batch */
+  size_t rgb;           /* float  [V*P*3]  (SH path only) */
+  size_t clamped;       /* uint8  [V*P*3]  (SH path only) */
+  size_t scan_status;   /* uint64 [blocks] decoupled look-back state of the fused scan */
+} OcrfGeomLayout;
+
+typedef struct OcrfBinLayout {
+  size_t total;
+  size_t keys;          /* uint64 [N] sorted */
+  size_t point_list;    /* uint32 [N] sorted Gaussian ids */
+  size_t keys_tmp;      /* uint64 [N] the other half of the sort's ping-pong */
+  size_t vals_tmp;      /* uint32 [N] */
+  size_t keys_unsorted; /* where duplicateWithKeys writes: keys_tmp when the pass count is odd, else keys */
+  size_t vals_unsorted; /* (transient: overwritten by the sort) */
+  size_t records;       /* OCRF_RECORD_BYTES * N, sorted order (C == 3) or 32-byte records (C != 3) */
+  size_t histogram;     /* uint32 [8][256] */
+  size_t sort_status;   /* uint32 [passes][sort_tiles][256] + tickets */
+} OcrfBinLayout;
+
+typedef struct OcrfImageLayout {
+  size_t total;
+  size_t ranges;    /* uint2  [V*tiles] */
+  size_t final_T;   /* float  [V*H*W] */
+  size_t n_contrib; /* uint32 [V*H*W] */
+  size_t max_contrib; /* uint32 [V*tiles] largest n_contrib of the tile (lets backward skip the tail) */
+} OcrfImageLayout;
+
+int ocrf_abi_version(void);
+const char* ocrf_error_string(int code);
+
+int ocrf_geom_layout(const OcrfShape* shape, int use_sh, OcrfGeomLayout* out);
+int ocrf_bin_layout(const OcrfShape* shape, uint64_t num_pairs, OcrfBinLayout* out);
+int ocrf_image_layout(const OcrfShape* shape, OcrfImageLayout* out);
+/* number of key bits the sort covers: 32 + getHigherMsb(V * tiles) (rasterizer_impl.cu:35-50,300) */
+int ocrf_sort_end_bit(const OcrfShape* shape);
+
+/* Stage 1 (forward.cu:155-256 + the InclusiveSum at rasterizer_impl.cu:277).
+ * means3D [S,P,3], scales [S,P,3] / rotations [S,P,4] or cov3D_precomp [S,P,6], opacities [S,P],
+ * shs [S,P,M,3] or NULL, cams [V,OCRF_CAM_STRIDE].  Writes radii [V,P] and the geom workspace
+ * (header[0] = total number of (tile, Gaussian) pairs of the batch). */
+int ocrf_preprocess_forward(void* stream, const OcrfShape* shape, const float* means3D, const float* scales,
+                            const float* rotations, const float* cov3D_precomp, const float* opacities,
+                            const float* shs, const float* cams, float scale_modifier, int prefiltered,
+                            int32_t* radii, void* geom_ws);
+
+/* Stage 2 (rasterizer_impl.cu:70-138,289-318): duplicateWithKeys + onesweep radix sort of the
+ * 64-bit (view*tiles+tile | depth) keys + identifyTileRanges + record packing.
+ * `pair_capacity` is the number of pairs the binning workspace was laid out for; the true count is
+ * read on the device from the geom header, and exceeding the capacity sets header[1] bit 0 and
+ * renders nothing rather than overrunning.  colors [S,P,C] (ignored when the SH path produced rgb). */
+int ocrf_bin_forward(void* stream, const OcrfShape* shape, uint64_t pair_capacity, const int32_t* radii,
+                     const float* colors, int use_sh, void* geom_ws, void* bin_ws, void* image_ws);
+
+/* Stage 3 (forward.cu:261-374; median depth per the w-depth fork; opacity = 1 - final_T).
+ * bg [C]; out_color [V,C,H,W]; out_depth, out_opacity [V,1,H,W] (either may be NULL). */
+int ocrf_render_forward(void* stream, const OcrfShape* shape, uint64_t pair_capacity, const float* colors,
+                        int use_sh, const float* bg, const void* geom_ws, const void* bin_ws, void* image_ws,
+                        float* out_color, float* out_depth, float* out_opacity);
+
+/* Stage 4 (backward.cu:399-557).  dL_dcolor [V,C,H,W]; dL_dopacity_map [V,1,H,W] or NULL.
+ * Accumulates into ggrad [V,P,OCRF_GGRAD_STRIDE] and dL_dcolors [S,P,C] (or [V,P,3] when use_sh);
+ * both must be zeroed by the caller (as torch::zeros in rasterize_points.cu:151-159). */
+int ocrf_render_backward(void* stream, const OcrfShape* shape, uint64_t pair_capacity, const float* colors,
+                         int use_sh, const float* bg, const void* geom_ws, const void* bin_ws,
+                         const void* image_ws, const float* dL_dcolor, const float* dL_dopacity_map,
+                         float* ggrad, float* dL_dcolors);
+
+/* backward.cu:144-396: screen-space gradients -> dL_dmeans3D [S,P,3], dL_dmeans2D [V,P,3],
+ * dL_dopacities [S,P], dL_dscales [S,P,3] + dL_drotations [S,P,4] (or dL_dcov3D [S,P,6] when
+ * cov3D_precomp was given), dL_dshs [S,P,M,3] (SH path; dL_dcolors_view is then the [V,P,3] buffer
+ * written by ocrf_render_backward).  Sums over the views of a sample happen here. */
+int ocrf_preprocess_backward(void* stream, const OcrfShape* shape, const float* means3D, const float* scales,
+                             const float* rotations, const float* cov3D_precomp, const float* shs,
+                             const float* cams, float scale_modifier, const int32_t* radii, const void* geom_ws,
+                             const float* ggrad, const float* dL_dcolors_view, float* dL_dmeans3D,
+                             float* dL_dmeans2D, float* dL_dopacities, float* dL_dscales, float* dL_drotations,
+                             float* dL_dcov3D, float* dL_dshs);
+
+/* rasterizer_impl.cu:54-66,141-152.  means3D [P,3]; view/proj column-major 4x4; present uint8 [P]. */
+int ocrf_mark_visible(void* stream, int32_t P, const float* means3D, const float* viewmatrix,
+                      const float* projmatrix, uint8_t* present);
+
+/* Stand-alone pieces of stage 2, exposed for tests and for callers that bring their own keys:
+ * stable ascending sort of (uint64 key, uint32 value) pairs on key bits [0, end_bit).
+ * ws must hold ocrf_sort_workspace_bytes(n); keys_tmp/vals_tmp are ping-pong buffers of n elements.
+ * The sorted result is left in keys_out/vals_out. */
+size_t ocrf_sort_workspace_bytes(uint64_t n);
+int ocrf_sort_pairs(void* stream, uint64_t n, int end_bit, const uint64_t* keys_in, const uint32_t* vals_in,
+                    uint64_t* keys_out, uint32_t* vals_out, uint64_t* keys_tmp, uint32_t* vals_tmp, void* ws);
+
+/* Stage 5: mask = sigmoid(conv KxK([mean_c x, max_c x]) + opacity_bev); out = x * mask.
+ * x, out [B,C,H,W]; w [2,K,K]; opacity_bev, mask [B,1,H,W]; stats [B,2,H,W] (kept for backward). */
+int ocrf_opacity_mask_forward(void* stream, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, const float* x,
+                              const float* w, const float* opacity_bev, float* out, float* mask, float* stats);
+/* g_x [B,C,H,W], g_opacity_bev [B,1,H,W] are written; g_w [2,K,K] is ACCUMULATED (zero it first);
+ * scratch holds B*3*H*W floats. */
+int ocrf_opacity_mask_backward(void* stream, int32_t B, int32_t C, int32_t H, int32_t W, int32_t K, const float* x,
+                               const float* w, const float* mask, const float* stats, const float* g_out,
+                               float* g_x, float* g_w, float* g_opacity_bev, float* scratch);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCRF_RASTER_H */

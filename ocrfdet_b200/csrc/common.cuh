@@ -1,0 +1,138 @@
+// Shared device/host helpers of libocrf_raster.so.  sm_100a only.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ocrf_raster.h"
+
+namespace ocrf {
+
+constexpr int TILE = 16;               // blend tile edge (config.h:16-17 of the reference: BLOCK_X = BLOCK_Y = 16)
+constexpr int TILE_PIX = TILE * TILE;  // pixels per tile
+constexpr int NUM_SMS = 148;           // B200
+
+// geom header slots (uint32)
+constexpr int HDR_NUM_PAIRS = 0;
+constexpr int HDR_ERROR = 1;
+constexpr int HDR_TICKET = 2;
+constexpr uint32_t ERR_PAIR_OVERFLOW = 1u;
+constexpr uint32_t ERR_PREFILTERED = 2u;
+
+struct Camera {  // OCRF_CAM_STRIDE floats
+  float view[16];
+  float proj[16];
+  float campos[3];
+  float tanfovx, tanfovy;
+  float pad[3];
+};
+static_assert(sizeof(Camera) == OCRF_CAM_STRIDE * 4, "camera record size");
+
+// One (tile, Gaussian) pair as the blend kernels consume it (C == 3).
+struct __align__(16) Record {
+  float x, y, cA, cB;     // pixel-space mean, conic A, B
+  float cC, op, depth, r; // conic C, opacity, view depth, red
+  float g, b;             // green, blue
+  uint32_t id;            // Gaussian index inside its sample
+  uint32_t pad;
+};
+static_assert(sizeof(Record) == OCRF_RECORD_BYTES, "record size");
+
+// Same for C != 3: features are gathered by id.
+struct __align__(16) RecordLite {
+  float x, y, cA, cB;
+  float cC, op, depth;
+  uint32_t id;
+};
+
+__host__ __device__ inline size_t align128(size_t x) { return (x + 127) & ~size_t(127); }
+__host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+inline int tiles_x(const OcrfShape& s) { return (s.W + TILE - 1) / TILE; }
+inline int tiles_y(const OcrfShape& s) { return (s.H + TILE - 1) / TILE; }
+
+template <typename T>
+__host__ __device__ inline T* at(void* base, size_t off) { return reinterpret_cast<T*>(static_cast<char*>(base) + off); }
+template <typename T>
+__host__ __device__ inline const T* at(const void* base, size_t off) {
+  return reinterpret_cast<const T*>(static_cast<const char*>(base) + off);
+}
+
+// ---- radix sort geometry (shared between layout code and kernels) ----
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // keys per CTA per pass
+constexpr int SORT_MAX_PASSES = 8;
+
+inline uint64_t sort_tiles(uint64_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+
+struct SortWs {
+  size_t hist;    // uint32 [SORT_MAX_PASSES][256]
+  size_t ticket;  // uint32 [SORT_MAX_PASSES] (padded to 128 B)
+  size_t status;  // uint32 [SORT_MAX_PASSES][tiles + 1][256]
+  size_t total;
+};
+inline SortWs sort_ws_layout(uint64_t n) {
+  SortWs w;
+  size_t off = 0;
+  w.hist = off;   off = ((off + SORT_MAX_PASSES * 256 * 4) + 127) & ~size_t(127);
+  w.ticket = off; off = ((off + SORT_MAX_PASSES * 4) + 127) & ~size_t(127);
+  w.status = off; off = ((off + (size_t)SORT_MAX_PASSES * (sort_tiles(n) + 1) * 256 * 4) + 127) & ~size_t(127);
+  w.total = off;
+  return w;
+}
+// radix_sort.cu: data starts in (keys_a, vals_a); result in (keys_b, vals_b) when the pass count
+// ceil(end_bit/8) is odd, back in (keys_a, vals_a) when even.  n is read from *n_dev (<= n_cap).
+int sort_pairs_device(cudaStream_t st, const uint32_t* n_dev, uint64_t n_cap, int end_bit, uint64_t* keys_a,
+                      uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, void* ws);
+
+// ---- preprocess geometry ----
+constexpr int PRE_THREADS = 256;
+
+// ---- PTX helpers: mbarrier + 1D bulk async copy (TMA unit, SASS UBLKCP) ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// exp() for the blend: one MUFU.EX2.  |x| <= ~6 on every path whose result is used, so the
+// absolute error of x*log2(e) is < 5e-7 and the relative error of the result < 4e-7.
+__device__ __forceinline__ float fast_exp(float x) { return exp2f(x * 1.4426950408889634f); }
+
+}  // namespace ocrf
+
+#define OCRF_CHECK_LAST()                   \
+  do {                                      \
+    cudaError_t e__ = cudaGetLastError();   \
+    if (e__ != cudaSuccess) return (int)e__; \
+  } while (0)

@@ -1,0 +1,382 @@
+// Stage 4: per-tile reverse-order backward of the blend.
+//
+// Replaces renderCUDA<3> backward (cuda_rasterizer/backward.cu:399-557), whose nine global
+// atomicAdd per (pixel, Gaussian) pair are its dominant cost.  Here
+//   * the tile's records arrive back-to-front through the same mbarrier/bulk-copy ring as forward,
+//     and the traversal starts at the tile's largest n_contrib instead of the end of its list;
+//   * per record, the lanes of a warp that actually blended it reduce their nine partial gradients
+//     with a 14-shuffle butterfly (8-value reduce-scatter + one scalar), only when at least one
+//     lane contributed;
+//   * warps then combine in shared memory, and each record issues ONE set of global reductions per
+//     tile: a 16-byte and an 8-byte vector red for (dmean2D, dconic, dopacity) and three scalar
+//     reds for the colour -- 256x fewer global atomics than the reference in the dense case.
+// The arithmetic follows SURVEY.md appendix A5 (T recovered by division, suffix colour recurrence,
+// background term, no clamp mask) plus the opacity-map term  +T_final/(1-alpha) * dL/dO.
+// Summation order differs from the reference's unordered atomics: gradients agree to ~1e-5 rel.
+#include "common.cuh"
+
+namespace ocrf {
+
+constexpr int BWD_BATCH = 256;
+constexpr int BWD_ACC = 12;  // floats per record accumulator row (9 used)
+
+__device__ __forceinline__ float ex2_approx_b(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Reduce-scatter of 8 values over the warp: afterwards lane L (any L) holds the warp total of value
+// index ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1).
+__device__ __forceinline__ float butterfly8(float (&v)[8], int lane) {
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+  float w[4];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float keep = h16 ? v[i + 4] : v[i];
+    const float send = h16 ? v[i] : v[i + 4];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+  float u[2];
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const float keep = h8 ? w[i + 2] : w[i];
+    const float send = h8 ? w[i] : w[i + 2];
+    u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+  const float keep = h4 ? u[1] : u[0];
+  const float send = h4 ? u[0] : u[1];
+  float r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
+    int W, int H, int P, int views_per_sample, int colors_per_view, const uint2* __restrict__ ranges,
+    const Record* __restrict__ records, const float* __restrict__ bg, const float* __restrict__ final_T,
+    const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ max_contrib,
+    const float* __restrict__ dL_dpix, const float* __restrict__ dL_dopa, float* __restrict__ ggrad,
+    float* __restrict__ dL_dcolors) {
+  constexpr int NT = TILE_PIX / PPT;
+  __shared__ __align__(128) Record s_rec[2][BWD_BATCH];
+  __shared__ __align__(16) float s_acc[BWD_BATCH][BWD_ACC];
+  __shared__ uint32_t s_touched[BWD_BATCH];
+  __shared__ __align__(8) uint64_t s_bar[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = gridDim.x, tiles_per_view = gridDim.x * gridDim.y;
+  const int view = blockIdx.z;
+  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  const size_t vt = (size_t)view * tiles_per_view + tile;
+  const int mc = (int)max_contrib[vt];
+  if (mc == 0) return;
+  const uint2 range = ranges[vt];
+  const Record* src = records + range.x;
+  const int rounds = (mc + BWD_BATCH - 1) / BWD_BATCH;
+
+  const size_t HW = (size_t)H * W;
+  const int bx = (warp & 1) * 8 + (lane & 7);
+  const int by = (warp >> 1) * (4 * PPT) + (lane >> 3);
+  float fx[PPT], fy[PPT], T[PPT], Tf[PPT], g0[PPT], g1[PPT], g2[PPT], gop[PPT], bgdot[PPT];
+  float a0[PPT], a1[PPT], a2[PPT], lc0[PPT], lc1[PPT], lc2[PPT], last_alpha[PPT];
+  int nc[PPT];
+  const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+#pragma unroll
+  for (int p = 0; p < PPT; p++) {
+    const int px = blockIdx.x * TILE + bx, py = blockIdx.y * TILE + by + 4 * p;
+    const bool inside = px < W && py < H;
+    const size_t pix = (size_t)py * W + px;
+    fx[p] = (float)px;
+    fy[p] = (float)py;
+    Tf[p] = inside ? final_T[view * HW + pix] : 0.f;
+    T[p] = Tf[p];
+    nc[p] = inside ? (int)n_contrib[view * HW + pix] : 0;
+    g0[p] = inside ? dL_dpix[((size_t)view * 3 + 0) * HW + pix] : 0.f;
+    g1[p] = inside ? dL_dpix[((size_t)view * 3 + 1) * HW + pix] : 0.f;
+    g2[p] = inside ? dL_dpix[((size_t)view * 3 + 2) * HW + pix] : 0.f;
+    gop[p] = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
+    bgdot[p] = bg0 * g0[p] + bg1 * g1[p] + bg2 * g2[p];
+    a0[p] = a1[p] = a2[p] = lc0[p] = lc1[p] = lc2[p] = last_alpha[p] = 0.f;
+  }
+  const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+  // round r covers local list indices [lo_r, hi_r) with hi_r = mc - r*BATCH (back to front)
+  auto issue = [&](int r) {
+    const int hi = mc - r * BWD_BATCH;
+    const int lo = max(0, hi - BWD_BATCH);
+    const uint32_t bytes = (uint32_t)(hi - lo) * sizeof(Record);
+    mbar_expect_tx(&s_bar[r & 1], bytes);
+    bulk_g2s(&s_rec[r & 1][0], src + lo, bytes, &s_bar[r & 1]);
+  };
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+  }
+  for (int i = tid; i < BWD_BATCH * BWD_ACC; i += NT) (&s_acc[0][0])[i] = 0.f;
+  for (int i = tid; i < BWD_BATCH; i += NT) s_touched[i] = 0;
+  __syncthreads();
+  if (tid == 0) {
+    issue(0);
+    if (rounds > 1) issue(1);
+  }
+
+  for (int r = 0; r < rounds; r++) {
+    const int st = r & 1;
+    const int hi = mc - r * BWD_BATCH;
+    const int lo = max(0, hi - BWD_BATCH);
+    const int cnt = hi - lo;
+    mbar_wait(&s_bar[st], (r >> 1) & 1);
+    const float4* rec4 = reinterpret_cast<const float4*>(&s_rec[st][0]);
+
+    for (int j = cnt - 1; j >= 0; j--) {
+      const int k = lo + j;  // position in the tile list; pixel p blended it iff k < nc[p] and tests pass
+      const float4 a = rec4[3 * j], b = rec4[3 * j + 1];
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      float v8 = 0.f;
+      bool any = false;
+      float2 c = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int p = 0; p < PPT; p++) {
+        const float dx = a.x - fx[p], dy = a.y - fy[p];
+        const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+        const float G = ex2_approx_b(power * 1.4426950408889634f);
+        const float alpha = fminf(0.99f, b.y * G);
+        const bool ok = k < nc[p] && power <= 0.0f && alpha >= 1.0f / 255.0f;
+        if (!ok) continue;
+        if (!any) c = *reinterpret_cast<const float2*>(&rec4[3 * j + 2]);
+        any = true;
+        const float rcp = __fdividef(1.f, 1.f - alpha);
+        T[p] *= rcp;
+        const float w = alpha * T[p];
+        a0[p] = last_alpha[p] * lc0[p] + (1.f - last_alpha[p]) * a0[p];
+        a1[p] = last_alpha[p] * lc1[p] + (1.f - last_alpha[p]) * a1[p];
+        a2[p] = last_alpha[p] * lc2[p] + (1.f - last_alpha[p]) * a2[p];
+        lc0[p] = b.w; lc1[p] = c.x; lc2[p] = c.y;
+        float dL_dalpha = (b.w - a0[p]) * g0[p] + (c.x - a1[p]) * g1[p] + (c.y - a2[p]) * g2[p];
+        dL_dalpha *= T[p];
+        last_alpha[p] = alpha;
+        dL_dalpha += (Tf[p] * rcp) * (gop[p] - bgdot[p]);
+        const float dL_dG = b.y * dL_dalpha;
+        const float gdx = G * dx, gdy = G * dy;
+        const float dG_ddelx = -gdx * a.z - gdy * a.w;
+        const float dG_ddely = -gdy * b.x - gdx * a.w;
+        v[0] += dL_dG * dG_ddelx * ddelx_dx;
+        v[1] += dL_dG * dG_ddely * ddely_dy;
+        v[2] += -0.5f * gdx * dx * dL_dG;
+        v[3] += -0.5f * gdx * dy * dL_dG;
+        v[4] += -0.5f * gdy * dy * dL_dG;
+        v[5] += G * dL_dalpha;
+        v[6] += w * g0[p];
+        v[7] += w * g1[p];
+        v8 += w * g2[p];
+      }
+      if (!__any_sync(0xffffffffu, any)) continue;
+      const float r8 = butterfly8(v, lane);
+      const float r1 = warp_sum(v8);
+      if ((lane & 3) == 0) atomicAdd(&s_acc[j][lane >> 2], r8);
+      if (lane == 1) {
+        atomicAdd(&s_acc[j][8], r1);
+        s_touched[j] = 1;
+      }
+    }
+    __syncthreads();  // accumulators of this batch are complete
+    // flush: one thread per record (reads the ids still sitting in stage `st`)
+    for (int j = tid; j < cnt; j += NT) {
+      if (!s_touched[j]) continue;
+      s_touched[j] = 0;
+      const uint32_t id = s_rec[st][j].id;
+      float* row = &s_acc[j][0];
+      const float4 q0 = *reinterpret_cast<const float4*>(row);
+      const float4 q1 = *reinterpret_cast<const float4*>(row + 4);
+      const float q2 = row[8];
+      *reinterpret_cast<float4*>(row) = make_float4(0.f, 0.f, 0.f, 0.f);
+      *reinterpret_cast<float4*>(row + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+      row[8] = 0.f;
+      float* gg = ggrad + ((size_t)view * P + id) * OCRF_GGRAD_STRIDE;
+      atomicAdd(reinterpret_cast<float4*>(gg), q0);
+      atomicAdd(reinterpret_cast<float2*>(gg + 4), make_float2(q1.x, q1.y));
+      float* gc = dL_dcolors + ((size_t)(colors_per_view ? view : view / views_per_sample) * P + id) * 3;
+      atomicAdd(gc, q1.z);
+      atomicAdd(gc + 1, q1.w);
+      atomicAdd(gc + 2, q2);
+    }
+    __syncthreads();  // stage `st` fully consumed: only now may round r+2 land in it
+    if (tid == 0 && r + 2 < rounds) issue(r + 2);
+  }
+}
+
+// Generic channel count (C != 3): 32-byte records, features and feature gradients by id.
+constexpr int BWDG_BATCH = 128;
+
+__global__ void __launch_bounds__(TILE_PIX) render_backward_generic_kernel(
+    int W, int H, int C, int P, int views_per_sample, const uint2* __restrict__ ranges,
+    const RecordLite* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
+    const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+    const uint32_t* __restrict__ max_contrib, const float* __restrict__ dL_dpix, const float* __restrict__ dL_dopa,
+    float* __restrict__ ggrad, float* __restrict__ dL_dfeats) {
+  // One sweep per tile.  dL/dalpha of a pair needs the sum over ALL channels before the geometry
+  // gradients can be formed, so each thread walks every channel of the current record before moving
+  // on.  The per-channel suffix state "accum_rec" (C floats per pixel) lives in dynamic shared
+  // memory; the "last colour" of the recurrence is re-read from the feature table through the id of
+  // the previously blended record instead of being stored.
+  __shared__ __align__(16) RecordLite s_rec[BWDG_BATCH];
+  __shared__ __align__(16) float s_acc[BWDG_BATCH][8];
+  extern __shared__ float s_dyn[];  // [TILE_PIX][C] suffix accumulators "accum_rec" (last colour is re-read)
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = gridDim.x, tiles_per_view = gridDim.x * gridDim.y;
+  const int view = blockIdx.z;
+  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  const size_t vt = (size_t)view * tiles_per_view + tile;
+  const int mc = (int)max_contrib[vt];
+  if (mc == 0) return;
+  const uint2 range = ranges[vt];
+  const int s = view / views_per_sample;
+  const float* fbase = feats + (size_t)s * P * C;
+  float* gfbase = dL_dfeats + (size_t)s * P * C;
+  const size_t HW = (size_t)H * W;
+  const int px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
+  const int py = blockIdx.y * TILE + (warp >> 1) * 4 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const size_t pix = (size_t)py * W + px;
+  const float fx = (float)px, fy = (float)py;
+  const float Tf = inside ? final_T[view * HW + pix] : 0.f;
+  const int nc = inside ? (int)n_contrib[view * HW + pix] : 0;
+  const float gop = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
+  float bgdot = 0.f;
+  if (inside)
+    for (int ch = 0; ch < C; ch++) bgdot += bg[ch] * dL_dpix[((size_t)view * C + ch) * HW + pix];
+  float* my_accum = s_dyn + (size_t)tid * C;  // accum_rec per channel
+  for (int ch = 0; ch < C; ch++) my_accum[ch] = 0.f;
+  float T = Tf, last_alpha = 0.f;
+  int last_j_global = -1;  // list position of the previously blended Gaussian (its colour = "last colour")
+  const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+  const int rounds = (mc + BWDG_BATCH - 1) / BWDG_BATCH;
+
+  for (int r = 0; r < rounds; r++) {
+    const int hi = mc - r * BWDG_BATCH;
+    const int lo = max(0, hi - BWDG_BATCH);
+    const int cnt = hi - lo;
+    __syncthreads();
+    if (tid < cnt) s_rec[tid] = records[range.x + lo + tid];
+    for (int i = tid; i < BWDG_BATCH * 8; i += TILE_PIX) (&s_acc[0][0])[i] = 0.f;
+    __syncthreads();
+    for (int j = cnt - 1; j >= 0; j--) {
+      const int k = lo + j;
+      const float4 a = reinterpret_cast<const float4*>(&s_rec[j])[0];
+      const float4 b = reinterpret_cast<const float4*>(&s_rec[j])[1];
+      const uint32_t id = __float_as_uint(b.w);
+      const float dx = a.x - fx, dy = a.y - fy;
+      const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+      const float G = ex2_approx_b(power * 1.4426950408889634f);
+      const float alpha = fminf(0.99f, b.y * G);
+      const bool ok = k < nc && power <= 0.0f && alpha >= 1.0f / 255.0f;
+      if (!__any_sync(0xffffffffu, ok)) continue;
+      float rcp = 1.f, w = 0.f, dL_dalpha = 0.f;
+      if (ok) {
+        rcp = __fdividef(1.f, 1.f - alpha);
+        T *= rcp;
+        w = alpha * T;
+      }
+      // colour part, channel by channel: features of this Gaussian and of the previously blended one
+      const float* fcur = fbase + (size_t)id * C;
+      const uint32_t last_id = last_j_global >= 0 ? records[range.x + last_j_global].id : 0u;
+      const float* flast = fbase + (size_t)last_id * C;
+      for (int ch = 0; ch < C; ch++) {
+        float contrib = 0.f;
+        if (ok) {
+          const float cval = __ldg(fcur + ch);
+          const float lcv = last_j_global >= 0 ? __ldg(flast + ch) : 0.f;
+          const float acc = last_alpha * lcv + (1.f - last_alpha) * my_accum[ch];
+          my_accum[ch] = acc;
+          const float gch = dL_dpix[((size_t)view * C + ch) * HW + pix];
+          dL_dalpha += (cval - acc) * gch;
+          contrib = w * gch;
+        }
+        const float tot = warp_sum(contrib);
+        if (lane == 0 && tot != 0.f) atomicAdd(gfbase + (size_t)id * C + ch, tot);
+      }
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (ok) {
+        dL_dalpha *= T;
+        last_alpha = alpha;
+        last_j_global = k;
+        dL_dalpha += (Tf * rcp) * (gop - bgdot);
+        const float dL_dG = b.y * dL_dalpha;
+        const float gdx = G * dx, gdy = G * dy;
+        v[0] = dL_dG * (-gdx * a.z - gdy * a.w) * ddelx_dx;
+        v[1] = dL_dG * (-gdy * b.x - gdx * a.w) * ddely_dy;
+        v[2] = -0.5f * gdx * dx * dL_dG;
+        v[3] = -0.5f * gdx * dy * dL_dG;
+        v[4] = -0.5f * gdy * dy * dL_dG;
+        v[5] = G * dL_dalpha;
+      }
+      const float r8 = butterfly8(v, lane);
+      if ((lane & 3) == 0 && (lane >> 2) < 6) atomicAdd(&s_acc[j][lane >> 2], r8);
+    }
+    __syncthreads();
+    for (int j = tid; j < cnt; j += TILE_PIX) {
+      const float4 q0 = *reinterpret_cast<const float4*>(&s_acc[j][0]);
+      const float2 q1 = *reinterpret_cast<const float2*>(&s_acc[j][4]);
+      if (q0.x == 0.f && q0.y == 0.f && q0.z == 0.f && q0.w == 0.f && q1.x == 0.f && q1.y == 0.f) continue;
+      float* gg = ggrad + ((size_t)view * P + s_rec[j].id) * OCRF_GGRAD_STRIDE;
+      atomicAdd(reinterpret_cast<float4*>(gg), q0);
+      atomicAdd(reinterpret_cast<float2*>(gg + 4), q1);
+    }
+  }
+}
+
+}  // namespace ocrf
+
+using namespace ocrf;
+
+static int env_int_b(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+extern "C" int ocrf_render_backward(void* stream, const OcrfShape* sh, uint64_t pair_capacity, const float* colors,
+                                    int use_sh, const float* bg, const void* geom_ws, const void* bin_ws,
+                                    const void* image_ws, const float* dL_dcolor, const float* dL_dopacity_map,
+                                    float* ggrad, float* dL_dcolors) {
+  if (!sh || !bg || !bin_ws || !image_ws || !dL_dcolor || !ggrad || !dL_dcolors) return OCRF_EINVAL;
+  (void)geom_ws;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  OcrfBinLayout B;
+  OcrfImageLayout I;
+  int rc = ocrf_bin_layout(sh, pair_capacity, &B);
+  if (rc) return rc;
+  ocrf_image_layout(sh, &I);
+  const dim3 grid(tiles_x(*sh), tiles_y(*sh), sh->V);
+  const uint2* ranges = at<uint2>(image_ws, I.ranges);
+  const float* fT = at<float>(image_ws, I.final_T);
+  const uint32_t* nc = at<uint32_t>(image_ws, I.n_contrib);
+  const uint32_t* mc = at<uint32_t>(image_ws, I.max_contrib);
+  if (sh->C == 3) {
+    static const int ppt = env_int_b("OCRF_BWD_PPT", 1);
+    const Record* rec = at<Record>(bin_ws, B.records);
+    if (ppt == 2)
+      render_backward_c3_kernel<2><<<grid, TILE_PIX / 2, 0, st>>>(sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
+                                                                  ranges, rec, bg, fT, nc, mc, dL_dcolor,
+                                                                  dL_dopacity_map, ggrad, dL_dcolors);
+    else
+      render_backward_c3_kernel<1><<<grid, TILE_PIX, 0, st>>>(sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
+                                                              ranges, rec, bg, fT, nc, mc, dL_dcolor, dL_dopacity_map,
+                                                              ggrad, dL_dcolors);
+  } else {
+    if (!colors) return OCRF_EINVAL;
+    const size_t dyn = (size_t)TILE_PIX * sh->C * sizeof(float);
+    if (dyn > 160 * 1024) return OCRF_ECAPACITY;
+    cudaError_t e = cudaFuncSetAttribute(render_backward_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)dyn);
+    if (e != cudaSuccess) return (int)e;
+    render_backward_generic_kernel<<<grid, TILE_PIX, dyn, st>>>(
+        sh->W, sh->H, sh->C, sh->P, sh->views_per_sample, ranges, at<RecordLite>(bin_ws, B.records), colors, bg, fT, nc,
+        mc, dL_dcolor, dL_dopacity_map, ggrad, dL_dcolors);
+  }
+  OCRF_CHECK_LAST();
+  return 0;
+}

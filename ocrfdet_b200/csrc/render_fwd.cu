@@ -1,0 +1,307 @@
+// Stage 3: 16x16-tile forward alpha compositing of colour/features, median depth and opacity.
+//
+// Replaces renderCUDA<3> (cuda_rasterizer/forward.cu:261-374), adds the w-depth fork's median depth
+// (/root/reference/diff-gaussian-rasterization-w-depth/README.md:8-13) and the opacity map 1 - T.
+//
+// Design
+//   * grid = (tiles_x, tiles_y, V): every view of the batch in one launch.
+//   * The tile's (already packed, contiguous) records are streamed into shared memory by the TMA
+//     unit: one elected thread issues a 1-D cp.async.bulk per batch of 256 records into a two-stage
+//     ring guarded by mbarriers, so the copy of batch r+1 runs under the blending of batch r and no
+//     thread spends registers or LSU issue slots on staging.
+//   * A warp owns a compact 8x4 (PPT=1) or 8x8 (PPT=2) pixel block rather than a 16x2 strip: fewer
+//     Gaussians of the tile list reach any pixel of the warp, so more iterations are skipped by all
+//     32 lanes at once.
+//   * Every thread reads a record with three broadcast LDS.128; exp() is one MUFU.EX2.
+//   * Early ray termination as the reference: the CTA leaves as soon as every pixel is done.
+// The blend arithmetic keeps the reference's expressions and thresholds (power > 0, alpha < 1/255,
+// min(0.99, .), stop-before-blend at T < 1e-4), see SURVEY.md appendix A4.
+#include "common.cuh"
+
+namespace ocrf {
+
+constexpr int FWD_BATCH = 256;  // records per shared-memory stage
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(TILE_PIX / PPT) render_forward_c3_kernel(
+    int W, int H, const uint2* __restrict__ ranges, const Record* __restrict__ records, const float* __restrict__ bg,
+    float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ max_contrib,
+    float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_opacity) {
+  constexpr int NT = TILE_PIX / PPT;
+  __shared__ __align__(128) Record s_rec[2][FWD_BATCH];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ uint32_t s_max;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = gridDim.x, tiles_per_view = gridDim.x * gridDim.y;
+  const int view = blockIdx.z;
+  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  const uint2 range = ranges[(size_t)view * tiles_per_view + tile];
+  const int n = (int)(range.y - range.x);
+  const int rounds = (n + FWD_BATCH - 1) / FWD_BATCH;
+  const Record* src = records + range.x;
+
+  // pixel block of this warp
+  const int bx = (warp & 1) * 8 + (lane & 7);
+  const int by = (warp >> 1) * (4 * PPT) + (lane >> 3);
+  int px[PPT], py[PPT];
+  bool inside[PPT], done[PPT];
+  float fx[PPT], fy[PPT];
+#pragma unroll
+  for (int p = 0; p < PPT; p++) {
+    px[p] = blockIdx.x * TILE + bx;
+    py[p] = blockIdx.y * TILE + by + 4 * p;
+    inside[p] = px[p] < W && py[p] < H;
+    done[p] = !inside[p];
+    fx[p] = (float)px[p];
+    fy[p] = (float)py[p];
+  }
+
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+    s_max = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+      if (r < rounds) {
+        const uint32_t bytes = (uint32_t)min(FWD_BATCH, n - r * FWD_BATCH) * sizeof(Record);
+        mbar_expect_tx(&s_bar[r], bytes);
+        bulk_g2s(&s_rec[r][0], src + r * FWD_BATCH, bytes, &s_bar[r]);
+      }
+  }
+
+  float T[PPT], D[PPT], C0[PPT], C1[PPT], C2[PPT];
+  uint32_t last[PPT];
+#pragma unroll
+  for (int p = 0; p < PPT; p++) {
+    T[p] = 1.f; D[p] = 15.f; C0[p] = C1[p] = C2[p] = 0.f; last[p] = 0;
+  }
+
+  for (int r = 0; r < rounds; r++) {
+    const int st = r & 1;
+    mbar_wait(&s_bar[st], (r >> 1) & 1);
+    const int cnt = min(FWD_BATCH, n - r * FWD_BATCH);
+    const float4* rec4 = reinterpret_cast<const float4*>(&s_rec[st][0]);
+    bool all_done = true;
+#pragma unroll
+    for (int p = 0; p < PPT; p++) all_done = all_done && done[p];
+    if (!all_done) {
+      for (int j = 0; j < cnt; j++) {
+        const float4 a = rec4[3 * j], b = rec4[3 * j + 1];
+        bool any_blend = false;
+        float alpha_p[PPT];
+#pragma unroll
+        for (int p = 0; p < PPT; p++) {
+          const float dx = a.x - fx[p], dy = a.y - fy[p];
+          const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+          const float alpha = fminf(0.99f, b.y * ex2_approx(power * 1.4426950408889634f));
+          const bool ok = !done[p] && power <= 0.0f && alpha >= 1.0f / 255.0f;
+          alpha_p[p] = ok ? alpha : 0.f;
+          any_blend = any_blend || ok;
+        }
+        if (!any_blend) continue;
+        const float2 c = *reinterpret_cast<const float2*>(&rec4[3 * j + 2]);
+#pragma unroll
+        for (int p = 0; p < PPT; p++) {
+          if (alpha_p[p] == 0.f) continue;
+          const float alpha = alpha_p[p];
+          const float test_T = T[p] * (1.f - alpha);
+          if (test_T < 0.0001f) {
+            done[p] = true;
+            continue;
+          }
+          const float w = alpha * T[p];
+          C0[p] += b.w * w;
+          C1[p] += c.x * w;
+          C2[p] += c.y * w;
+          if (T[p] > 0.5f && test_T < 0.5f) D[p] = b.z;
+          T[p] = test_T;
+          last[p] = (uint32_t)(r * FWD_BATCH + j + 1);
+        }
+        all_done = true;
+#pragma unroll
+        for (int p = 0; p < PPT; p++) all_done = all_done && done[p];
+        if (all_done) break;
+      }
+    }
+    // everyone is finished with stage `st`; leave early once the whole tile is saturated
+    const int num_done = __syncthreads_count(all_done);
+    const bool quit = num_done == NT;
+    if (quit) {
+      if (r + 1 < rounds) mbar_wait(&s_bar[(r + 1) & 1], ((r + 1) >> 1) & 1);  // drain the copy in flight
+      break;
+    }
+    if (tid == 0 && r + 2 < rounds) {
+      const uint32_t bytes = (uint32_t)min(FWD_BATCH, n - (r + 2) * FWD_BATCH) * sizeof(Record);
+      mbar_expect_tx(&s_bar[st], bytes);
+      bulk_g2s(&s_rec[st][0], src + (r + 2) * FWD_BATCH, bytes, &s_bar[st]);
+    }
+  }
+
+  uint32_t my_max = 0;
+  const size_t HW = (size_t)H * W;
+#pragma unroll
+  for (int p = 0; p < PPT; p++) {
+    if (!inside[p]) continue;
+    const size_t pix = (size_t)py[p] * W + px[p];
+    final_T[view * HW + pix] = T[p];
+    n_contrib[view * HW + pix] = last[p];
+    my_max = max(my_max, last[p]);
+    float* oc = out_color + (size_t)view * 3 * HW + pix;
+    oc[0] = C0[p] + T[p] * bg[0];
+    oc[HW] = C1[p] + T[p] * bg[1];
+    oc[2 * HW] = C2[p] + T[p] * bg[2];
+    if (out_depth) out_depth[view * HW + pix] = D[p];
+    if (out_opacity) out_opacity[view * HW + pix] = 1.f - T[p];
+  }
+  my_max = __reduce_max_sync(0xffffffffu, my_max);
+  if (lane == 0 && my_max) atomicMax(&s_max, my_max);
+  __syncthreads();
+  if (tid == 0) max_contrib[(size_t)view * tiles_per_view + tile] = s_max;
+}
+
+// Generic channel count: 32-byte records, features gathered by id, CK channels per traversal.
+constexpr int FWD_CK = 16;
+constexpr int FWDG_BATCH = 128;
+
+__global__ void __launch_bounds__(TILE_PIX) render_forward_generic_kernel(
+    int W, int H, int C, int P, int views_per_sample, const uint2* __restrict__ ranges,
+    const RecordLite* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
+    float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ max_contrib,
+    float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_opacity) {
+  __shared__ __align__(16) RecordLite s_rec[FWDG_BATCH];
+  __shared__ __align__(16) float s_feat[FWDG_BATCH][FWD_CK];
+  __shared__ uint32_t s_max;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = gridDim.x, tiles_per_view = gridDim.x * gridDim.y;
+  const int view = blockIdx.z;
+  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  const uint2 range = ranges[(size_t)view * tiles_per_view + tile];
+  const int n = (int)(range.y - range.x);
+  const int rounds = (n + FWDG_BATCH - 1) / FWDG_BATCH;
+  const float* fbase = feats + (size_t)(view / views_per_sample) * P * C;
+
+  const int px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
+  const int py = blockIdx.y * TILE + (warp >> 1) * 4 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const float fx = (float)px, fy = (float)py;
+  const size_t HW = (size_t)H * W;
+  const size_t pix = (size_t)py * W + px;
+  if (tid == 0) s_max = 0;
+
+  for (int c0 = 0; c0 < C; c0 += FWD_CK) {
+    const int ck = min(FWD_CK, C - c0);
+    bool done = !inside;
+    float T = 1.f, D = 15.f;
+    uint32_t last = 0;
+    float acc[FWD_CK];
+#pragma unroll
+    for (int k = 0; k < FWD_CK; k++) acc[k] = 0.f;
+    for (int r = 0; r < rounds; r++) {
+      const int num_done = __syncthreads_count(done);
+      if (num_done == TILE_PIX) break;
+      const int cnt = min(FWDG_BATCH, n - r * FWDG_BATCH);
+      if (tid < cnt) s_rec[tid] = records[range.x + r * FWDG_BATCH + tid];
+      // gather the feature chunk: 4 threads per Gaussian when the rows are 16-byte aligned
+      for (int e = tid; e < cnt * FWD_CK; e += TILE_PIX) {
+        const int j = e / FWD_CK, k = e - j * FWD_CK;
+        const uint32_t id = records[range.x + r * FWDG_BATCH + j].id;
+        s_feat[j][k] = k < ck ? __ldg(fbase + (size_t)id * C + c0 + k) : 0.f;
+      }
+      __syncthreads();
+      for (int j = 0; !done && j < cnt; j++) {
+        const float4 a = reinterpret_cast<const float4*>(&s_rec[j])[0];
+        const float4 b = reinterpret_cast<const float4*>(&s_rec[j])[1];
+        const float dx = a.x - fx, dy = a.y - fy;
+        const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+        if (power > 0.0f) continue;
+        const float alpha = fminf(0.99f, b.y * ex2_approx(power * 1.4426950408889634f));
+        if (alpha < 1.0f / 255.0f) continue;
+        const float test_T = T * (1.f - alpha);
+        if (test_T < 0.0001f) {
+          done = true;
+          continue;
+        }
+        const float w = alpha * T;
+#pragma unroll
+        for (int k = 0; k < FWD_CK; k += 4) {
+          const float4 f = *reinterpret_cast<const float4*>(&s_feat[j][k]);
+          acc[k] += f.x * w; acc[k + 1] += f.y * w; acc[k + 2] += f.z * w; acc[k + 3] += f.w * w;
+        }
+        if (T > 0.5f && test_T < 0.5f) D = b.z;
+        T = test_T;
+        last = (uint32_t)(r * FWDG_BATCH + j + 1);
+      }
+    }
+    if (inside) {
+#pragma unroll
+      for (int k = 0; k < FWD_CK; k++)
+        if (k < ck) out_color[((size_t)view * C + c0 + k) * HW + pix] = acc[k] + T * bg[c0 + k];
+      if (c0 == 0) {
+        final_T[view * HW + pix] = T;
+        n_contrib[view * HW + pix] = last;
+        if (out_depth) out_depth[view * HW + pix] = D;
+        if (out_opacity) out_opacity[view * HW + pix] = 1.f - T;
+        atomicMax(&s_max, last);
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) max_contrib[(size_t)view * tiles_per_view + tile] = s_max;
+}
+
+}  // namespace ocrf
+
+using namespace ocrf;
+
+static int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return s ? atoi(s) : dflt;
+}
+
+extern "C" int ocrf_render_forward(void* stream, const OcrfShape* sh, uint64_t pair_capacity, const float* colors,
+                                   int use_sh, const float* bg, const void* geom_ws, const void* bin_ws,
+                                   void* image_ws, float* out_color, float* out_depth, float* out_opacity) {
+  if (!sh || !bg || !bin_ws || !image_ws || !out_color) return OCRF_EINVAL;
+  if (sh->C <= 0 || (sh->C != 3 && !colors)) return OCRF_EINVAL;
+  (void)geom_ws;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  OcrfBinLayout B;
+  OcrfImageLayout I;
+  int rc = ocrf_bin_layout(sh, pair_capacity, &B);
+  if (rc) return rc;
+  ocrf_image_layout(sh, &I);
+  const dim3 grid(tiles_x(*sh), tiles_y(*sh), sh->V);
+  const uint2* ranges = at<uint2>(image_ws, I.ranges);
+  float* fT = at<float>(image_ws, I.final_T);
+  uint32_t* nc = at<uint32_t>(image_ws, I.n_contrib);
+  uint32_t* mc = at<uint32_t>(image_ws, I.max_contrib);
+  if (sh->C == 3) {
+    static const int ppt = env_int("OCRF_FWD_PPT", 1);
+    const Record* rec = at<Record>(bin_ws, B.records);
+    if (ppt == 2)
+      render_forward_c3_kernel<2><<<grid, TILE_PIX / 2, 0, st>>>(sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
+                                                                 out_depth, out_opacity);
+    else
+      render_forward_c3_kernel<1><<<grid, TILE_PIX, 0, st>>>(sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
+                                                             out_depth, out_opacity);
+  } else {
+    (void)use_sh;
+    render_forward_generic_kernel<<<grid, TILE_PIX, 0, st>>>(sh->W, sh->H, sh->C, sh->P, sh->views_per_sample, ranges,
+                                                             at<RecordLite>(bin_ws, B.records), colors, bg, fT, nc, mc,
+                                                             out_color, out_depth, out_opacity);
+  }
+  OCRF_CHECK_LAST();
+  return 0;
+}

@@ -1,0 +1,287 @@
+"""Host-side mirror of the reference plugin `diff_gaussian_rasterization` on top of the C ABI.
+
+Same names, argument meaning and error behaviour as
+/root/reference/mmdet3d/models/necks/MVSGaussian/lib/submodules/diff-gaussian-rasterization/
+diff_gaussian_rasterization/__init__.py  (cited below as PKG:line), with the live w-depth fork's
+3-tuple return `(color, radii, depth)` that OcRFDet unpacks
+(/root/reference/mmdet3d/models/necks/MVSGaussian/lib/gaussian_renderer/__init__.py:62).
+
+Extensions (all opt-in, the reference call keeps working unmodified):
+  * `debug` defaults to False, so the fork's 11-field settings tuple and the vendored 12-field one
+    both construct.
+  * `GaussianRasterizer(settings, return_opacity=True)` appends the accumulated opacity map
+    (1 - final_T) with a backward.
+  * any channel count C for `colors_precomp` (the reference is compiled for C = 3).
+  * `render_batch`: every (sample, view) pair of a rank in ONE launch sequence.
+
+PyTorch is plumbing here (device memory, streams, autograd glue); all compute is in
+libocrf_raster.so and there is no CPU / eager fallback.
+"""
+import ctypes as C
+from typing import NamedTuple, Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import OcrfBinLayout, OcrfGeomLayout, OcrfImageLayout, OcrfShape, check, current_stream, ptr
+
+
+class GaussianRasterizationSettings(NamedTuple):
+    """PKG:157-169 (the live fork omits `debug`: GR:39-57)."""
+    image_height: int
+    image_width: int
+    tanfovx: float
+    tanfovy: float
+    bg: torch.Tensor
+    scale_modifier: float
+    viewmatrix: torch.Tensor
+    projmatrix: torch.Tensor
+    sh_degree: int
+    campos: torch.Tensor
+    prefiltered: bool
+    debug: bool = False
+
+
+def pack_cameras(viewmatrix, projmatrix, campos, tanfovx, tanfovy):
+    """Camera records [V, 40] for the C ABI: view[16] proj[16] campos[3] tanfovx tanfovy pad[3].
+
+    viewmatrix / projmatrix are the reference's transposed 4x4 matrices ([4,4] or [V,4,4]);
+    tanfovx / tanfovy are floats or [V] tensors.  Built on the device of `viewmatrix`.
+    """
+    vm = viewmatrix.reshape(-1, 16).float()
+    V = vm.shape[0]
+    pm = projmatrix.reshape(-1, 16).float()
+    cp = campos.reshape(-1, 3).float()
+    dev = vm.device
+
+    def col(t):
+        if torch.is_tensor(t):
+            return t.reshape(-1, 1).float().to(dev).expand(V, 1)
+        return torch.full((V, 1), float(t), dtype=torch.float32, device=dev)
+
+    pad = torch.zeros((V, 3), dtype=torch.float32, device=dev)
+    return torch.cat([vm, pm, cp, col(tanfovx), col(tanfovy), pad], dim=1).contiguous()
+
+
+def _require_cuda(t, name):
+    if not t.is_cuda:
+        raise _lib.OcrfError("%s must be a CUDA tensor: the render path has no CPU implementation" % name)
+
+
+class _Workspaces:
+    """Byte layouts of the three caller-owned workspaces (one query each, no GPU work)."""
+
+    def __init__(self, shape, use_sh):
+        L = _lib.lib()
+        self.geom = OcrfGeomLayout()
+        self.image = OcrfImageLayout()
+        check(L.ocrf_geom_layout(C.byref(shape), int(use_sh), C.byref(self.geom)), "ocrf_geom_layout")
+        check(L.ocrf_image_layout(C.byref(shape), C.byref(self.image)), "ocrf_image_layout")
+
+    @staticmethod
+    def bin_layout(shape, n):
+        b = OcrfBinLayout()
+        check(_lib.lib().ocrf_bin_layout(C.byref(shape), C.c_uint64(n), C.byref(b)), "ocrf_bin_layout")
+        return b
+
+
+class _RasterizeBatch(torch.autograd.Function):
+    """The autograd node (PKG:44-155), batched over V views of S samples."""
+
+    @staticmethod
+    def forward(ctx, means3D, means2D, shs, colors, opacities, scales, rotations, cov3D_precomp, cams, bg, cfg):
+        L = _lib.lib()
+        S, P = means3D.shape[0], means3D.shape[1]
+        V = cams.shape[0]
+        use_sh = shs is not None
+        Cc = 3 if use_sh else colors.shape[-1]
+        W, H = cfg["W"], cfg["H"]
+        shape = OcrfShape(S, P, V, V // S, W, H, Cc, cfg["sh_degree"], shs.shape[2] if use_sh else 0)
+        dev = means3D.device
+        stream = current_stream()
+        ws = _Workspaces(shape, use_sh)
+        radii = torch.empty((V, P), dtype=torch.int32, device=dev)
+        geom = torch.empty(ws.geom.total, dtype=torch.uint8, device=dev)
+        image = torch.empty(ws.image.total, dtype=torch.uint8, device=dev)
+        color = torch.empty((V, Cc, H, W), dtype=torch.float32, device=dev)
+        depth = torch.empty((V, 1, H, W), dtype=torch.float32, device=dev)
+        opac = torch.empty((V, 1, H, W), dtype=torch.float32, device=dev)
+
+        check(L.ocrf_preprocess_forward(stream, C.byref(shape), ptr(means3D), ptr(scales), ptr(rotations),
+                                        ptr(cov3D_precomp), ptr(opacities), ptr(shs), ptr(cams),
+                                        C.c_float(cfg["scale_modifier"]), int(cfg["prefiltered"]), ptr(radii),
+                                        ptr(geom)), "ocrf_preprocess_forward")
+        capacity = cfg.get("pair_capacity")
+        if capacity is None:
+            # exact sizing: one 8-byte read-back per BATCH (the reference syncs once per view,
+            # rasterizer_impl.cu:281)
+            hdr = geom[ws.geom.header:ws.geom.header + 8].view(torch.int32).cpu()
+            num_pairs, err = int(hdr[0]) & 0xFFFFFFFF, int(hdr[1])
+            if err & 2:
+                raise _lib.OcrfError("Point is filtered although prefiltered is set. This shouldn't happen!")
+            capacity = num_pairs
+        else:
+            num_pairs = None
+        binl = _Workspaces.bin_layout(shape, capacity)
+        binning = torch.empty(binl.total, dtype=torch.uint8, device=dev)
+        check(L.ocrf_bin_forward(stream, C.byref(shape), C.c_uint64(capacity), ptr(radii), ptr(colors), int(use_sh),
+                                 ptr(geom), ptr(binning), ptr(image)), "ocrf_bin_forward")
+        check(L.ocrf_render_forward(stream, C.byref(shape), C.c_uint64(capacity), ptr(colors), int(use_sh), ptr(bg),
+                                    ptr(geom), ptr(binning), ptr(image), ptr(color), ptr(depth), ptr(opac)),
+              "ocrf_render_forward")
+
+        global _LAST_HEADER
+        _LAST_HEADER = geom[ws.geom.header:ws.geom.header + 8]
+        ctx.shape, ctx.cfg, ctx.capacity, ctx.use_sh = shape, cfg, capacity, use_sh
+        ctx.num_rendered = num_pairs
+        ctx.layouts = (ws.geom, binl, ws.image)
+        ctx.save_for_backward(means3D, shs, colors, scales, rotations, cov3D_precomp, cams, bg, radii, geom, binning,
+                              image)
+        ctx.mark_non_differentiable(radii, depth)  # no depth backward in the fork (its README:13)
+        return color, radii, depth, opac
+
+    @staticmethod
+    def backward(ctx, g_color, _g_radii, _g_depth, g_opac):
+        L = _lib.lib()
+        means3D, shs, colors, scales, rotations, cov3D_precomp, cams, bg, radii, geom, binning, image = ctx.saved_tensors
+        shape, cfg, use_sh = ctx.shape, ctx.cfg, ctx.use_sh
+        S, P, V, Cc = shape.S, shape.P, shape.V, shape.C
+        dev = means3D.device
+        stream = current_stream()
+        if g_color is None:
+            g_color = torch.zeros((V, Cc, shape.H, shape.W), dtype=torch.float32, device=dev)
+        g_color = g_color.contiguous()
+        g_opac = g_opac.contiguous() if g_opac is not None else None
+        ggrad = torch.zeros((V, P, _lib.OCRF_GGRAD_STRIDE), dtype=torch.float32, device=dev)
+        g_feat = torch.zeros((V, P, 3) if use_sh else (S, P, Cc), dtype=torch.float32, device=dev)
+        check(L.ocrf_render_backward(stream, C.byref(shape), C.c_uint64(ctx.capacity), ptr(colors), int(use_sh),
+                                     ptr(bg), ptr(geom), ptr(binning), ptr(image), ptr(g_color), ptr(g_opac),
+                                     ptr(ggrad), ptr(g_feat)), "ocrf_render_backward")
+        g_means3D = torch.empty_like(means3D)
+        g_means2D = torch.empty((V, P, 3), dtype=torch.float32, device=dev)
+        g_opacities = torch.empty((S, P, 1), dtype=torch.float32, device=dev)
+        has_cov = cov3D_precomp is not None
+        g_scales = None if has_cov else torch.empty_like(scales)
+        g_rots = None if has_cov else torch.empty_like(rotations)
+        g_cov = torch.empty_like(cov3D_precomp) if has_cov else None
+        g_shs = torch.empty_like(shs) if use_sh else None
+        check(L.ocrf_preprocess_backward(stream, C.byref(shape), ptr(means3D), ptr(scales), ptr(rotations),
+                                         ptr(cov3D_precomp), ptr(shs), ptr(cams), C.c_float(cfg["scale_modifier"]),
+                                         ptr(radii), ptr(geom), ptr(ggrad), ptr(g_feat) if use_sh else None,
+                                         ptr(g_means3D), ptr(g_means2D), ptr(g_opacities), ptr(g_scales), ptr(g_rots),
+                                         ptr(g_cov), ptr(g_shs)), "ocrf_preprocess_backward")
+        return (g_means3D, g_means2D, g_shs, None if use_sh else g_feat, g_opacities, g_scales, g_rots, g_cov, None,
+                None, None)
+
+
+_LAST_HEADER = None  # geom header of the most recent forward (for check_overflow in capacity mode)
+
+
+def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors_precomp=None, shs=None, scales=None,
+                 rotations=None, cov3D_precomp=None, means2D=None, scale_modifier=1.0, sh_degree=0, prefiltered=False,
+                 pair_capacity: Optional[int] = None):
+    """Render V = cams.shape[0] views of S = means3D.shape[0] samples in one launch sequence.
+
+    means3D [S,P,3]; opacities [S,P,1]; colors_precomp [S,P,C] or shs [S,P,M,3]; scales [S,P,3] and
+    rotations [S,P,4], or cov3D_precomp [S,P,6]; cams from `pack_cameras`, view v looks at sample
+    v // (V // S).  Returns (color [V,C,H,W], radii [V,P], depth [V,1,H,W], opacity [V,1,H,W]).
+    `means2D` ([V,P,3] zeros, requires_grad) receives dL/dmean2D as in the reference.
+    `pair_capacity`: if given, the binning workspace is sized for that many (tile, Gaussian) pairs
+    and NO host synchronisation happens (CUDA-graph friendly); an overflow renders background and
+    raises on the next `check_overflow`.
+    """
+    _require_cuda(means3D, "means3D")
+    if means3D.dim() != 3 or means3D.shape[-1] != 3:
+        raise Exception("means3D must have dimensions (samples, num_points, 3)")
+    S, P = means3D.shape[0], means3D.shape[1]
+    V = cams.shape[0]
+    if V % S != 0:
+        raise Exception("the number of views must be a multiple of the number of samples")
+    if (shs is None) == (colors_precomp is None):
+        raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+    if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+            ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+        raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+    f = lambda t: None if t is None else t.float().contiguous()  # noqa: E731
+    if means2D is None:
+        means2D = torch.zeros((V, P, 3), dtype=torch.float32, device=means3D.device)
+    cfg = dict(W=int(image_width), H=int(image_height), scale_modifier=float(scale_modifier), sh_degree=int(sh_degree),
+               prefiltered=bool(prefiltered), pair_capacity=pair_capacity)
+    if P == 0:
+        Cc = 3 if shs is not None else colors_precomp.shape[-1]
+        z = lambda c: torch.zeros((V, c, cfg["H"], cfg["W"]), dtype=torch.float32, device=means3D.device)  # noqa
+        return z(Cc), torch.zeros((V, 0), dtype=torch.int32, device=means3D.device), z(1), z(1)
+    return _RasterizeBatch.apply(f(means3D), means2D, f(shs), f(colors_precomp), f(opacities), f(scales), f(rotations),
+                                 f(cov3D_precomp), f(cams), f(bg), cfg)
+
+
+def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                        raster_settings, return_opacity=False):
+    """PKG:20-42: the single-view entry.  Empty tensors stand for absent inputs (PKG:197-207)."""
+    none_if_empty = lambda t: None if (t is None or t.numel() == 0) else t  # noqa: E731
+    sh, colors_precomp = none_if_empty(sh), none_if_empty(colors_precomp)
+    scales, rotations, cov3Ds_precomp = none_if_empty(scales), none_if_empty(rotations), none_if_empty(cov3Ds_precomp)
+    if means3D.dim() != 2 or means3D.shape[1] != 3:
+        raise Exception("means3D must have dimensions (num_points, 3)")  # rasterize_points.cu:57-59
+    st = raster_settings
+    P = means3D.shape[0]
+    H, W = int(st.image_height), int(st.image_width)
+    dev = means3D.device
+    if P == 0:  # rasterize_points.cu:81: zero image, nothing rendered
+        Cc = 3 if sh is not None else colors_precomp.shape[-1]
+        out = (torch.zeros((Cc, H, W), dtype=torch.float32, device=dev), torch.zeros((0,), dtype=torch.int32, device=dev),
+               torch.zeros((1, H, W), dtype=torch.float32, device=dev))
+        return out + ((torch.zeros((1, H, W), dtype=torch.float32, device=dev),) if return_opacity else ())
+    cams = pack_cameras(st.viewmatrix.to(dev), st.projmatrix.to(dev), st.campos.to(dev), st.tanfovx, st.tanfovy)
+    u = lambda t: None if t is None else t.unsqueeze(0)  # noqa: E731
+    m2d = means2D.unsqueeze(0) if means2D is not None else None
+    color, radii, depth, opac = render_batch(
+        u(means3D), u(opacities.reshape(P, 1)), cams, H, W, st.bg.to(dev), colors_precomp=u(colors_precomp),
+        shs=u(sh), scales=u(scales), rotations=u(rotations), cov3D_precomp=u(cov3Ds_precomp), means2D=m2d,
+        scale_modifier=st.scale_modifier, sh_degree=st.sh_degree, prefiltered=st.prefiltered)
+    out = (color[0], radii[0], depth[0])
+    return out + ((opac[0],) if return_opacity else ())
+
+
+class GaussianRasterizer(nn.Module):
+    """PKG:171-220."""
+
+    def __init__(self, raster_settings, return_opacity=False):
+        super().__init__()
+        self.raster_settings = raster_settings
+        self.return_opacity = return_opacity
+
+    def markVisible(self, positions):
+        # PKG:176-185 -> rasterizer_impl.cu:141-152
+        with torch.no_grad():
+            st = self.raster_settings
+            _require_cuda(positions, "positions")
+            positions = positions.float().contiguous()
+            P = positions.shape[0]
+            present = torch.zeros((P,), dtype=torch.bool, device=positions.device)
+            vm = st.viewmatrix.to(positions.device).float().contiguous()
+            pm = st.projmatrix.to(positions.device).float().contiguous()
+            check(_lib.lib().ocrf_mark_visible(current_stream(), P, ptr(positions), ptr(vm), ptr(pm), ptr(present)),
+                  "ocrf_mark_visible")
+        return present
+
+    def forward(self, means3D, means2D, opacities, shs=None, colors_precomp=None, scales=None, rotations=None,
+                cov3D_precomp=None):
+        if (shs is None and colors_precomp is None) or (shs is not None and colors_precomp is not None):
+            raise Exception('Please provide excatly one of either SHs or precomputed colors!')
+        if ((scales is None or rotations is None) and cov3D_precomp is None) or \
+                ((scales is not None or rotations is not None) and cov3D_precomp is not None):
+            raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                   self.raster_settings, return_opacity=self.return_opacity)
+
+
+def check_overflow():
+    """Raise if the last capacity-mode render overflowed its binning workspace (reads 8 bytes: synchronises)."""
+    if _LAST_HEADER is None:
+        return
+    hdr = _LAST_HEADER.view(torch.int32)[:2].cpu()
+    if int(hdr[1]) & 1:
+        raise _lib.OcrfError("binning workspace overflow: %d (tile, Gaussian) pairs exceed pair_capacity"
+                             % (int(hdr[0]) & 0xFFFFFFFF))
