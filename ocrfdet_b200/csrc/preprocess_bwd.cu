@@ -7,6 +7,11 @@
 // sample's cameras, accumulates dL/dmean3D, dL/dSigma and dL/dopacity in registers and writes each
 // output exactly once -- no atomics, deterministic, and the sum over views that a per-view API
 // leaves to autograd happens in registers.
+//
+// Precision: the conic -> covariance -> quaternion chain cancels heavily in float32 (the reference's
+// (denom - a*c) is -b*b; two float32 builds of the same formulas differ by ~1e-4 of the largest
+// gradient).  This kernel is P-proportional and B200 has FP64 to spare, so the chain runs in double:
+// ~2x the ALU time of a kernel that is bound by its 100 B/Gaussian of HBM traffic anyway.
 #include "common.cuh"
 #include "gaussian_math.cuh"
 
@@ -35,6 +40,22 @@ __device__ __forceinline__ void sh_basis_grad(int deg, float x, float y, float z
   g[15][0] = OCRF_SH_C3_6 * 3.f * (xx - yy); g[15][1] = OCRF_SH_C3_6 * -6.f * xy;
 }
 
+// Sigma = A^T diag(s^2) A in double (the forward's float value is only needed bit-exactly for the keys)
+__device__ __forceinline__ void cov3d_f64(const float* sc, float mod, float4 q, double* out) {
+  const double r = q.x, x = q.y, y = q.z, z = q.w;
+  const double A[3][3] = {{1. - 2. * (y * y + z * z), 2. * (x * y + r * z), 2. * (x * z - r * y)},
+                          {2. * (x * y - r * z), 1. - 2. * (x * x + z * z), 2. * (y * z + r * x)},
+                          {2. * (x * z + r * y), 2. * (y * z - r * x), 1. - 2. * (x * x + y * y)}};
+  double s2[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) { const double s = (double)mod * sc[k]; s2[k] = s * s; }
+  int e = 0;
+#pragma unroll
+  for (int i = 0; i < 3; i++)
+#pragma unroll
+    for (int j = i; j < 3; j++) out[e++] = s2[0] * A[0][i] * A[0][j] + s2[1] * A[1][i] * A[1][j] + s2[2] * A[2][i] * A[2][j];
+}
+
 __global__ void __launch_bounds__(256) preprocess_backward_kernel(
     OcrfShape sh, const float* __restrict__ means3D, const float* __restrict__ scales,
     const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp, const float* __restrict__ shs,
@@ -52,9 +73,9 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= sh.P) return;
   const size_t gi = (size_t)s * sh.P + i;
-  const float x = means3D[3 * gi], y = means3D[3 * gi + 1], z = means3D[3 * gi + 2];
+  const double x = means3D[3 * gi], y = means3D[3 * gi + 1], z = means3D[3 * gi + 2];
 
-  float c6[6];
+  double c6[6];
   float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
   float sc[3] = {0.f, 0.f, 0.f};
   if (cov3D_precomp != nullptr) {
@@ -63,20 +84,20 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
   } else {
     q = *reinterpret_cast<const float4*>(rotations + gi * 4);
     sc[0] = scales[3 * gi]; sc[1] = scales[3 * gi + 1]; sc[2] = scales[3 * gi + 2];
-    cov3d_from_scale_rot(sc[0], sc[1], sc[2], scale_modifier, q, c6);
+    cov3d_f64(sc, scale_modifier, q, c6);
   }
-  const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
+  const double S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
 
-  float gmean[3] = {0.f, 0.f, 0.f}, gcov[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  float gop = 0.f;
+  double gmean[3] = {0., 0., 0.}, gcov[6] = {0., 0., 0., 0., 0., 0.};
+  double gop = 0.;
   const int nb = (sh.sh_degree + 1) * (sh.sh_degree + 1);
   if (shs != nullptr)
-    for (int k = 0; k < sh.sh_M * 3; k++) dL_dshs[gi * (size_t)sh.sh_M * 3 + k] = 0.f;
+    for (int k = 0; k < sh.sh_M * 3; k++) dL_dshs[gi * (size_t)sh.sh_M * 3 + k] = 0.;
 
   for (int lv = 0; lv < vps; lv++) {
     const int v = s * vps + lv;
     const size_t o = (size_t)v * sh.P + i;
-    float g2x = 0.f, g2y = 0.f;
+    double g2x = 0., g2y = 0.;
     if (radii[o] > 0) {
       const Camera& cam = s_cams[lv];
       const float* vm = cam.view;
@@ -85,20 +106,20 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
       const float2 gb = *reinterpret_cast<const float2*>(ggrad + o * OCRF_GGRAD_STRIDE + 4);  // dC dOp
       g2x = ga.x; g2y = ga.y;
       gop += gb.y;
-      const float fy = sh.H / (2.0f * cam.tanfovy), fx = sh.W / (2.0f * cam.tanfovx);
+      const double fy = sh.H / (2.0 * cam.tanfovy), fx = sh.W / (2.0 * cam.tanfovx);
       // ---- conic -> cov2D -> cov3D and view-space mean ----
-      float t[3];
+      double t[3];
 #pragma unroll
       for (int r = 0; r < 3; r++) t[r] = vm[r] * x + vm[4 + r] * y + vm[8 + r] * z + vm[12 + r];
-      const float limx = 1.3f * cam.tanfovx, limy = 1.3f * cam.tanfovy;
-      const float txtz = t[0] / t[2], tytz = t[1] / t[2];
-      t[0] = fminf(limx, fmaxf(-limx, txtz)) * t[2];
-      t[1] = fminf(limy, fmaxf(-limy, tytz)) * t[2];
-      const float xmul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
-      const float ymul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
-      const float itz = 1.f / t[2], itz2 = itz * itz, itz3 = itz2 * itz;
-      const float J00 = fx * itz, J11 = fy * itz, J02 = -(fx * t[0]) * itz2, J12 = -(fy * t[1]) * itz2;
-      float T0[3], T1[3], ST0[3], ST1[3];
+      const double limx = (double)1.3f * cam.tanfovx, limy = (double)1.3f * cam.tanfovy;
+      const double txtz = t[0] / t[2], tytz = t[1] / t[2];
+      t[0] = fmin(limx, fmax(-limx, txtz)) * t[2];
+      t[1] = fmin(limy, fmax(-limy, tytz)) * t[2];
+      const double xmul = (txtz < -limx || txtz > limx) ? 0. : 1.;
+      const double ymul = (tytz < -limy || tytz > limy) ? 0. : 1.;
+      const double itz = 1. / t[2], itz2 = itz * itz, itz3 = itz2 * itz;
+      const double J00 = fx * itz, J11 = fy * itz, J02 = -(fx * t[0]) * itz2, J12 = -(fy * t[1]) * itz2;
+      double T0[3], T1[3], ST0[3], ST1[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         T0[k] = vm[4 * k] * J00 + vm[4 * k + 2] * J02;
@@ -109,14 +130,14 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
         ST0[k] = S[k][0] * T0[0] + S[k][1] * T0[1] + S[k][2] * T0[2];
         ST1[k] = S[k][0] * T1[0] + S[k][1] * T1[1] + S[k][2] * T1[2];
       }
-      const float a = (T0[0] * ST0[0] + T0[1] * ST0[1] + T0[2] * ST0[2]) + 0.3f;
-      const float b = T0[0] * ST1[0] + T0[1] * ST1[1] + T0[2] * ST1[2];
-      const float c = (T1[0] * ST1[0] + T1[1] * ST1[1] + T1[2] * ST1[2]) + 0.3f;
-      const float gA = ga.z, gB = ga.w, gC = gb.x;
-      const float denom = a * c - b * b;
-      const float d2i = 1.0f / ((denom * denom) + 0.0000001f);
-      float da = 0.f, db = 0.f, dc = 0.f;
-      if (d2i != 0.f) {
+      const double a = (T0[0] * ST0[0] + T0[1] * ST0[1] + T0[2] * ST0[2]) + (double)0.3f;
+      const double b = T0[0] * ST1[0] + T0[1] * ST1[1] + T0[2] * ST1[2];
+      const double c = (T1[0] * ST1[0] + T1[1] * ST1[1] + T1[2] * ST1[2]) + (double)0.3f;
+      const double gA = ga.z, gB = ga.w, gC = gb.x;
+      const double denom = a * c - b * b;
+      const double d2i = 1.0 / ((denom * denom) + (double)0.0000001f);
+      double da = 0., db = 0., dc = 0.;
+      if (d2i != 0.) {
         da = d2i * (-c * c * gA + 2 * b * c * gB + (denom - a * c) * gC);
         dc = d2i * (-a * a * gC + 2 * a * b * gB + (denom - a * c) * gA);
         db = d2i * 2 * (b * c * gA - (denom + 2 * b * b) * gB + a * b * gC);
@@ -127,52 +148,56 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
         gcov[2] += 2 * T0[0] * T0[2] * da + (T0[0] * T1[2] + T0[2] * T1[0]) * db + 2 * T1[0] * T1[2] * dc;
         gcov[4] += 2 * T0[2] * T0[1] * da + (T0[1] * T1[2] + T0[2] * T1[1]) * db + 2 * T1[1] * T1[2] * dc;
       }
-      float dT0[3], dT1[3];
+      double dT0[3], dT1[3];
 #pragma unroll
       for (int k = 0; k < 3; k++) {
         dT0[k] = 2 * ST0[k] * da + ST1[k] * db;
         dT1[k] = 2 * ST1[k] * dc + ST0[k] * db;
       }
-      const float dJ00 = vm[0] * dT0[0] + vm[4] * dT0[1] + vm[8] * dT0[2];
-      const float dJ02 = vm[2] * dT0[0] + vm[6] * dT0[1] + vm[10] * dT0[2];
-      const float dJ11 = vm[1] * dT1[0] + vm[5] * dT1[1] + vm[9] * dT1[2];
-      const float dJ12 = vm[2] * dT1[0] + vm[6] * dT1[1] + vm[10] * dT1[2];
-      const float dtx = xmul * -fx * itz2 * dJ02;
-      const float dty = ymul * -fy * itz2 * dJ12;
-      const float dtz = -fx * itz2 * dJ00 - fy * itz2 * dJ11 + (2 * fx * t[0]) * itz3 * dJ02 + (2 * fy * t[1]) * itz3 * dJ12;
+      const double dJ00 = vm[0] * dT0[0] + vm[4] * dT0[1] + vm[8] * dT0[2];
+      const double dJ02 = vm[2] * dT0[0] + vm[6] * dT0[1] + vm[10] * dT0[2];
+      const double dJ11 = vm[1] * dT1[0] + vm[5] * dT1[1] + vm[9] * dT1[2];
+      const double dJ12 = vm[2] * dT1[0] + vm[6] * dT1[1] + vm[10] * dT1[2];
+      const double dtx = xmul * -fx * itz2 * dJ02;
+      const double dty = ymul * -fy * itz2 * dJ12;
+      const double dtz = -fx * itz2 * dJ00 - fy * itz2 * dJ11 + (2 * fx * t[0]) * itz3 * dJ02 + (2 * fy * t[1]) * itz3 * dJ12;
 #pragma unroll
       for (int j = 0; j < 3; j++) gmean[j] += vm[4 * j] * dtx + vm[4 * j + 1] * dty + vm[4 * j + 2] * dtz;
       // ---- screen-space mean -> 3D mean ----
-      const float hw = pm[3] * x + pm[7] * y + pm[11] * z + pm[15];
-      const float mw = 1.0f / (hw + 0.0000001f);
-      const float mul1 = (pm[0] * x + pm[4] * y + pm[8] * z + pm[12]) * mw * mw;
-      const float mul2 = (pm[1] * x + pm[5] * y + pm[9] * z + pm[13]) * mw * mw;
+      const double hw = pm[3] * x + pm[7] * y + pm[11] * z + pm[15];
+      const double mw = 1.0 / (hw + (double)0.0000001f);
+      const double mul1 = (pm[0] * x + pm[4] * y + pm[8] * z + pm[12]) * mw * mw;
+      const double mul2 = (pm[1] * x + pm[5] * y + pm[9] * z + pm[13]) * mw * mw;
 #pragma unroll
       for (int j = 0; j < 3; j++)
         gmean[j] += (pm[4 * j] * mw - pm[4 * j + 3] * mul1) * g2x + (pm[4 * j + 1] * mw - pm[4 * j + 3] * mul2) * g2y;
       // ---- SH colours (view dependent) ----
       if (shs != nullptr) {
-        const float d0[3] = {x - cam.campos[0], y - cam.campos[1], z - cam.campos[2]};
-        const float s2 = d0[0] * d0[0] + d0[1] * d0[1] + d0[2] * d0[2];
-        const float len = sqrtf(s2);
-        const float dir[3] = {d0[0] / len, d0[1] / len, d0[2] / len};
-        float bas[16], bg3[16][3];
-        sh_basis(sh.sh_degree, dir[0], dir[1], dir[2], bas);
-        sh_basis_grad(sh.sh_degree, dir[0], dir[1], dir[2], bg3);
-        float grgb[3], ddir[3] = {0.f, 0.f, 0.f};
+        const double d0[3] = {x - cam.campos[0], y - cam.campos[1], z - cam.campos[2]};
+        const double s2 = d0[0] * d0[0] + d0[1] * d0[1] + d0[2] * d0[2];
+        const double len = sqrt(s2);
+        const double dir[3] = {d0[0] / len, d0[1] / len, d0[2] / len};
+        double bas[16], bg3[16][3];
+        { float bf[16]; sh_basis(sh.sh_degree, (float)dir[0], (float)dir[1], (float)dir[2], bf);
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) grgb[ch] = clamped[o * 3 + ch] ? 0.f : dL_dcolors_view[o * 3 + ch];
+          for (int k = 0; k < 16; k++) bas[k] = bf[k]; }
+        { float gf[16][3]; sh_basis_grad(sh.sh_degree, (float)dir[0], (float)dir[1], (float)dir[2], gf);
+#pragma unroll
+          for (int k = 0; k < 16; k++) { bg3[k][0] = gf[k][0]; bg3[k][1] = gf[k][1]; bg3[k][2] = gf[k][2]; } }
+        double grgb[3], ddir[3] = {0., 0., 0.};
+#pragma unroll
+        for (int ch = 0; ch < 3; ch++) grgb[ch] = clamped[o * 3 + ch] ? 0. : dL_dcolors_view[o * 3 + ch];
         const float* coef = shs + gi * (size_t)sh.sh_M * 3;
         float* gsh = dL_dshs + gi * (size_t)sh.sh_M * 3;
         for (int k = 0; k < nb; k++)
 #pragma unroll
           for (int ch = 0; ch < 3; ch++) {
             gsh[3 * k + ch] += bas[k] * grgb[ch];
-            const float cg = coef[3 * k + ch] * grgb[ch];
+            const double cg = coef[3 * k + ch] * grgb[ch];
             ddir[0] += bg3[k][0] * cg; ddir[1] += bg3[k][1] * cg; ddir[2] += bg3[k][2] * cg;
           }
-        const float inv32 = 1.0f / sqrtf(s2 * s2 * s2);
-        const float dotv = d0[0] * ddir[0] + d0[1] * ddir[1] + d0[2] * ddir[2];
+        const double inv32 = 1.0 / sqrt(s2 * s2 * s2);
+        const double dotv = d0[0] * ddir[0] + d0[1] * ddir[1] + d0[2] * ddir[2];
 #pragma unroll
         for (int ax = 0; ax < 3; ax++) gmean[ax] += (s2 * ddir[ax] - d0[ax] * dotv) * inv32;
       }
@@ -180,7 +205,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
     if (dL_dmeans2D) {
       dL_dmeans2D[o * 3] = g2x;
       dL_dmeans2D[o * 3 + 1] = g2y;
-      dL_dmeans2D[o * 3 + 2] = 0.f;
+      dL_dmeans2D[o * 3 + 2] = 0.;
     }
   }
 
@@ -194,31 +219,31 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
     return;
   }
   // ---- cov3D -> scale, quaternion (no normalisation Jacobian, backward.cu:340) ----
-  const float r = q.x, qx = q.y, qy = q.z, qz = q.w;
-  const float Rg[3][3] = {{1.f - 2.f * (qy * qy + qz * qz), 2.f * (qx * qy + r * qz), 2.f * (qx * qz - r * qy)},
-                          {2.f * (qx * qy - r * qz), 1.f - 2.f * (qx * qx + qz * qz), 2.f * (qy * qz + r * qx)},
-                          {2.f * (qx * qz + r * qy), 2.f * (qy * qz - r * qx), 1.f - 2.f * (qx * qx + qy * qy)}};
-  const float sm[3] = {scale_modifier * sc[0], scale_modifier * sc[1], scale_modifier * sc[2]};
-  const float Gs[3][3] = {{gcov[0], 0.5f * gcov[1], 0.5f * gcov[2]},
-                          {0.5f * gcov[1], gcov[3], 0.5f * gcov[4]},
-                          {0.5f * gcov[2], 0.5f * gcov[4], gcov[5]}};
-  float D[3][3];
+  const double r = q.x, qx = q.y, qy = q.z, qz = q.w;
+  const double Rg[3][3] = {{1. - 2. * (qy * qy + qz * qz), 2. * (qx * qy + r * qz), 2. * (qx * qz - r * qy)},
+                          {2. * (qx * qy - r * qz), 1. - 2. * (qx * qx + qz * qz), 2. * (qy * qz + r * qx)},
+                          {2. * (qx * qz + r * qy), 2. * (qy * qz - r * qx), 1. - 2. * (qx * qx + qy * qy)}};
+  const double sm[3] = {(double)scale_modifier * sc[0], (double)scale_modifier * sc[1], (double)scale_modifier * sc[2]};
+  const double Gs[3][3] = {{gcov[0], 0.5 * gcov[1], 0.5 * gcov[2]},
+                          {0.5 * gcov[1], gcov[3], 0.5 * gcov[4]},
+                          {0.5 * gcov[2], 0.5 * gcov[4], gcov[5]}};
+  double D[3][3];
 #pragma unroll
   for (int p = 0; p < 3; p++) {
-    float ds = 0.f;
+    double ds = 0.;
 #pragma unroll
     for (int c2 = 0; c2 < 3; c2++) {
-      const float dM = 2.0f * sm[p] * (Rg[p][0] * Gs[0][c2] + Rg[p][1] * Gs[1][c2] + Rg[p][2] * Gs[2][c2]);
+      const double dM = 2.0 * sm[p] * (Rg[p][0] * Gs[0][c2] + Rg[p][1] * Gs[1][c2] + Rg[p][2] * Gs[2][c2]);
       ds += Rg[p][c2] * dM;
       D[p][c2] = sm[p] * dM;
     }
     dL_dscales[gi * 3 + p] = ds;
   }
   float4 gq;
-  gq.x = 2 * qz * (D[0][1] - D[1][0]) + 2 * qy * (D[2][0] - D[0][2]) + 2 * qx * (D[1][2] - D[2][1]);
-  gq.y = 2 * qy * (D[1][0] + D[0][1]) + 2 * qz * (D[2][0] + D[0][2]) + 2 * r * (D[1][2] - D[2][1]) - 4 * qx * (D[2][2] + D[1][1]);
-  gq.z = 2 * qx * (D[1][0] + D[0][1]) + 2 * r * (D[2][0] - D[0][2]) + 2 * qz * (D[1][2] + D[2][1]) - 4 * qy * (D[2][2] + D[0][0]);
-  gq.w = 2 * r * (D[0][1] - D[1][0]) + 2 * qx * (D[2][0] + D[0][2]) + 2 * qy * (D[1][2] + D[2][1]) - 4 * qz * (D[1][1] + D[0][0]);
+  gq.x = (float)(2 * qz * (D[0][1] - D[1][0]) + 2 * qy * (D[2][0] - D[0][2]) + 2 * qx * (D[1][2] - D[2][1]));
+  gq.y = (float)(2 * qy * (D[1][0] + D[0][1]) + 2 * qz * (D[2][0] + D[0][2]) + 2 * r * (D[1][2] - D[2][1]) - 4 * qx * (D[2][2] + D[1][1]));
+  gq.z = (float)(2 * qx * (D[1][0] + D[0][1]) + 2 * r * (D[2][0] - D[0][2]) + 2 * qz * (D[1][2] + D[2][1]) - 4 * qy * (D[2][2] + D[0][0]));
+  gq.w = (float)(2 * r * (D[0][1] - D[1][0]) + 2 * qx * (D[2][0] + D[0][2]) + 2 * qy * (D[1][2] + D[2][1]) - 4 * qz * (D[1][1] + D[0][0]));
   *reinterpret_cast<float4*>(dL_drotations + gi * 4) = gq;
 }
 

@@ -131,8 +131,11 @@ class _RasterizeBatch(torch.autograd.Function):
                                     ptr(geom), ptr(binning), ptr(image), ptr(color), ptr(depth), ptr(opac)),
               "ocrf_render_forward")
 
-        global _LAST_HEADER
+        global _LAST_HEADER, _LAST_STATE
         _LAST_HEADER = geom[ws.geom.header:ws.geom.header + 8]
+        if KEEP_STATE:
+            _LAST_STATE = dict(shape=shape, layouts=(ws.geom, binl, ws.image), geom=geom, binning=binning, image=image,
+                               radii=radii, capacity=capacity)
         ctx.shape, ctx.cfg, ctx.capacity, ctx.use_sh = shape, cfg, capacity, use_sh
         ctx.num_rendered = num_pairs
         ctx.layouts = (ws.geom, binl, ws.image)
@@ -176,6 +179,45 @@ class _RasterizeBatch(torch.autograd.Function):
 
 
 _LAST_HEADER = None  # geom header of the most recent forward (for check_overflow in capacity mode)
+KEEP_STATE = False   # tests / bench statistics: keep the workspaces of the most recent forward alive
+_LAST_STATE = None
+
+
+def last_state():
+    """Typed views into the workspaces of the most recent forward (requires KEEP_STATE = True).
+
+    Mirrors what the reference keeps in its geomBuffer / binningBuffer / imgBuffer blobs (PKG:97).
+    Reading `num_pairs` synchronises.
+    """
+    st = _LAST_STATE
+    if st is None:
+        raise _lib.OcrfError("no state kept: set ocrfdet_b200.rasterizer.KEEP_STATE = True before rendering")
+    shape, (g, b, im) = st["shape"], st["layouts"]
+    geom, binning, image = st["geom"], st["binning"], st["image"]
+    V, P, W, H = shape.V, shape.P, shape.W, shape.H
+    n = V * P
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+
+    def view(buf, off, count, dtype, *dims):
+        nbytes = count * torch.empty((), dtype=dtype).element_size()
+        return buf[off:off + nbytes].view(dtype).view(*dims)
+
+    hdr = view(geom, g.header, 2, torch.int32, 2).cpu()
+    N = int(hdr[0]) & 0xFFFFFFFF
+    if N > st["capacity"]:
+        N = 0
+    out = dict(
+        num_pairs=N, error=int(hdr[1]), radii=st["radii"],
+        depths=view(geom, g.depths, n, torch.float32, V, P), xy=view(geom, g.xy, 2 * n, torch.float32, V, P, 2),
+        conic_opacity=view(geom, g.conic_opacity, 4 * n, torch.float32, V, P, 4),
+        tiles_touched=view(geom, g.tiles_touched, n, torch.int32, V, P),
+        offsets=view(geom, g.offsets, n, torch.int32, V * P),
+        keys=view(binning, b.keys, N, torch.int64, N), point_list=view(binning, b.point_list, N, torch.int32, N),
+        ranges=view(image, im.ranges, 2 * V * tiles, torch.int32, V, tiles, 2),
+        final_T=view(image, im.final_T, V * H * W, torch.float32, V, H, W),
+        n_contrib=view(image, im.n_contrib, V * H * W, torch.int32, V, H, W),
+        max_contrib=view(image, im.max_contrib, V * tiles, torch.int32, V, tiles))
+    return out
 
 
 def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors_precomp=None, shs=None, scales=None,
@@ -220,6 +262,7 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
                         raster_settings, return_opacity=False):
     """PKG:20-42: the single-view entry.  Empty tensors stand for absent inputs (PKG:197-207)."""
     none_if_empty = lambda t: None if (t is None or t.numel() == 0) else t  # noqa: E731
+    channels = colors_precomp.shape[-1] if (colors_precomp is not None and colors_precomp.dim() == 2) else 3
     sh, colors_precomp = none_if_empty(sh), none_if_empty(colors_precomp)
     scales, rotations, cov3Ds_precomp = none_if_empty(scales), none_if_empty(rotations), none_if_empty(cov3Ds_precomp)
     if means3D.dim() != 2 or means3D.shape[1] != 3:
@@ -229,7 +272,7 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
     H, W = int(st.image_height), int(st.image_width)
     dev = means3D.device
     if P == 0:  # rasterize_points.cu:81: zero image, nothing rendered
-        Cc = 3 if sh is not None else colors_precomp.shape[-1]
+        Cc = channels
         out = (torch.zeros((Cc, H, W), dtype=torch.float32, device=dev), torch.zeros((0,), dtype=torch.int32, device=dev),
                torch.zeros((1, H, W), dtype=torch.float32, device=dev))
         return out + ((torch.zeros((1, H, W), dtype=torch.float32, device=dev),) if return_opacity else ())

@@ -481,140 +481,31 @@ void ocrf_oracle_render_backward(int P, int W, int H, int C, const uint32_t* ran
  * Any of dL_dscales/dL_drots (when cov3D_precomp is given) or dL_dcov3D/dL_dshs may be NULL.
  * Gaussians with radii <= 0 receive zeros.
  * ------------------------------------------------------------------------------------------ */
-void ocrf_oracle_preprocess_backward(int P, int sh_deg, int sh_M, const float* means, const int32_t* radii,
-                                     const float* shs, const uint8_t* clamped, const float* scales,
-                                     float scale_modifier, const float* rots, const float* cov3D, const float* view,
-                                     const float* proj, const float* campos, int W, int H, float tanfovx,
-                                     float tanfovy, const float* dL_dmean2D, const float* dL_dconic,
-                                     const float* dL_dcolor, float* dL_dmeans, float* dL_dcov3D, float* dL_dscales,
-                                     float* dL_drots, float* dL_dshs) {
-  const float fy = H / (2.0f * tanfovy), fx = W / (2.0f * tanfovx);
-  for (int i = 0; i < P; i++) {
-    float gmean[3] = {0, 0, 0}, gcov[6] = {0, 0, 0, 0, 0, 0};
-    if (dL_dscales) dL_dscales[3 * i] = dL_dscales[3 * i + 1] = dL_dscales[3 * i + 2] = 0.f;
-    if (dL_drots) dL_drots[4 * i] = dL_drots[4 * i + 1] = dL_drots[4 * i + 2] = dL_drots[4 * i + 3] = 0.f;
-    if (dL_dshs) memset(dL_dshs + (size_t)i * sh_M * 3, 0, sizeof(float) * (size_t)sh_M * 3);
-    if (radii[i] > 0) {
-      const float x = means[3 * i], y = means[3 * i + 1], z = means[3 * i + 2];
-      const float* c6 = cov3D + 6 * i;
-      /* --- conic -> 2D covariance -> 3D covariance and view-space mean (backward.cu:144-274) --- */
-      float t[3];
-      for (int r = 0; r < 3; r++) t[r] = view[r] * x + view[4 + r] * y + view[8 + r] * z + view[12 + r];
-      const float limx = 1.3f * tanfovx, limy = 1.3f * tanfovy;
-      const float txtz = t[0] / t[2], tytz = t[1] / t[2];
-      t[0] = fminf(limx, fmaxf(-limx, txtz)) * t[2];
-      t[1] = fminf(limy, fmaxf(-limy, tytz)) * t[2];
-      const float xmul = (txtz < -limx || txtz > limx) ? 0.f : 1.f;
-      const float ymul = (tytz < -limy || tytz > limy) ? 0.f : 1.f;
-      const float J00 = fx / t[2], J11 = fy / t[2];
-      const float J02 = -(fx * t[0]) / (t[2] * t[2]), J12 = -(fy * t[1]) / (t[2] * t[2]);
-      float T0[3], T1[3];
-      for (int k = 0; k < 3; k++) {
-        T0[k] = view[4 * k] * J00 + view[4 * k + 2] * J02;
-        T1[k] = view[4 * k + 1] * J11 + view[4 * k + 2] * J12;
-      }
-      const float S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
-      float ST0[3], ST1[3]; /* S . T_i */
-      for (int k = 0; k < 3; k++) {
-        ST0[k] = S[k][0] * T0[0] + S[k][1] * T0[1] + S[k][2] * T0[2];
-        ST1[k] = S[k][0] * T1[0] + S[k][1] * T1[1] + S[k][2] * T1[2];
-      }
-      const float a = (T0[0] * ST0[0] + T0[1] * ST0[1] + T0[2] * ST0[2]) + 0.3f;
-      const float b = T0[0] * ST1[0] + T0[1] * ST1[1] + T0[2] * ST1[2];
-      const float c = (T1[0] * ST1[0] + T1[1] * ST1[1] + T1[2] * ST1[2]) + 0.3f;
-      const float gA = dL_dconic[3 * i], gB = dL_dconic[3 * i + 1], gC = dL_dconic[3 * i + 2];
-      const float denom = a * c - b * b;
-      const float d2i = 1.0f / ((denom * denom) + 0.0000001f);
-      float da = 0.f, db = 0.f, dc = 0.f;
-      if (d2i != 0.f) {
-        da = d2i * (-c * c * gA + 2 * b * c * gB + (denom - a * c) * gC);
-        dc = d2i * (-a * a * gC + 2 * a * b * gB + (denom - a * c) * gA);
-        db = d2i * 2 * (b * c * gA - (denom + 2 * b * b) * gB + a * b * gC);
-        static const int kk[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
-        for (int e = 0; e < 6; e++) {
-          const int p = kk[e][0], q = kk[e][1];
-          if (p == q) gcov[e] = T0[p] * T0[p] * da + T0[p] * T1[p] * db + T1[p] * T1[p] * dc;
-          else gcov[e] = 2 * T0[p] * T0[q] * da + (T0[p] * T1[q] + T0[q] * T1[p]) * db + 2 * T1[p] * T1[q] * dc;
-        }
-      }
-      float dT0[3], dT1[3];
-      for (int k = 0; k < 3; k++) {
-        dT0[k] = 2 * ST0[k] * da + ST1[k] * db;
-        dT1[k] = 2 * ST1[k] * dc + ST0[k] * db;
-      }
-      const float dJ00 = view[0] * dT0[0] + view[4] * dT0[1] + view[8] * dT0[2];
-      const float dJ02 = view[2] * dT0[0] + view[6] * dT0[1] + view[10] * dT0[2];
-      const float dJ11 = view[1] * dT1[0] + view[5] * dT1[1] + view[9] * dT1[2];
-      const float dJ12 = view[2] * dT1[0] + view[6] * dT1[1] + view[10] * dT1[2];
-      const float tz = 1.f / t[2], tz2 = tz * tz, tz3 = tz2 * tz;
-      const float dtx = xmul * -fx * tz2 * dJ02;
-      const float dty = ymul * -fy * tz2 * dJ12;
-      const float dtz = -fx * tz2 * dJ00 - fy * tz2 * dJ11 + (2 * fx * t[0]) * tz3 * dJ02 + (2 * fy * t[1]) * tz3 * dJ12;
-      for (int j = 0; j < 3; j++) gmean[j] = view[4 * j] * dtx + view[4 * j + 1] * dty + view[4 * j + 2] * dtz;
-      /* --- screen-space mean -> 3D mean (backward.cu:370-387) --- */
-      const float hw = proj[3] * x + proj[7] * y + proj[11] * z + proj[15];
-      const float mw = 1.0f / (hw + 0.0000001f);
-      const float mul1 = (proj[0] * x + proj[4] * y + proj[8] * z + proj[12]) * mw * mw;
-      const float mul2 = (proj[1] * x + proj[5] * y + proj[9] * z + proj[13]) * mw * mw;
-      const float g2x = dL_dmean2D[2 * i], g2y = dL_dmean2D[2 * i + 1];
-      for (int j = 0; j < 3; j++)
-        gmean[j] += (proj[4 * j] * mw - proj[4 * j + 3] * mul1) * g2x + (proj[4 * j + 1] * mw - proj[4 * j + 3] * mul2) * g2y;
-      /* --- SH colours (backward.cu:20-139) --- */
-      if (shs) {
-        const float d0[3] = {x - campos[0], y - campos[1], z - campos[2]};
-        const float len = sqrtf(d0[0] * d0[0] + d0[1] * d0[1] + d0[2] * d0[2]);
-        const float d[3] = {d0[0] / len, d0[1] / len, d0[2] / len};
-        float bas[16], bg3[16][3];
-        sh_basis(sh_deg, d[0], d[1], d[2], bas);
-        sh_basis_grad(sh_deg, d[0], d[1], d[2], bg3);
-        const int n = sh_count(sh_deg);
-        float grgb[3], ddir[3] = {0, 0, 0};
-        for (int ch = 0; ch < 3; ch++) grgb[ch] = clamped[3 * i + ch] ? 0.f : dL_dcolor[3 * i + ch];
-        for (int k = 0; k < n; k++)
-          for (int ch = 0; ch < 3; ch++) {
-            const float coef = shs[((size_t)i * sh_M + k) * 3 + ch];
-            dL_dshs[((size_t)i * sh_M + k) * 3 + ch] = bas[k] * grgb[ch];
-            for (int ax = 0; ax < 3; ax++) ddir[ax] += bg3[k][ax] * coef * grgb[ch];
-          }
-        /* through the normalisation dir = d0/|d0| (auxiliary.h:107-117) */
-        const float s2 = d0[0] * d0[0] + d0[1] * d0[1] + d0[2] * d0[2];
-        const float inv32 = 1.0f / sqrtf(s2 * s2 * s2);
-        const float dotv = d0[0] * ddir[0] + d0[1] * ddir[1] + d0[2] * ddir[2];
-        for (int ax = 0; ax < 3; ax++) gmean[ax] += (s2 * ddir[ax] - d0[ax] * dotv) * inv32;
-      }
-      /* --- 3D covariance -> scale and quaternion (backward.cu:278-341) --- */
-      if (scales && dL_dscales && dL_drots) {
-        const float r = rots[4 * i], qx = rots[4 * i + 1], qy = rots[4 * i + 2], qz = rots[4 * i + 3];
-        /* Rg[row][col]: the rotation as the reference lays it out (its glm matrix read row = inner index) */
-        const float Rg[3][3] = {
-            {1.f - 2.f * (qy * qy + qz * qz), 2.f * (qx * qy + r * qz), 2.f * (qx * qz - r * qy)},
-            {2.f * (qx * qy - r * qz), 1.f - 2.f * (qx * qx + qz * qz), 2.f * (qy * qz + r * qx)},
-            {2.f * (qx * qz + r * qy), 2.f * (qy * qz - r * qx), 1.f - 2.f * (qx * qx + qy * qy)}};
-        const float s[3] = {scale_modifier * scales[3 * i], scale_modifier * scales[3 * i + 1], scale_modifier * scales[3 * i + 2]};
-        /* Mg = diag(s) Rg ; Sigma = Mg^T Mg ; dL/dMg = 2 Mg Gs with Gs the symmetric gradient */
-        const float Gs[3][3] = {{gcov[0], 0.5f * gcov[1], 0.5f * gcov[2]},
-                                {0.5f * gcov[1], gcov[3], 0.5f * gcov[4]},
-                                {0.5f * gcov[2], 0.5f * gcov[4], gcov[5]}};
-        float dM[3][3];
-        for (int p = 0; p < 3; p++)
-          for (int q = 0; q < 3; q++)
-            dM[p][q] = 2.0f * (s[p] * Rg[p][0] * Gs[0][q] + s[p] * Rg[p][1] * Gs[1][q] + s[p] * Rg[p][2] * Gs[2][q]);
-        float D[3][3]; /* dL/dRg */
-        for (int p = 0; p < 3; p++) {
-          dL_dscales[3 * i + p] = Rg[p][0] * dM[p][0] + Rg[p][1] * dM[p][1] + Rg[p][2] * dM[p][2];
-          for (int q = 0; q < 3; q++) D[p][q] = s[p] * dM[p][q];
-        }
-        dL_drots[4 * i + 0] = 2 * qz * (D[0][1] - D[1][0]) + 2 * qy * (D[2][0] - D[0][2]) + 2 * qx * (D[1][2] - D[2][1]);
-        dL_drots[4 * i + 1] = 2 * qy * (D[1][0] + D[0][1]) + 2 * qz * (D[2][0] + D[0][2]) + 2 * r * (D[1][2] - D[2][1]) - 4 * qx * (D[2][2] + D[1][1]);
-        dL_drots[4 * i + 2] = 2 * qx * (D[1][0] + D[0][1]) + 2 * r * (D[2][0] - D[0][2]) + 2 * qz * (D[1][2] + D[2][1]) - 4 * qy * (D[2][2] + D[0][0]);
-        dL_drots[4 * i + 3] = 2 * r * (D[0][1] - D[1][0]) + 2 * qx * (D[2][0] + D[0][2]) + 2 * qy * (D[1][2] + D[2][1]) - 4 * qz * (D[1][1] + D[0][0]);
-      }
-    }
-    for (int j = 0; j < 3; j++) dL_dmeans[3 * i + j] = gmean[j];
-    if (dL_dcov3D)
-      for (int e = 0; e < 6; e++) dL_dcov3D[6 * i + e] = gcov[e];
-  }
-}
+#define REAL float
+#define RMIN fminf
+#define RMAX fmaxf
+#define RSQRT sqrtf
+#define OCRF_PB_NAME ocrf_oracle_preprocess_backward
+#include "preprocess_backward.inc"
+#undef REAL
+#undef RMIN
+#undef RMAX
+#undef RSQRT
+#undef OCRF_PB_NAME
+/* Same chain evaluated in double from double screen-space gradients: the conic -> covariance ->
+ * quaternion chain cancels heavily in float32 (e.g. (denom - a*c) is -b*b), so two float32 builds of
+ * the reference formulas differ from each other by ~1e-4 of the largest gradient. */
+#define REAL double
+#define RMIN fmin
+#define RMAX fmax
+#define RSQRT sqrt
+#define OCRF_PB_NAME ocrf_oracle_preprocess_backward_f64
+#include "preprocess_backward.inc"
+#undef REAL
+#undef RMIN
+#undef RMAX
+#undef RSQRT
+#undef OCRF_PB_NAME
 
 /* ------------------------------------------------------------------------------------------
  * Stage 5: opacity mask of the HOA lift (view_transformer_ocrf.py:230-242 `ObatinOpacityMask`,

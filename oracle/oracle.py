@@ -154,21 +154,26 @@ def render_backward(P, W, H, ranges, point_list, xy, conic_opacity, colors, bg, 
 
 def preprocess_backward(means, radii, cov3D, view, proj, W, H, tanfovx, tanfovy, dL_dmean2D, dL_dconic, scales=None,
                         rots=None, scale_modifier=1.0, shs=None, sh_degree=0, clamped=None, campos=None,
-                        dL_dcolor=None):
+                        dL_dcolor=None, f64=False):
+    """f64=False: float32 arithmetic like the reference.  f64=True: the same chain in double from double
+    screen-space gradients (the well-conditioned value both float32 implementations are judged against)."""
     means = _f32(means)
     P = means.shape[0]
     scales, rots, shs = _f32(scales), _f32(rots), _f32(shs)
     sh_M = 0 if shs is None else shs.shape[1]
     campos = _f32(campos if campos is not None else np.zeros(3))
-    g = dict(means=np.zeros((P, 3), np.float32), cov3D=np.zeros((P, 6), np.float32),
-             scales=np.zeros((P, 3), np.float32), rots=np.zeros((P, 4), np.float32),
-             shs=None if shs is None else np.zeros_like(shs))
-    lib().ocrf_oracle_preprocess_backward(
+    rt = np.float64 if f64 else np.float32
+    _f32g = (lambda a: None if a is None else np.ascontiguousarray(np.asarray(a, dtype=rt)))
+    g = dict(means=np.zeros((P, 3), rt), cov3D=np.zeros((P, 6), rt),
+             scales=np.zeros((P, 3), rt), rots=np.zeros((P, 4), rt),
+             shs=None if shs is None else np.zeros(shs.shape, rt))
+    fn = lib().ocrf_oracle_preprocess_backward_f64 if f64 else lib().ocrf_oracle_preprocess_backward
+    fn(
         C.c_int(P), C.c_int(sh_degree), C.c_int(sh_M), _ptr(means), _ptr(np.ascontiguousarray(radii, np.int32)), _ptr(shs),
         _ptr(None if clamped is None else np.ascontiguousarray(clamped, np.uint8)), _ptr(scales),
         C.c_float(scale_modifier), _ptr(rots), _ptr(_f32(cov3D)), _ptr(_f32(view).reshape(-1)),
         _ptr(_f32(proj).reshape(-1)), _ptr(campos), C.c_int(W), C.c_int(H), C.c_float(tanfovx), C.c_float(tanfovy),
-        _ptr(_f32(dL_dmean2D)), _ptr(_f32(dL_dconic)), _ptr(_f32(dL_dcolor)), _ptr(g["means"]), _ptr(g["cov3D"]),
+        _ptr(_f32g(dL_dmean2D)), _ptr(_f32g(dL_dconic)), _ptr(_f32g(dL_dcolor)), _ptr(g["means"]), _ptr(g["cov3D"]),
         _ptr(g["scales"] if scales is not None else None), _ptr(g["rots"] if scales is not None else None),
         _ptr(g["shs"]))
     return g
@@ -188,16 +193,20 @@ def rasterize(means, opacities, colors, view, proj, W, H, tanfovx, tanfovy, bg, 
 
 
 def rasterize_backward(state, means, view, proj, W, H, tanfovx, tanfovy, bg, out, dL_dcolor, dL_dopacity_map=None,
-                       scales=None, rots=None, scale_modifier=1.0, shs=None, sh_degree=0, campos=None):
-    """Whole backward path.  Returns dict of gradients as the plugin returns them."""
+                       scales=None, rots=None, scale_modifier=1.0, shs=None, sh_degree=0, campos=None, f64=True):
+    """Whole backward path.  Returns dict of gradients as the plugin returns them.
+
+    f64=True (default) evaluates the per-Gaussian chain in double from the double-accumulated
+    screen-space sums; f64=False rounds those sums to float32 and uses float32 arithmetic exactly like
+    the reference's two preprocess-backward kernels."""
     pre, b, feats = state["pre"], state["bin"], state["feats"]
     P = pre["radii"].shape[0]
     g = render_backward(P, W, H, b["ranges"], b["point_list"], pre["xy"], pre["conic_opacity"], feats, bg,
                         out["final_T"], out["n_contrib"], dL_dcolor, dL_dopacity_map)
     pb = preprocess_backward(means, pre["radii"], pre["cov3D"], view, proj, W, H, tanfovx, tanfovy,
-                             g["mean2D"].astype(np.float32), g["conic"].astype(np.float32), scales=scales, rots=rots,
+                             g["mean2D"], g["conic"], scales=scales, rots=rots,
                              scale_modifier=scale_modifier, shs=shs, sh_degree=sh_degree, clamped=pre["clamped"],
-                             campos=campos, dL_dcolor=g["colors"].astype(np.float32))
+                             campos=campos, dL_dcolor=g["colors"], f64=f64)
     return dict(means3D=pb["means"], means2D=g["mean2D"], colors=g["colors"], opacities=g["opacity"],
                 scales=pb["scales"], rotations=pb["rots"], cov3D=pb["cov3D"], shs=pb["shs"], conic=g["conic"])
 

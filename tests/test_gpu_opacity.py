@@ -1,0 +1,70 @@
+"""Stage 5 (HOA opacity mask) and the drop-in call sequence of OcRFDet's render() wrapper."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import oracle
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,C,H,W,K", [(2, 80, 128, 128, 7), (1, 5, 20, 33, 3), (3, 16, 40, 24, 7)])
+def test_opacity_mask_forward_backward(B, C, H, W, K):
+    from ocrfdet_b200.opacity_lift import opacity_mask
+    rng = np.random.default_rng(B * 100 + C)
+    x = rng.normal(size=(B, C, H, W)).astype(np.float32)
+    w = (rng.normal(size=(1, 2, K, K)) * 0.2).astype(np.float32)
+    ob = rng.normal(size=(B, 1, H, W)).astype(np.float32)
+    go = rng.normal(size=(B, C, H, W)).astype(np.float32)
+    xt, wt, ot = (torch.from_numpy(a).cuda().requires_grad_(True) for a in (x, w, ob))
+    out, mask = opacity_mask(xt, wt, ot)
+    wo, wm, ws = oracle.opacity_mask_forward(x, w, ob)
+    assert np.abs(out.detach().cpu().numpy() - wo).max() <= 1e-5 * (1 + np.abs(wo).max())
+    assert np.abs(mask.detach().cpu().numpy() - wm).max() <= 1e-5
+    (out * torch.from_numpy(go).cuda()).sum().backward()
+    gx, gw, gop = oracle.opacity_mask_backward(x, w, wm, ws, go)
+    assert util.rel_err(xt.grad.cpu().numpy(), gx) <= 1e-4
+    assert util.rel_err(wt.grad.cpu().numpy().reshape(2, K, K), gw) <= 1e-4
+    assert util.rel_err(ot.grad.cpu().numpy(), gop) <= 1e-4
+    # and against the reference's own torch formulation (view_transformer_ocrf.py:230-242)
+    x2, w2, o2 = (torch.from_numpy(a).cuda().requires_grad_(True) for a in (x, w, ob))
+    s = torch.cat([x2.mean(1, keepdim=True), x2.max(1, keepdim=True)[0]], 1)
+    ref_out = x2 * torch.sigmoid(torch.nn.functional.conv2d(s, w2, padding=K // 2) + o2)
+    assert float((ref_out - out).abs().max()) <= 1e-5 * (1 + float(ref_out.abs().max()))
+
+
+def test_dropin_render_wrapper_call_sequence():
+    """Exactly what gaussian_renderer/__init__.py:17-75 does, against the import name it uses."""
+    from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+    W, H = 176, 64
+    g, cams = util.small_scene("ring", P=8000, seed=31, W=W, H=H, n_views=3)
+    cam = cams[2]
+    gc = util.to_cuda(g)
+    data = {"FovX": torch.tensor(2 * math.atan(cam["tanfovx"])).cuda(), "FovY": torch.tensor(2 * math.atan(cam["tanfovy"])).cuda(),
+            "height": H, "width": W, "world_view_transform": torch.from_numpy(cam["viewmatrix"]).cuda(),
+            "full_proj_transform": torch.from_numpy(cam["projmatrix"]).cuda(),
+            "camera_center": torch.from_numpy(cam["campos"]).cuda()}
+    pts_xyz, pts_rgb = gc["means3D"], gc["colors"].requires_grad_(True)
+    bg_color = torch.tensor([0, 0, 0], dtype=torch.float32, device="cuda")
+    screenspace_points = torch.zeros_like(pts_xyz, dtype=torch.float32, requires_grad=True, device="cuda") + 0
+    screenspace_points.retain_grad()
+    tanfovx = math.tan(data["FovX"] * 0.5)
+    tanfovy = math.tan(data["FovY"] * 0.5)
+    raster_settings = GaussianRasterizationSettings(
+        image_height=int(data["height"]), image_width=int(data["width"]), tanfovx=tanfovx, tanfovy=tanfovy, bg=bg_color,
+        scale_modifier=1.0, viewmatrix=data["world_view_transform"], projmatrix=data["full_proj_transform"], sh_degree=3,
+        campos=data["camera_center"], prefiltered=False)
+    rasterizer = GaussianRasterizer(raster_settings=raster_settings)
+    rendered_image, _, rendered_depth = rasterizer(means3D=pts_xyz, means2D=screenspace_points, shs=None,
+                                                   colors_precomp=pts_rgb, opacities=gc["opacities"], scales=gc["scales"],
+                                                   rotations=gc["rotations"], cov3D_precomp=None)
+    assert rendered_image.shape == (3, H, W) and rendered_depth.shape == (1, H, W)
+    rendered_image.mean().backward()
+    assert screenspace_points.grad is not None and screenspace_points.grad.shape == pts_xyz.shape
+    assert float(pts_rgb.grad.abs().sum()) > 0
+    cam2 = dict(cam, tanfovx=tanfovx, tanfovy=tanfovy)
+    want, _ = util.oracle_forward(g, cam2, W, H, [0, 0, 0])
+    util.assert_image_close(rendered_image.detach().cpu().numpy(), want["color"], want["ambiguous"], 1e-5, "render()")

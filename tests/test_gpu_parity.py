@@ -1,0 +1,253 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on identical inputs.
+
+Bars (BASELINE.json north_star): tile keys / sort order / tile ranges bit-exact; forward outputs within
+1e-5 abs/rel; gradients within 1e-4 rel.
+"""
+import numpy as np
+import pytest
+import torch
+
+from ocrfdet_b200 import rasterizer as R
+from oracle import oracle
+from tests import util
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-5
+GRAD_TOL = 1e-4
+
+
+def _render_single(g, cam, bg, return_opacity=True, **kw):
+    R.KEEP_STATE = True
+    gc = util.to_cuda(g)
+    for k in ("means3D", "scales", "rotations", "opacities", "colors"):
+        if k in gc:
+            gc[k].requires_grad_(True)
+    st = util.settings_for(cam, bg, **kw)
+    rast = R.GaussianRasterizer(st, return_opacity=return_opacity)
+    means2D = torch.zeros_like(gc["means3D"], requires_grad=True)
+    out = rast(means3D=gc["means3D"], means2D=means2D, opacities=gc["opacities"], colors_precomp=gc["colors"],
+               scales=gc["scales"], rotations=gc["rotations"])
+    return out, gc, means2D
+
+
+SCENES = [
+    ("frustum", dict(P=3000, seed=1, W=160, H=96)),
+    ("frustum", dict(P=500, seed=2, W=50, H=37)),      # image not a multiple of the tile size
+    ("ring", dict(P=20000, seed=3, W=352, H=128)),
+    ("frustum", dict(P=10000, seed=4, W=704, H=256)),  # BASELINE config 1
+]
+
+
+@pytest.mark.parametrize("kind,kw", SCENES)
+def test_preprocess_and_binning_bit_exact(kind, kw):
+    g, cams = util.small_scene(kind, **kw)
+    cam, W, H = cams[0], kw["W"], kw["H"]
+    bg = [0.0, 0.0, 0.0]
+    (_color, radii, _depth, _op), _, _ = _render_single(g, cam, bg)
+    st = R.last_state()
+    want, wst = util.oracle_forward(g, cam, W, H, bg)
+    pre, b = wst["pre"], wst["bin"]
+    vis = pre["radii"] > 0
+    assert np.array_equal(radii.cpu().numpy(), pre["radii"])
+    assert np.array_equal(st["tiles_touched"][0].cpu().numpy().astype(np.uint32), pre["tiles_touched"])
+    assert np.array_equal(st["offsets"].cpu().numpy().astype(np.uint32), b["offsets"])
+    # float state: compare BIT PATTERNS on visible Gaussians (culled entries are never written)
+    for name, ref in (("depths", pre["depths"]), ("xy", pre["xy"]), ("conic_opacity", pre["conic_opacity"])):
+        got = st[name][0].cpu().numpy()
+        assert np.array_equal(got[vis].view(np.uint32), ref[vis].view(np.uint32)), name
+    assert st["num_pairs"] == b["N"]
+    assert np.array_equal(st["keys"].cpu().numpy().view(np.uint64), b["keys"])
+    assert np.array_equal(st["point_list"].cpu().numpy().view(np.uint32), b["point_list"])
+    assert np.array_equal(st["ranges"][0].cpu().numpy().view(np.uint32), b["ranges"])
+
+
+@pytest.mark.parametrize("kind,kw", SCENES)
+def test_forward_outputs(kind, kw):
+    g, cams = util.small_scene(kind, **kw)
+    cam, W, H = cams[0], kw["W"], kw["H"]
+    bg = [0.2, 0.5, 0.1]
+    (color, _radii, depth, opac), _, _ = _render_single(g, cam, bg)
+    want, _ = util.oracle_forward(g, cam, W, H, bg)
+    amb = want["ambiguous"]
+    util.assert_image_close(color.detach().cpu().numpy(), want["color"], amb, FWD_TOL, "color")
+    util.assert_image_close(opac.detach().cpu().numpy(), want["opacity"], amb, FWD_TOL, "opacity")
+    d = depth.cpu().numpy()
+    assert np.array_equal(d[0][~amb.astype(bool)], want["depth"][0][~amb.astype(bool)]), "median depth"
+    st = R.last_state()
+    nc = st["n_contrib"][0].cpu().numpy()
+    assert np.array_equal(nc[~amb.astype(bool)], want["n_contrib"].astype(np.int32)[~amb.astype(bool)])
+
+
+@pytest.mark.parametrize("kind,kw", SCENES[:3])
+def test_backward_gradients(kind, kw):
+    g, cams = util.small_scene(kind, **kw)
+    cam, W, H = cams[0], kw["W"], kw["H"]
+    bg = [0.3, 0.1, 0.6]
+    rng = np.random.default_rng(7)
+    gcol = rng.normal(size=(3, H, W)).astype(np.float32)
+    gop = rng.normal(size=(1, H, W)).astype(np.float32)
+    (color, _radii, _depth, opac), gc, means2D = _render_single(g, cam, bg)
+    loss = (color * torch.from_numpy(gcol).cuda()).sum() + (opac * torch.from_numpy(gop).cuda()).sum()
+    loss.backward()
+    want, wst = util.oracle_forward(g, cam, W, H, bg)
+    # the oracle's backward must start from the SAME forward state as the GPU (n_contrib / final_T)
+    gw = util.oracle_backward(g, cam, W, H, bg, want, wst, gcol, gop)
+    pairs = [("means3D", gc["means3D"].grad, gw["means3D"]), ("scales", gc["scales"].grad, gw["scales"]),
+             ("rotations", gc["rotations"].grad, gw["rotations"]),
+             ("opacities", gc["opacities"].grad.reshape(-1), gw["opacities"]), ("colors", gc["colors"].grad, gw["colors"]),
+             ("means2D", means2D.grad[:, :2], gw["means2D"])]
+    for name, got, ref in pairs:
+        e = util.rel_err(got.cpu().numpy(), ref)
+        assert e <= GRAD_TOL, "%s gradient rel err %.3g" % (name, e)
+    assert float(means2D.grad[:, 2].abs().max()) == 0.0
+
+
+def test_batch_matches_single_views():
+    W, H = 352, 128
+    g, cams = util.small_scene("ring", P=20000, seed=5, W=W, H=H, n_views=6)
+    bg = [0.0, 0.0, 0.0]
+    gc = util.to_cuda(g)
+    u = lambda t: t.unsqueeze(0)  # noqa: E731
+    color, radii, depth, opac = R.render_batch(u(gc["means3D"]), u(gc["opacities"]), util.cams_tensor(cams), H, W,
+                                               torch.tensor(bg, device="cuda"), colors_precomp=u(gc["colors"]),
+                                               scales=u(gc["scales"]), rotations=u(gc["rotations"]))
+    for v, cam in enumerate(cams):
+        (c1, r1, d1, o1), _, _ = _render_single(g, cam, bg)
+        assert torch.equal(color[v], c1) and torch.equal(radii[v], r1) and torch.equal(depth[v], d1)
+        assert torch.equal(opac[v], o1)
+
+
+def test_batch_gradients_sum_over_views():
+    W, H = 160, 96
+    g, cams = util.small_scene("ring", P=6000, seed=6, W=W, H=H, n_views=3)
+    bg = [0.1, 0.2, 0.3]
+    rng = np.random.default_rng(3)
+    gcol = torch.from_numpy(rng.normal(size=(3, 3, H, W)).astype(np.float32)).cuda()
+    gc = util.to_cuda(g)
+    names = ("means3D", "scales", "rotations", "opacities", "colors")
+    for k in names:
+        gc[k].requires_grad_(True)
+    u = lambda t: t.unsqueeze(0)  # noqa: E731
+    color, _, _, _ = R.render_batch(u(gc["means3D"]), u(gc["opacities"]), util.cams_tensor(cams), H, W,
+                                    torch.tensor(bg, device="cuda"), colors_precomp=u(gc["colors"]),
+                                    scales=u(gc["scales"]), rotations=u(gc["rotations"]))
+    (color * gcol).sum().backward()
+    got = {k: gc[k].grad.clone() for k in names}
+    acc = {k: 0 for k in names}
+    for v, cam in enumerate(cams):
+        want, wst = util.oracle_forward(g, cam, W, H, bg)
+        gw = util.oracle_backward(g, cam, W, H, bg, want, wst, gcol[v].cpu().numpy())
+        for k in names:
+            acc[k] = acc[k] + np.asarray(gw[k], np.float64)
+    for k in names:
+        e = util.rel_err(got[k].cpu().numpy().reshape(acc[k].shape), acc[k])
+        assert e <= GRAD_TOL, "%s batched gradient rel err %.3g" % (k, e)
+
+
+@pytest.mark.parametrize("C", [1, 8, 19])
+def test_generic_channel_count(C):
+    W, H = 96, 64
+    g, cams = util.small_scene("frustum", P=1500, seed=8, W=W, H=H, channels=C)
+    cam = cams[0]
+    bg = list(np.linspace(0.1, 0.9, C).astype(np.float32))
+    rng = np.random.default_rng(5)
+    gcol = rng.normal(size=(C, H, W)).astype(np.float32)
+    (color, _r, depth, opac), gc, means2D = _render_single(g, cam, bg)
+    want, wst = util.oracle_forward(g, cam, W, H, bg)
+    util.assert_image_close(color.detach().cpu().numpy(), want["color"], want["ambiguous"], FWD_TOL, "features")
+    (color * torch.from_numpy(gcol).cuda()).sum().backward()
+    gw = util.oracle_backward(g, cam, W, H, bg, want, wst, gcol)
+    for name, got, ref in (("colors", gc["colors"].grad, gw["colors"]), ("means3D", gc["means3D"].grad, gw["means3D"]),
+                           ("scales", gc["scales"].grad, gw["scales"]),
+                           ("opacities", gc["opacities"].grad.reshape(-1), gw["opacities"])):
+        e = util.rel_err(got.cpu().numpy(), ref)
+        assert e <= GRAD_TOL, "%s gradient rel err %.3g (C=%d)" % (name, e, C)
+
+
+def test_sh_and_cov3d_precomp_paths():
+    W, H = 128, 80
+    g, cams = util.small_scene("frustum", P=1200, seed=9, W=W, H=H)
+    cam = cams[0]
+    bg = [0.0, 0.1, 0.2]
+    rng = np.random.default_rng(11)
+    P = g["means3D"].shape[0]
+    shs = (rng.normal(size=(P, 16, 3)) * 0.3).astype(np.float32)
+    cov = util.cov3d_numpy(g["scales"], g["rotations"])
+    gcol = rng.normal(size=(3, H, W)).astype(np.float32)
+    for deg in (0, 2, 3):
+        R.KEEP_STATE = True
+        st = util.settings_for(cam, bg, sh_degree=deg)
+        m = torch.from_numpy(g["means3D"]).cuda().requires_grad_(True)
+        sh_t = torch.from_numpy(shs).cuda().requires_grad_(True)
+        cov_t = torch.from_numpy(cov).cuda().requires_grad_(True)
+        op_t = torch.from_numpy(g["opacities"]).cuda().requires_grad_(True)
+        color, radii, depth = R.GaussianRasterizer(st)(means3D=m, means2D=torch.zeros_like(m), opacities=op_t, shs=sh_t,
+                                                       cov3D_precomp=cov_t)
+        want, wst = oracle.rasterize(g["means3D"], g["opacities"], None, cam["viewmatrix"], cam["projmatrix"], W, H,
+                                     cam["tanfovx"], cam["tanfovy"], np.asarray(bg, np.float32), cov3D_precomp=cov,
+                                     shs=shs, sh_degree=deg, campos=cam["campos"])
+        util.assert_image_close(color.detach().cpu().numpy(), want["color"], want["ambiguous"], FWD_TOL, "SH colour")
+        (color * torch.from_numpy(gcol).cuda()).sum().backward()
+        gw = oracle.rasterize_backward(wst, g["means3D"], cam["viewmatrix"], cam["projmatrix"], W, H, cam["tanfovx"],
+                                       cam["tanfovy"], np.asarray(bg, np.float32), want, gcol, shs=shs, sh_degree=deg,
+                                       campos=cam["campos"])
+        for name, got, ref in (("shs", sh_t.grad, gw["shs"]), ("cov3D", cov_t.grad, gw["cov3D"]),
+                               ("means3D", m.grad, gw["means3D"]), ("opacities", op_t.grad.reshape(-1), gw["opacities"])):
+            e = util.rel_err(got.cpu().numpy(), ref)
+            assert e <= GRAD_TOL, "%s gradient rel err %.3g (deg %d)" % (name, e, deg)
+
+
+def test_edge_cases():
+    W, H = 64, 48
+    g, cams = util.small_scene("frustum", P=300, seed=10, W=W, H=H)
+    cam = cams[0]
+    bg = [0.25, 0.5, 0.75]
+    st = util.settings_for(cam, bg)
+    rast = R.GaussianRasterizer(st, return_opacity=True)
+    # (1) nothing visible: every Gaussian behind the camera -> pure background, zero gradients
+    gb = dict(g)
+    gb["means3D"] = g["means3D"] * np.array([1, 1, -1], np.float32)
+    gc = util.to_cuda(gb)
+    gc["colors"].requires_grad_(True)
+    color, radii, depth, opac = rast(means3D=gc["means3D"], means2D=torch.zeros_like(gc["means3D"]),
+                                     opacities=gc["opacities"], colors_precomp=gc["colors"], scales=gc["scales"],
+                                     rotations=gc["rotations"])
+    assert int(radii.abs().sum()) == 0
+    want = torch.tensor(bg, device="cuda").view(3, 1, 1).expand(3, H, W)
+    assert torch.equal(color, want) and float(opac.abs().max()) == 0.0 and float((depth - 15).abs().max()) == 0.0
+    color.sum().backward()
+    assert float(gc["colors"].grad.abs().max()) == 0.0
+    # (2) P == 0: zero image as the reference binding (rasterize_points.cu:68,81)
+    e = torch.zeros((0, 3), device="cuda")
+    color, radii, depth, opac = rast(means3D=e, means2D=e, opacities=torch.zeros((0, 1), device="cuda"), colors_precomp=e,
+                                     scales=e, rotations=torch.zeros((0, 4), device="cuda"))
+    assert color.shape == (3, H, W) and float(color.abs().max()) == 0.0 and radii.numel() == 0
+    # (3) argument errors of the reference wrapper
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        rast(means3D=gc["means3D"], means2D=None, opacities=gc["opacities"], scales=gc["scales"], rotations=gc["rotations"])
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair"):
+        rast(means3D=gc["means3D"], means2D=None, opacities=gc["opacities"], colors_precomp=gc["colors"])
+    # (4) markVisible
+    vis = rast.markVisible(torch.from_numpy(g["means3D"]).cuda())
+    assert np.array_equal(vis.cpu().numpy(), oracle.mark_visible(g["means3D"], cam["viewmatrix"], cam["projmatrix"]))
+
+
+def test_capacity_mode_no_sync_and_overflow():
+    W, H = 160, 96
+    g, cams = util.small_scene("frustum", P=3000, seed=12, W=W, H=H)
+    bg = torch.zeros(3, device="cuda")
+    gc = util.to_cuda(g)
+    u = lambda t: t.unsqueeze(0)  # noqa: E731
+    args = (u(gc["means3D"]), u(gc["opacities"]), util.cams_tensor(cams), H, W, bg)
+    kw = dict(colors_precomp=u(gc["colors"]), scales=u(gc["scales"]), rotations=u(gc["rotations"]))
+    R.KEEP_STATE = True
+    exact = R.render_batch(*args, **kw)
+    n = R.last_state()["num_pairs"]
+    roomy = R.render_batch(*args, pair_capacity=2 * n + 1000, **kw)
+    R.check_overflow()
+    assert torch.equal(roomy[0], exact[0]) and torch.equal(roomy[2], exact[2])
+    tight = R.render_batch(*args, pair_capacity=n // 2, **kw)
+    with pytest.raises(Exception, match="overflow"):
+        R.check_overflow()
+    assert float(tight[0].abs().max()) == 0.0  # rendered background only, no overrun

@@ -1,0 +1,76 @@
+"""Shared helpers of the test-suite: scene construction, oracle / product / reference drivers."""
+import numpy as np
+import torch
+
+from ocrfdet_b200 import rasterizer as R
+from ocrfdet_b200.scenes import frustum_scene, ring_scene
+from oracle import oracle
+
+
+def small_scene(kind="frustum", P=2000, seed=0, W=160, H=96, channels=3, n_views=1):
+    if kind == "frustum":
+        g, cams = frustum_scene(P=P, seed=seed, width=W, height=H, channels=channels)
+    else:
+        g, cams = ring_scene(P=P, seed=seed, width=W, height=H, channels=channels, n_views=n_views)
+    return g, cams
+
+
+def oracle_forward(g, cam, W, H, bg, **kw):
+    return oracle.rasterize(g["means3D"], g["opacities"], g["colors"], cam["viewmatrix"], cam["projmatrix"], W, H,
+                            cam["tanfovx"], cam["tanfovy"], np.asarray(bg, np.float32), scales=g.get("scales"),
+                            rots=g.get("rotations"), campos=cam["campos"], **kw)
+
+
+def oracle_backward(g, cam, W, H, bg, out, state, dL_dcolor, dL_dopacity=None, **kw):
+    return oracle.rasterize_backward(state, g["means3D"], cam["viewmatrix"], cam["projmatrix"], W, H, cam["tanfovx"],
+                                     cam["tanfovy"], np.asarray(bg, np.float32), out, dL_dcolor, dL_dopacity,
+                                     scales=g.get("scales"), rots=g.get("rotations"), campos=cam["campos"], **kw)
+
+
+def to_cuda(g):
+    return {k: torch.from_numpy(np.ascontiguousarray(v)).cuda() for k, v in g.items()}
+
+
+def settings_for(cam, bg, sh_degree=0, scale_modifier=1.0):
+    dev = "cuda"
+    return R.GaussianRasterizationSettings(
+        image_height=cam["height"], image_width=cam["width"], tanfovx=cam["tanfovx"], tanfovy=cam["tanfovy"],
+        bg=torch.tensor(bg, dtype=torch.float32, device=dev), scale_modifier=scale_modifier,
+        viewmatrix=torch.from_numpy(cam["viewmatrix"]).to(dev), projmatrix=torch.from_numpy(cam["projmatrix"]).to(dev),
+        sh_degree=sh_degree, campos=torch.from_numpy(cam["campos"]).to(dev), prefiltered=False)
+
+
+def cams_tensor(cams):
+    vm = torch.from_numpy(np.stack([c["viewmatrix"] for c in cams])).cuda()
+    pm = torch.from_numpy(np.stack([c["projmatrix"] for c in cams])).cuda()
+    cp = torch.from_numpy(np.stack([c["campos"] for c in cams])).cuda()
+    tx = torch.tensor([c["tanfovx"] for c in cams], dtype=torch.float32).cuda()
+    ty = torch.tensor([c["tanfovy"] for c in cams], dtype=torch.float32).cuda()
+    return R.pack_cameras(vm, pm, cp, tx, ty)
+
+
+def rel_err(a, b):
+    a = np.asarray(a, np.float64)
+    b = np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def assert_image_close(got, want, ambiguous, tol=1e-5, what="image"):
+    """|got - want| <= tol * (1 + |want|) on every pixel whose blend decisions were not borderline;
+    borderline pixels (a handful) may differ by one blended Gaussian (<= ~1/255 of the value range)."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    amb = np.asarray(ambiguous).astype(bool)
+    err = np.abs(got - want) / (1.0 + np.abs(want))
+    clean = err[..., ~amb] if err.ndim == 3 else err[~amb]
+    assert clean.size == 0 or clean.max() <= tol, "%s: max err %.3g on unambiguous pixels" % (what, clean.max())
+    assert amb.mean() < 0.01, "%s: too many borderline pixels (%.2f%%)" % (what, 100 * amb.mean())
+
+
+def cov3d_numpy(scales, rots):
+    """[P,6] upper triangle of Sigma = A^T diag(s^2) A for quaternion (r,x,y,z) (forward.cu:118-152)."""
+    r, x, y, z = (rots[:, i].astype(np.float64) for i in range(4))
+    A = np.stack([1 - 2 * (y * y + z * z), 2 * (x * y + r * z), 2 * (x * z - r * y),
+                  2 * (x * y - r * z), 1 - 2 * (x * x + z * z), 2 * (y * z + r * x),
+                  2 * (x * z + r * y), 2 * (y * z - r * x), 1 - 2 * (x * x + y * y)], 1).reshape(-1, 3, 3)
+    S = np.einsum("pki,pk,pkj->pij", A, scales.astype(np.float64) ** 2, A)
+    return np.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1).astype(np.float32)
