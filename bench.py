@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- rendered camera views/s (fwd+bwd) of the OcRF Gaussian render path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload config2]
+
+Contract (see DESIGN.md "Measurement"):
+  * a STEP is one pass of the hot path over one batch: BASELINE.json config 2 -- one sample of
+    100,000 voxel-grid Gaussians rendered into its 6 camera views at 256x704, colour + median depth
+    + opacity, forward AND backward (upstream gradients on colour and opacity).
+  * `value`  = views/s with inputs resident in HBM, CUDA-event timed per step on the launching
+    stream, L2 flushed (256 MB write) before every timed step, max over ranks.
+  * `e2e`    = the same metric through the public API with HOST (pinned) buffers: H2D of the
+    Gaussian parameters, forward, backward, D2H of the parameter gradients, inside the timed region.
+  * `roofline` for the dominant kernel (algorithmic bytes / its event-timed duration vs the measured
+    HBM peak) plus per-stage times; `cpu_baseline` = the C oracle port on the host cores (1 view).
+  * --impl reference: the reference's OWN rasterizer.  Its render path is CUDA-only, so "the
+    reference's implementation on this box" is oracle/_ref/libinria_ref.so (the vendored Inria
+    kernels, unmodified) called once per view like OcRFDet does; if that library is absent the arm
+    falls back to the CPU oracle port.
+  * N > 1 (torchrun): every rank renders its own sample (weak scaling) and the per-view opacity maps
+    are all-gathered (the path's single collective).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+W, H, P, VIEWS, C = 704, 256, 100_000, 6, 3
+METRIC = "rendered camera views/sec (6x256x704 fwd+bwd)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="run a few untimed steps and exit (for ncu)")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for n, val in zip(names, r[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(rank, device):
+    from ocrfdet_b200.scenes import ring_scene
+    g, cams = ring_scene(P=P, seed=1234 + 1000 * rank, width=W, height=H, channels=C, n_views=VIEWS)
+    rng = np.random.default_rng(99 + rank)
+    gcol = rng.normal(size=(VIEWS, C, H, W)).astype(np.float32)
+    gop = rng.normal(size=(VIEWS, 1, H, W)).astype(np.float32)
+    return g, cams, gcol, gop
+
+
+def run_ours(args, rank, world, device):
+    from ocrfdet_b200 import _lib, rasterizer as R
+    from ocrfdet_b200.sharding import gather_opacity_maps
+    _lib.lib()
+    g, cams, gcol_np, gop_np = make_inputs(rank, device)
+    names = ("means3D", "scales", "rotations", "opacities", "colors")
+    host = {k: torch.from_numpy(g[k]).unsqueeze(0).contiguous().pin_memory() for k in names}
+    dev = {k: host[k].to(device).requires_grad_(True) for k in names}
+    cam_t = R.pack_camera_dicts(cams, device)
+    bg = torch.zeros(3, device=device)
+    gcol, gop = torch.from_numpy(gcol_np).to(device), torch.from_numpy(gop_np).to(device)
+    side = torch.cuda.Stream() if world > 1 else None
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def render(t):
+        return R.render_batch(t["means3D"], t["opacities"], cam_t, H, W, bg, colors_precomp=t["colors"],
+                              scales=t["scales"], rotations=t["rotations"])
+
+    def step(t=dev):
+        for k in names:
+            t[k].grad = None
+        color, radii, depth, opac = render(t)
+        gathered = gather_opacity_maps(opac.detach(), world, VIEWS, stream=side) if world > 1 else opac
+        torch.autograd.backward([color, opac], [gcol, gop])
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        return gathered
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if args.profile_only:
+        for _ in range(args.steps):
+            step()
+        torch.cuda.synchronize()
+        return None
+
+    # ---- workload statistics (one extra forward with the workspaces kept) ----
+    R.KEEP_STATE = True
+    with torch.no_grad():
+        render(dev)
+    st = R.last_state()
+    stats = dict(P=P, P_vis=int((st["radii"] > 0).sum()), N_dup=int(st["num_pairs"]),
+                 N_pair=int(st["n_contrib"].sum(dtype=torch.int64)))
+    R.KEEP_STATE = False
+    R._LAST_STATE = None
+    end_bit = _lib.lib().ocrf_sort_end_bit(_lib.C.byref(_lib.OcrfShape(1, P, VIEWS, VIEWS, W, H, C, 0, 0)))
+    passes = (end_bit + 7) // 8
+    launches_per_step = 7 + passes
+
+    # ---- device-resident throughput ----
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)  # evict L2 (126 MB) before every timed step; not timed
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    if world > 1:
+        dist.barrier()
+    total_ms = sum(a.elapsed_time(b) for a, b in evs)
+    if world > 1:
+        t = torch.tensor([total_ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t[0])
+    ms_per_step = total_ms / args.steps
+    value = world * VIEWS / (ms_per_step / 1e3)
+
+    # ---- per-stage device time (CUDA events on the launching stream, L2 flushed per step) ----
+    stage_ms = {}
+    marks = []
+    R.STAGE_HOOK = lambda name: marks.append((name, _rec()))
+
+    def _rec():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    reps = min(10, args.steps)
+    for _ in range(reps):
+        flush.fill_(1)
+        marks.append(("begin", _rec()))
+        step()
+    torch.cuda.synchronize()
+    R.STAGE_HOOK = None
+    for (n0, e0), (n1, e1) in zip(marks[:-1], marks[1:]):
+        if n1 in ("begin", "backward_begin"):
+            continue
+        stage_ms[n1] = stage_ms.get(n1, 0.0) + e0.elapsed_time(e1) / reps
+
+    # algorithmic bytes per step (S = sort passes)
+    n_dup, p_vis, wh = stats["N_dup"], stats["P_vis"], W * H * VIEWS
+    alg = {
+        "preprocess": VIEWS * P * 44 + p_vis * 36,
+        "binning": n_dup * (12 + 8 + 24 * passes + 8) + n_dup * (32 + 4 * C + 48),
+        "render_forward": n_dup * 48 + wh * (4 * (C + 2) + 8),
+        "render_backward": wh * (4 * (C + 2) + 8) + n_dup * 48 + n_dup * 2 * 4 * (6 + C),
+        "preprocess_backward": p_vis * (36 + 24 + 4 * (3 + 3 + 4 + C + 1)) + VIEWS * P * 4,
+    }
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    dom = max(stage_ms, key=stage_ms.get) if stage_ms else "render_backward"
+    ach = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms.get(dom) else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes": alg[dom], "kernel_ms": stage_ms.get(dom),
+                "note": "blend kernels are FP32-issue/MUFU bound, not HBM bound (SURVEY 8d): see pair_rate"}
+    stages = {k: {"ms": round(v, 4), "alg_GB": round(alg[k] / 1e9, 4),
+                  "GBps": round(alg[k] / (v * 1e-3) / 1e9, 1) if v > 0 else None} for k, v in stage_ms.items()}
+    pair_rate = {"N_pair_per_step": stats["N_pair"],
+                 "fwd_Gpairs_per_s": stats["N_pair"] / (stage_ms["render_forward"] * 1e-3) / 1e9
+                 if stage_ms.get("render_forward") else None,
+                 "bwd_Gpairs_per_s": stats["N_pair"] / (stage_ms["render_backward"] * 1e-3) / 1e9
+                 if stage_ms.get("render_backward") else None}
+
+    # ---- end to end through the public API with host buffers ----
+    grads_host = {k: torch.empty_like(host[k]).pin_memory() for k in names}
+    h2d = sum(host[k].numel() * 4 for k in names)
+    d2h = sum(grads_host[k].numel() * 4 for k in names)
+    e2e_steps = max(3, min(args.steps, 20))
+
+    def e2e_step():
+        t = {k: host[k].to(device, non_blocking=True).requires_grad_(True) for k in names}
+        step(t)
+        for k in names:
+            grads_host[k].copy_(t[k].grad, non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_tot = 0.0
+    for _ in range(e2e_steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        e2e_step()
+        e1.record()
+        e1.synchronize()
+        t_tot += e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([t_tot], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_tot = float(t[0])
+    e2e = {"value": world * VIEWS / (t_tot / e2e_steps / 1e3), "unit": "views/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "ms_per_step": t_tot / e2e_steps, "steps": e2e_steps}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(g, cams, gcol_np, gop_np)
+
+    out = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_per_render": ms_per_step / VIEWS,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": "BASELINE config 2: 1 sample x 6 views 256x704, 100k voxel-grid Gaussians, "
+                                  "colour+depth+opacity fwd+bwd, per GPU", "views_per_step_per_gpu": VIEWS,
+                      "gaussians": P, "image": [H, W], "channels": C, "l2": "flushed (256 MB write) before each timed step",
+                      "parallelism": "(sample,view) shards, %d rank(s); opacity-map all-gather" % world},
+           "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+           "gpu_launches_per_step": launches_per_step, "roofline": roofline, "stages": stages, "pair_rate": pair_rate,
+           "workload_stats": stats, "impl": "ours"}
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    return out
+
+
+def cpu_baseline(g, cams, gcol, gop, views=1):
+    """The C oracle port on the host cores, one view of the same workload, forward + backward."""
+    from oracle import oracle
+    cam = cams[0]
+    bg = np.zeros(3, np.float32)
+    t0 = time.time()
+    for v in range(views):
+        cam = cams[v]
+        out, st = oracle.rasterize(g["means3D"], g["opacities"], g["colors"], cam["viewmatrix"], cam["projmatrix"], W, H,
+                                   cam["tanfovx"], cam["tanfovy"], bg, scales=g["scales"], rots=g["rotations"])
+        oracle.rasterize_backward(st, g["means3D"], cam["viewmatrix"], cam["projmatrix"], W, H, cam["tanfovx"],
+                                  cam["tanfovy"], bg, out, gcol[v], gop[v], scales=g["scales"], rots=g["rotations"])
+    dt = time.time() - t0
+    return {"value": views / dt, "unit": "views/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": "%d of the step's %d views (256x704, 100k Gaussians), fwd+bwd, C oracle with OpenMP over tiles"
+                      % (views, VIEWS), "seconds": dt}
+
+
+def run_reference(args, rank, world, device):
+    """The reference's own rasterizer on this box, called per view as OcRFDet does (VT:1153)."""
+    from oracle import ref
+    if rank != 0:
+        return None
+    g, cams, gcol_np, gop_np = make_inputs(0, device)
+    base = {"metric": METRIC, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "impl": "reference",
+            "config": {"workload": "BASELINE config 2: 1 sample x 6 views 256x704, 100k voxel-grid Gaussians, fwd+bwd",
+                       "views_per_step_per_gpu": VIEWS, "gaussians": P, "image": [H, W], "channels": C}}
+    if not (ref.available() and torch.cuda.is_available()):
+        cpu = cpu_baseline(g, cams, gcol_np, gop_np)
+        base.update({"value": cpu["value"], "ms_per_step": 1e3 * VIEWS / cpu["value"], "cpu_baseline": cpu,
+                     "e2e": {"value": cpu["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "config": dict(base["config"], note="reference CUDA library absent: CPU oracle port timed instead")})
+        return base
+    names = ("means3D", "scales", "rotations", "opacities", "colors")
+    t = {k: torch.from_numpy(g[k]).to(device) for k in names}
+    bg = torch.zeros(3, device=device)
+    gcol = torch.from_numpy(gcol_np).to(device)
+    cam_t = [{k: (torch.from_numpy(c[k]).to(device) if isinstance(c[k], np.ndarray) else c[k]) for k in c} for c in cams]
+    rr = ref.RefRasterizer()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+
+    def step():
+        for v in range(VIEWS):
+            c = cam_t[v]
+            col, radii, n = rr.forward(t["means3D"], t["opacities"], t["colors"], c["viewmatrix"], c["projmatrix"],
+                                       c["campos"], W, H, c["tanfovx"], c["tanfovy"], bg, scales=t["scales"],
+                                       rotations=t["rotations"])
+            rr.backward(t["means3D"], t["colors"], c["viewmatrix"], c["projmatrix"], c["campos"], c["tanfovx"],
+                        c["tanfovy"], bg, radii, gcol[v], scales=t["scales"], rotations=t["rotations"])
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    evs = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
+    value = VIEWS / (ms / 1e3)
+    base.update({"value": value, "ms_per_step": ms, "ms_per_render": ms / VIEWS, "clocks": clocks,
+                 "cpu_baseline": {"value": value, "unit": "views/s", "cores": 0, "kind": "reference",
+                                  "sample": "the reference render path is CUDA-only: this arm runs its vendored CUDA "
+                                            "rasterizer (oracle/_ref, unmodified kernels + CUB) on the same B200, one "
+                                            "call per view with its blocking num_rendered read-back, no depth/opacity"},
+                 "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    rr.close()
+    return base
+
+
+def main():
+    args = parse()
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        if args.impl == "reference":
+            out = run_reference(args, rank, world, "cpu")
+            if out is not None:
+                print(json.dumps(out))
+            return
+        raise SystemExit("bench.py needs a CUDA device: the render path has no CPU implementation "
+                         "(the CPU oracle is test infrastructure and is only timed as cpu_baseline)")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if args.impl == "reference":
+        out = run_reference(args, rank, world, device)
+        if out is not None:
+            print(json.dumps(out))
+        return
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    out = run_ours(args, rank, world, device)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if rank == 0 and out is not None:
+        print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -8,7 +8,7 @@ The package holds only what the hot path needs:
   sharding.py     (sample, view) partition over ranks + the opacity-map all-gather
 """
 from .rasterizer import (GaussianRasterizationSettings, GaussianRasterizer, rasterize_gaussians, render_batch,  # noqa
-                         pack_cameras)
+                         pack_cameras, pack_camera_dicts)
 
 __all__ = ["GaussianRasterizationSettings", "GaussianRasterizer", "rasterize_gaussians", "render_batch",
-           "pack_cameras"]
+           "pack_cameras", "pack_camera_dicts"]

@@ -64,6 +64,17 @@ def pack_cameras(viewmatrix, projmatrix, campos, tanfovx, tanfovy):
     return torch.cat([vm, pm, cp, col(tanfovx), col(tanfovy), pad], dim=1).contiguous()
 
 
+def pack_camera_dicts(cams, device="cuda"):
+    """`pack_cameras` for a list of `ocrfdet_b200.cameras.make_camera` dicts (numpy) -> [V,40] on `device`."""
+    import numpy as np
+    vm = torch.from_numpy(np.stack([c["viewmatrix"] for c in cams])).to(device)
+    pm = torch.from_numpy(np.stack([c["projmatrix"] for c in cams])).to(device)
+    cp = torch.from_numpy(np.stack([c["campos"] for c in cams])).to(device)
+    tx = torch.tensor([c["tanfovx"] for c in cams], dtype=torch.float32).to(device)
+    ty = torch.tensor([c["tanfovy"] for c in cams], dtype=torch.float32).to(device)
+    return pack_cameras(vm, pm, cp, tx, ty)
+
+
 def _require_cuda(t, name):
     if not t.is_cuda:
         raise _lib.OcrfError("%s must be a CUDA tensor: the render path has no CPU implementation" % name)
@@ -112,6 +123,7 @@ class _RasterizeBatch(torch.autograd.Function):
                                         ptr(cov3D_precomp), ptr(opacities), ptr(shs), ptr(cams),
                                         C.c_float(cfg["scale_modifier"]), int(cfg["prefiltered"]), ptr(radii),
                                         ptr(geom)), "ocrf_preprocess_forward")
+        _stage("preprocess")
         capacity = cfg.get("pair_capacity")
         if capacity is None:
             # exact sizing: one 8-byte read-back per BATCH (the reference syncs once per view,
@@ -127,9 +139,11 @@ class _RasterizeBatch(torch.autograd.Function):
         binning = torch.empty(binl.total, dtype=torch.uint8, device=dev)
         check(L.ocrf_bin_forward(stream, C.byref(shape), C.c_uint64(capacity), ptr(radii), ptr(colors), int(use_sh),
                                  ptr(geom), ptr(binning), ptr(image)), "ocrf_bin_forward")
+        _stage("binning")
         check(L.ocrf_render_forward(stream, C.byref(shape), C.c_uint64(capacity), ptr(colors), int(use_sh), ptr(bg),
                                     ptr(geom), ptr(binning), ptr(image), ptr(color), ptr(depth), ptr(opac)),
               "ocrf_render_forward")
+        _stage("render_forward")
 
         global _LAST_HEADER, _LAST_STATE
         _LAST_HEADER = geom[ws.geom.header:ws.geom.header + 8]
@@ -152,6 +166,7 @@ class _RasterizeBatch(torch.autograd.Function):
         S, P, V, Cc = shape.S, shape.P, shape.V, shape.C
         dev = means3D.device
         stream = current_stream()
+        _stage("backward_begin")
         if g_color is None:
             g_color = torch.zeros((V, Cc, shape.H, shape.W), dtype=torch.float32, device=dev)
         g_color = g_color.contiguous()
@@ -161,6 +176,7 @@ class _RasterizeBatch(torch.autograd.Function):
         check(L.ocrf_render_backward(stream, C.byref(shape), C.c_uint64(ctx.capacity), ptr(colors), int(use_sh),
                                      ptr(bg), ptr(geom), ptr(binning), ptr(image), ptr(g_color), ptr(g_opac),
                                      ptr(ggrad), ptr(g_feat)), "ocrf_render_backward")
+        _stage("render_backward")
         g_means3D = torch.empty_like(means3D)
         g_means2D = torch.empty((V, P, 3), dtype=torch.float32, device=dev)
         g_opacities = torch.empty((S, P, 1), dtype=torch.float32, device=dev)
@@ -174,6 +190,7 @@ class _RasterizeBatch(torch.autograd.Function):
                                          ptr(radii), ptr(geom), ptr(ggrad), ptr(g_feat) if use_sh else None,
                                          ptr(g_means3D), ptr(g_means2D), ptr(g_opacities), ptr(g_scales), ptr(g_rots),
                                          ptr(g_cov), ptr(g_shs)), "ocrf_preprocess_backward")
+        _stage("preprocess_backward")
         return (g_means3D, g_means2D, g_shs, None if use_sh else g_feat, g_opacities, g_scales, g_rots, g_cov, None,
                 None, None)
 
@@ -181,6 +198,12 @@ class _RasterizeBatch(torch.autograd.Function):
 _LAST_HEADER = None  # geom header of the most recent forward (for check_overflow in capacity mode)
 KEEP_STATE = False   # tests / bench statistics: keep the workspaces of the most recent forward alive
 _LAST_STATE = None
+STAGE_HOOK = None    # bench: callable(name) invoked on the launching stream after each stage's launches
+
+
+def _stage(name):
+    if STAGE_HOOK is not None:
+        STAGE_HOOK(name)
 
 
 def last_state():

@@ -41,12 +41,7 @@ def settings_for(cam, bg, sh_degree=0, scale_modifier=1.0):
 
 
 def cams_tensor(cams):
-    vm = torch.from_numpy(np.stack([c["viewmatrix"] for c in cams])).cuda()
-    pm = torch.from_numpy(np.stack([c["projmatrix"] for c in cams])).cuda()
-    cp = torch.from_numpy(np.stack([c["campos"] for c in cams])).cuda()
-    tx = torch.tensor([c["tanfovx"] for c in cams], dtype=torch.float32).cuda()
-    ty = torch.tensor([c["tanfovy"] for c in cams], dtype=torch.float32).cuda()
-    return R.pack_cameras(vm, pm, cp, tx, ty)
+    return R.pack_camera_dicts(cams, "cuda")
 
 
 def rel_err(a, b):
