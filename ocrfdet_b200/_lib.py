@@ -13,6 +13,8 @@ OCRF_CAM_STRIDE = 40
 OCRF_RECORD_BYTES = 48
 OCRF_GGRAD_STRIDE = 8
 ABI_VERSION = 1
+OCRF_EINVAL = -1
+OCRF_ECAPACITY = -2
 
 EXPORTS = [
     "ocrf_abi_version", "ocrf_error_string", "ocrf_geom_layout", "ocrf_bin_layout", "ocrf_image_layout",

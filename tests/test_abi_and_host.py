@@ -1,0 +1,126 @@
+"""CPU suite: the C-ABI library loads and exports every symbol include/ocrf_raster.h declares, the
+layout queries work without a GPU, and the host-side mirror of the reference plugin behaves like it
+(names, defaults, argument errors) and fails loudly without CUDA."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from ocrfdet_b200 import _lib, cameras, rasterizer as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "ocrf_raster.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ocrf_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    names = _declared_functions()
+    assert len(names) >= 16
+    for n in names:
+        assert hasattr(L, n), "libocrf_raster.so does not export %s" % n
+    assert sorted(_lib.EXPORTS) == names
+    assert L.ocrf_abi_version() == _lib.ABI_VERSION
+    assert b"invalid" in L.ocrf_error_string(-1) and L.ocrf_error_string(0) == b"success"
+
+
+def test_layout_queries_and_argument_errors_without_gpu():
+    L = _lib.lib()
+    sh = _lib.OcrfShape(1, 100000, 6, 6, 704, 256, 3, 0, 0)
+    g, b, im = _lib.OcrfGeomLayout(), _lib.OcrfBinLayout(), _lib.OcrfImageLayout()
+    assert L.ocrf_geom_layout(C.byref(sh), 0, C.byref(g)) == 0
+    assert L.ocrf_bin_layout(C.byref(sh), 4_000_000, C.byref(b)) == 0
+    assert L.ocrf_image_layout(C.byref(sh), C.byref(im)) == 0
+    for lay in (g, b, im):
+        offs = [getattr(lay, f) for f, _ in lay._fields_ if f != "total"]
+        assert all(o % 128 == 0 for o in offs) and lay.total > max(offs)
+    assert g.conic_opacity - g.xy >= 6 * 100000 * 8 and b.records - b.vals_tmp >= 4_000_000 * 4
+    # 6 views x 704 tiles = 4224 -> 13 bits -> 45-bit keys; one view -> the reference's 42
+    assert L.ocrf_sort_end_bit(C.byref(sh)) == 45
+    assert L.ocrf_sort_end_bit(C.byref(_lib.OcrfShape(1, 10, 1, 1, 704, 256, 3, 0, 0))) == 42
+    assert L.ocrf_sort_end_bit(C.byref(_lib.OcrfShape(1, 10, 1, 1, 1408, 512, 3, 0, 0))) == 44
+    # odd pass count starts in the tmp half, even in the final half
+    assert b.keys_unsorted == b.keys  # 45 bits -> 6 passes (even)
+    assert L.ocrf_bin_layout(C.byref(sh), 1 << 30, C.byref(b)) == _lib.OCRF_ECAPACITY
+    # null pointers / bad sizes are rejected before any CUDA call
+    assert L.ocrf_preprocess_forward(None, C.byref(sh), None, None, None, None, None, None, None, 1.0, 0, None, None) == _lib.OCRF_EINVAL
+    assert L.ocrf_mark_visible(None, -1, None, None, None, None) == _lib.OCRF_EINVAL
+    assert L.ocrf_mark_visible(None, 0, None, None, None, None) == 0
+    assert L.ocrf_sort_pairs(None, 0, 42, None, None, None, None, None, None, None) == 0
+    assert L.ocrf_opacity_mask_forward(None, 1, 1, 4, 4, 2, None, None, None, None, None, None) == _lib.OCRF_EINVAL
+
+
+def test_settings_tuple_accepts_both_reference_flavours():
+    kw = dict(image_height=256, image_width=704, tanfovx=0.63, tanfovy=0.23, bg=torch.zeros(3), scale_modifier=1.0,
+              viewmatrix=torch.eye(4), projmatrix=torch.eye(4), sh_degree=3, campos=torch.zeros(3), prefiltered=False)
+    live = R.GaussianRasterizationSettings(**kw)                    # w-depth fork call site: 11 fields
+    vendored = R.GaussianRasterizationSettings(debug=True, **kw)    # vendored package: 12 fields
+    assert live.debug is False and vendored.debug is True and live._fields[:11] == vendored._fields[:11]
+    import diff_gaussian_rasterization as D
+    assert D.GaussianRasterizationSettings is R.GaussianRasterizationSettings
+    assert D.GaussianRasterizer is R.GaussianRasterizer
+
+
+def test_reference_argument_errors_and_loud_failure_without_cuda():
+    kw = dict(image_height=32, image_width=32, tanfovx=0.5, tanfovy=0.5, bg=torch.zeros(3), scale_modifier=1.0,
+              viewmatrix=torch.eye(4), projmatrix=torch.eye(4), sh_degree=0, campos=torch.zeros(3), prefiltered=False)
+    rast = R.GaussianRasterizer(R.GaussianRasterizationSettings(**kw))
+    m, o = torch.zeros(4, 3), torch.zeros(4, 1)
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        rast(means3D=m, means2D=m, opacities=o, scales=m, rotations=torch.zeros(4, 4))
+    with pytest.raises(Exception, match="excatly one of either SHs or precomputed colors"):
+        rast(means3D=m, means2D=m, opacities=o, shs=torch.zeros(4, 16, 3), colors_precomp=m, scales=m,
+             rotations=torch.zeros(4, 4))
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair"):
+        rast(means3D=m, means2D=m, opacities=o, colors_precomp=m)
+    with pytest.raises(Exception, match="exactly one of either scale/rotation pair"):
+        rast(means3D=m, means2D=m, opacities=o, colors_precomp=m, scales=m, rotations=torch.zeros(4, 4),
+             cov3D_precomp=torch.zeros(4, 6))
+    with pytest.raises(Exception, match="means3D must have dimensions"):
+        rast(means3D=torch.zeros(4, 2), means2D=m, opacities=o, colors_precomp=m, scales=m, rotations=torch.zeros(4, 4))
+    if not torch.cuda.is_available():
+        # CPU tensors: no silent fallback
+        with pytest.raises(_lib.OcrfError, match="no CPU implementation"):
+            rast(means3D=m, means2D=m, opacities=o, colors_precomp=m, scales=m, rotations=torch.zeros(4, 4))
+        with pytest.raises(_lib.OcrfError, match="no CPU implementation"):
+            rast.markVisible(m)
+        from ocrfdet_b200.opacity_lift import opacity_mask
+        with pytest.raises(_lib.OcrfError, match="no CPU implementation"):
+            opacity_mask(torch.zeros(1, 2, 4, 4), torch.zeros(1, 2, 7, 7), torch.zeros(1, 1, 4, 4))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "ocrfdet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f
+                assert "libocrf_oracle" not in txt and "libinria_ref" not in txt, f
+
+
+def test_camera_conventions():
+    K = np.array([[557.2, 0, 352.0], [0, 557.2, 128.0], [0, 0, 1]], np.float32)
+    cam = cameras.make_camera(K, np.eye(3), np.zeros(3), 704, 256)
+    assert abs(cam["tanfovx"] - 704 / (2 * 557.2)) < 1e-6 and abs(cam["tanfovy"] - 256 / (2 * 557.2)) < 1e-6
+    P = cam["projmatrix"].T  # back to column-vector convention
+    x = P @ np.array([0.0, 0.0, 10.0, 1.0], np.float32)
+    assert abs(x[0] / x[3]) < 1e-6 and abs(x[1] / x[3]) < 1e-6 and abs(x[3] - 10.0) < 1e-5
+    # the right image edge is NDC +1
+    x = P @ np.array([10.0 * cam["tanfovx"], 0.0, 10.0, 1.0], np.float32)
+    assert abs(x[0] / x[3] - 1.0) < 1e-5
+    ring = cameras.ego_ring_cameras()
+    assert len(ring) == 6
+    for c in ring:  # camera centre is (0, 0, 1.5) in ego coordinates
+        assert np.allclose(c["campos"], [0, 0, 1.5], atol=1e-5)
+    packed = R.pack_cameras(torch.from_numpy(np.stack([c["viewmatrix"] for c in ring])),
+                            torch.from_numpy(np.stack([c["projmatrix"] for c in ring])),
+                            torch.from_numpy(np.stack([c["campos"] for c in ring])), 0.63, torch.full((6,), 0.23))
+    assert packed.shape == (6, _lib.OCRF_CAM_STRIDE) and float(packed[3, 35]) == pytest.approx(0.63)
