@@ -82,14 +82,15 @@ typedef struct OcrfBinLayout {
   size_t vals_tmp;      /* uint32 [N] */
   size_t keys_unsorted; /* where duplicateWithKeys writes: keys_tmp when the pass count is odd, else keys */
   size_t vals_unsorted; /* (transient: overwritten by the sort) */
-  size_t records;       /* OCRF_RECORD_BYTES * N, sorted order (C == 3) or 32-byte records (C != 3) */
+  size_t records;       /* OCRF_RECORD_BYTES * N: per tile, the records that can reach a pixel of the tile */
   size_t histogram;     /* uint32 [8][256] */
   size_t sort_status;   /* uint32 [passes][sort_tiles][256] + tickets */
 } OcrfBinLayout;
 
 typedef struct OcrfImageLayout {
   size_t total;
-  size_t ranges;    /* uint2  [V*tiles] */
+  size_t ranges;    /* uint2  [V*tiles] [first, last+1) of the tile in the sorted list (the reference's ranges) */
+  size_t ranges_render; /* uint2 [V*tiles] [first, last+1) of the tile's culled records */
   size_t final_T;   /* float  [V*H*W] */
   size_t n_contrib; /* uint32 [V*H*W] */
   size_t max_contrib; /* uint32 [V*tiles] largest n_contrib of the tile (lets backward skip the tail) */

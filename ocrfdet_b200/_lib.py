@@ -40,7 +40,7 @@ class OcrfBinLayout(C.Structure):
 
 
 class OcrfImageLayout(C.Structure):
-    _fields_ = [(n, C.c_size_t) for n in ("total", "ranges", "final_T", "n_contrib", "max_contrib")]
+    _fields_ = [(n, C.c_size_t) for n in ("total", "ranges", "ranges_render", "final_T", "n_contrib", "max_contrib")]
 
 
 class OcrfError(RuntimeError):

@@ -79,52 +79,115 @@ __global__ void __launch_bounds__(256) duplicate_with_keys_kernel(OcrfShape sh, 
   }
 }
 
-// Boundary detection on the sorted keys (ranges zeroed beforehand) fused with the record gather.
-template <bool kLite>
-__global__ void __launch_bounds__(256) ranges_and_pack_kernel(OcrfShape sh, uint64_t n_cap, int use_sh,
-                                                              const uint32_t* __restrict__ header,
-                                                              const uint64_t* __restrict__ keys,
-                                                              const uint32_t* __restrict__ point_list,
-                                                              const float* __restrict__ depths,
-                                                              const float2* __restrict__ xy,
-                                                              const float4* __restrict__ conic_opacity,
-                                                              const float* __restrict__ rgb,
-                                                              const float* __restrict__ colors,
-                                                              uint2* __restrict__ ranges, void* __restrict__ records) {
+// One CTA per (view, tile): finds the tile's range in the sorted keys by binary search (replacing the
+// reference's memset + identifyTileRanges pass), then gathers each pair's blend inputs into 48-byte
+// records -- but only for Gaussians that can reach a pixel of THIS tile.  The reference's tile
+// rectangle is the bounding box of a 3-sigma circle of the LARGEST eigenvalue; about half of the
+// pairs it emits have alpha < 1/255 on every pixel of the tile.  They stay in the sorted list (keys,
+// point list and ranges remain bit-identical to the reference) but are dropped from the render
+// records by an exact-safe bound: the minimum of the conic's quadratic form over the tile's pixel
+// rectangle (continuous relaxation, evaluated on the four edges) gives the largest possible alpha;
+// a record is dropped only if that bound, with a 1e-3 relative margin for rounding, is below 1/255.
+// Each record keeps its 1-based position in the full list so n_contrib is the reference's value.
+__global__ void __launch_bounds__(256) ranges_cull_pack_kernel(OcrfShape sh, uint64_t n_cap, int use_sh, int has_rgb,
+                                                               const uint32_t* __restrict__ header,
+                                                               const uint64_t* __restrict__ keys,
+                                                               const uint32_t* __restrict__ point_list,
+                                                               const float* __restrict__ depths,
+                                                               const float2* __restrict__ xy,
+                                                               const float4* __restrict__ conic_opacity,
+                                                               const float* __restrict__ rgb,
+                                                               const float* __restrict__ colors,
+                                                               uint2* __restrict__ ranges,
+                                                               uint2* __restrict__ ranges_render,
+                                                               Record* __restrict__ records) {
+  __shared__ uint32_t s_bounds[2];
+  __shared__ uint32_t s_warp[8];
   const uint32_t total = header[HDR_NUM_PAIRS];
   const uint32_t n = (uint64_t)total <= n_cap ? total : 0u;
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const uint32_t cur = (uint32_t)(keys[i] >> 32);
-  if (i == 0) {
-    ranges[cur].x = 0;
-  } else {
-    const uint32_t prev = (uint32_t)(keys[i - 1] >> 32);
-    if (cur != prev) {
-      ranges[prev].y = i;
-      ranges[cur].x = i;
+  const uint32_t vt = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid < 2) {  // lower bound of vt (tid 0) and of vt + 1 (tid 1) in the keys' upper words
+    const uint32_t target = vt + tid;
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi) >> 1;
+      if ((uint32_t)(keys[mid] >> 32) < target) lo = mid + 1; else hi = mid;
     }
+    s_bounds[tid] = lo;
   }
-  if (i == n - 1) ranges[cur].y = n;
+  __syncthreads();
+  const uint32_t lo = s_bounds[0], hi = s_bounds[1];
+  if (tid == 0) ranges[vt] = lo < hi ? make_uint2(lo, hi) : make_uint2(0u, 0u);  // empty tiles read (0,0) as after the memset
 
-  const int tiles = ceil_div(sh.W, TILE) * ceil_div(sh.H, TILE);
-  const uint32_t v = cur / (uint32_t)tiles;
-  const uint32_t id = point_list[i];
-  const size_t g = (size_t)v * sh.P + id;
-  const float2 p = xy[g];
-  const float4 co = conic_opacity[g];
-  const float d = depths[g];
-  if (kLite) {
-    float4* out = reinterpret_cast<float4*>(records) + (size_t)i * 2;
-    out[0] = make_float4(p.x, p.y, co.x, co.y);
-    out[1] = make_float4(co.z, co.w, d, __uint_as_float(id));
-  } else {
-    const float* c = use_sh ? rgb + g * 3 : colors + ((size_t)(v / sh.views_per_sample) * sh.P + id) * 3;
-    float4* out = reinterpret_cast<float4*>(records) + (size_t)i * 3;
-    out[0] = make_float4(p.x, p.y, co.x, co.y);
-    out[1] = make_float4(co.z, co.w, d, __ldg(c));
-    out[2] = make_float4(__ldg(c + 1), __ldg(c + 2), __uint_as_float(id), 0.f);
+  const int gx = ceil_div(sh.W, TILE), tiles = gx * ceil_div(sh.H, TILE);
+  const uint32_t v = vt / (uint32_t)tiles;
+  const int t = (int)(vt - v * tiles);
+  const int tx = t % gx, ty = t / gx;
+  const float px0 = (float)(tx * TILE), px1 = (float)min(tx * TILE + TILE - 1, sh.W - 1);
+  const float py0 = (float)(ty * TILE), py1 = (float)min(ty * TILE + TILE - 1, sh.H - 1);
+  const size_t sample_base = (size_t)(v / sh.views_per_sample) * sh.P;
+
+  uint32_t kept_total = 0;
+  for (uint32_t base = lo; base < hi; base += 256) {
+    const uint32_t i = base + tid;
+    bool keep = false;
+    uint32_t id = 0;
+    float2 p = make_float2(0.f, 0.f);
+    float4 co = make_float4(0.f, 0.f, 0.f, 0.f);
+    size_t g = 0;
+    if (i < hi) {
+      id = point_list[i];
+      g = (size_t)v * sh.P + id;
+      p = xy[g];
+      co = conic_opacity[g];
+      // d = mean - pixel ranges over [dxl, dxh] x [dyl, dyh]
+      const float dxl = p.x - px1, dxh = p.x - px0, dyl = p.y - py1, dyh = p.y - py0;
+      float qmin = 0.f;
+      const bool inside = dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f;
+      if (!inside) {
+        const float A = co.x, B = co.y, Cc = co.z;
+        float q = INFINITY;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+          const float ex = e ? dxh : dxl;
+          const float sy = fminf(dyh, fmaxf(dyl, -B * ex / Cc));
+          q = fminf(q, A * ex * ex + 2.f * B * ex * sy + Cc * sy * sy);
+          const float ey = e ? dyh : dyl;
+          const float sx = fminf(dxh, fmaxf(dxl, -B * ey / A));
+          q = fminf(q, A * sx * sx + 2.f * B * sx * ey + Cc * ey * ey);
+        }
+        qmin = q;
+      }
+      const float alpha_max = co.w * __expf(-0.5f * qmin) * 1.001f;
+      keep = !(alpha_max < 1.0f / 255.0f);  // NaN anywhere keeps the record
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    uint32_t off = 0, chunk_total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      const uint32_t c = s_warp[w];
+      if (w < warp) off += c;
+      chunk_total += c;
+    }
+    if (keep) {
+      const uint32_t dst = lo + kept_total + off + __popc(bal & ((1u << lane) - 1));
+      float r = 0.f, gg = 0.f, bb = 0.f;
+      if (has_rgb) {
+        const float* c = use_sh ? rgb + g * 3 : colors + (sample_base + id) * 3;
+        r = __ldg(c); gg = __ldg(c + 1); bb = __ldg(c + 2);
+      }
+      float4* out = reinterpret_cast<float4*>(records + dst);
+      out[0] = make_float4(p.x, p.y, co.x, co.y);
+      out[1] = make_float4(co.z, co.w, __uint_as_float(i - lo + 1), r);
+      out[2] = make_float4(gg, bb, __uint_as_float(id), depths[g]);
+    }
+    kept_total += chunk_total;
+    __syncthreads();
   }
+  if (tid == 0) ranges_render[vt] = make_uint2(lo, lo + kept_total);
 }
 
 }  // namespace ocrf
@@ -156,7 +219,7 @@ extern "C" int ocrf_bin_layout(const OcrfShape* sh, uint64_t num_pairs, OcrfBinL
   out->keys_unsorted = (passes & 1) ? out->keys_tmp : out->keys;
   out->vals_unsorted = (passes & 1) ? out->vals_tmp : out->point_list;
   out->records = off;
-  off = align128(off + n * (sh->C == 3 ? OCRF_RECORD_BYTES : 32));
+  off = align128(off + n * OCRF_RECORD_BYTES);
   out->histogram = off;  // start of the sort workspace
   const SortWs w = sort_ws_layout(n);
   out->sort_status = off + w.status;
@@ -171,6 +234,7 @@ extern "C" int ocrf_image_layout(const OcrfShape* sh, OcrfImageLayout* out) {
   const size_t pix = (size_t)sh->V * sh->W * sh->H;
   size_t off = 0;
   out->ranges = off;      off = align128(off + tiles * 8);
+  out->ranges_render = off; off = align128(off + tiles * 8);
   out->max_contrib = off; off = align128(off + tiles * 4);
   out->final_T = off;     off = align128(off + pix * 4);
   out->n_contrib = off;   off = align128(off + pix * 4);
@@ -191,8 +255,10 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
   if (rc) return rc;
   ocrf_image_layout(sh, &I);
   const size_t tiles = (size_t)sh->V * tiles_x(*sh) * tiles_y(*sh);
-  cudaMemsetAsync(at<char>(image_ws, I.ranges), 0, tiles * 8, st);
-  if (pair_capacity == 0) return 0;
+  if (pair_capacity == 0) {  // nothing can be rendered: both range tables read (0,0)
+    cudaMemsetAsync(at<char>(image_ws, I.ranges), 0, I.max_contrib - I.ranges, st);
+    return 0;
+  }
 
   uint32_t* header = at<uint32_t>(geom_ws, G.header);
   const size_t n = (size_t)sh->V * sh->P;
@@ -210,18 +276,11 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
                          at<char>(bin_ws, B.histogram));
   if (rc) return rc;
 
-  const unsigned grid = (unsigned)((pair_capacity + 255) / 256);
-  if (sh->C == 3) {
-    ranges_and_pack_kernel<false><<<grid, 256, 0, st>>>(
-        *sh, pair_capacity, use_sh, header, at<uint64_t>(bin_ws, B.keys), at<uint32_t>(bin_ws, B.point_list),
-        at<float>(geom_ws, G.depths), at<float2>(geom_ws, G.xy), at<float4>(geom_ws, G.conic_opacity),
-        at<float>(geom_ws, G.rgb), colors, at<uint2>(image_ws, I.ranges), at<char>(bin_ws, B.records));
-  } else {
-    ranges_and_pack_kernel<true><<<grid, 256, 0, st>>>(
-        *sh, pair_capacity, use_sh, header, at<uint64_t>(bin_ws, B.keys), at<uint32_t>(bin_ws, B.point_list),
-        at<float>(geom_ws, G.depths), at<float2>(geom_ws, G.xy), at<float4>(geom_ws, G.conic_opacity),
-        at<float>(geom_ws, G.rgb), colors, at<uint2>(image_ws, I.ranges), at<char>(bin_ws, B.records));
-  }
+  ranges_cull_pack_kernel<<<(unsigned)tiles, 256, 0, st>>>(
+      *sh, pair_capacity, use_sh, sh->C == 3, header, at<uint64_t>(bin_ws, B.keys), at<uint32_t>(bin_ws, B.point_list),
+      at<float>(geom_ws, G.depths), at<float2>(geom_ws, G.xy), at<float4>(geom_ws, G.conic_opacity),
+      at<float>(geom_ws, G.rgb), colors, at<uint2>(image_ws, I.ranges), at<uint2>(image_ws, I.ranges_render),
+      at<Record>(bin_ws, B.records));
   OCRF_CHECK_LAST();
   return 0;
 }

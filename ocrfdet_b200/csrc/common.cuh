@@ -29,20 +29,15 @@ static_assert(sizeof(Camera) == OCRF_CAM_STRIDE * 4, "camera record size");
 
 // One (tile, Gaussian) pair as the blend kernels consume it (C == 3).
 struct __align__(16) Record {
-  float x, y, cA, cB;     // pixel-space mean, conic A, B
-  float cC, op, depth, r; // conic C, opacity, view depth, red
-  float g, b;             // green, blue
-  uint32_t id;            // Gaussian index inside its sample
-  uint32_t pad;
+  float x, y, cA, cB;  // pixel-space mean, conic A, B            (read for every test)
+  float cC, op;        // conic C, opacity                         (read for every test)
+  uint32_t orig;       // 1-based position in the tile's full (unculled) sorted list == the reference's "contributor"
+  float r;             // red
+  float g, b;          // green, blue                              (read only when blending)
+  uint32_t id;         // Gaussian index inside its sample
+  float depth;         // view-space depth (median-depth output)
 };
 static_assert(sizeof(Record) == OCRF_RECORD_BYTES, "record size");
-
-// Same for C != 3: features are gathered by id.
-struct __align__(16) RecordLite {
-  float x, y, cA, cB;
-  float cC, op, depth;
-  uint32_t id;
-};
 
 __host__ __device__ inline size_t align128(size_t x) { return (x + 127) & ~size_t(127); }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }

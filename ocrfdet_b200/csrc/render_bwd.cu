@@ -17,7 +17,7 @@
 
 namespace ocrf {
 
-constexpr int BWD_BATCH = 256;
+template <int PPT> struct BwdBatch { static constexpr int value = PPT == 1 ? 64 : 128; };  // records per stage
 constexpr int BWD_ACC = 12;  // floats per record accumulator row (9 used)
 
 __device__ __forceinline__ float ex2_approx_b(float x) {
@@ -54,15 +54,20 @@ __device__ __forceinline__ float butterfly8(float (&v)[8], int lane) {
 
 template <int PPT>
 __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
-    int W, int H, int P, int views_per_sample, int colors_per_view, const uint2* __restrict__ ranges,
+    int W, int H, int P, int views_per_sample, int colors_per_view, const uint2* __restrict__ ranges /* culled lists */,
     const Record* __restrict__ records, const float* __restrict__ bg, const float* __restrict__ final_T,
     const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ max_contrib,
     const float* __restrict__ dL_dpix, const float* __restrict__ dL_dopa, float* __restrict__ ggrad,
     float* __restrict__ dL_dcolors) {
   constexpr int NT = TILE_PIX / PPT;
+  constexpr int NW = NT / 32;
+  constexpr int BWD_BATCH = BwdBatch<PPT>::value;
+  // Per-warp partial sums of the current batch: every warp visits every record exactly once per
+  // batch, so it can STORE its reduced 9-vector (no shared-memory atomics -- float atomicAdd on
+  // shared memory compiles to a CAS loop) and a per-warp bit mask says which rows are valid.
   __shared__ __align__(128) Record s_rec[2][BWD_BATCH];
-  __shared__ __align__(16) float s_acc[BWD_BATCH][BWD_ACC];
-  __shared__ uint32_t s_touched[BWD_BATCH];
+  __shared__ __align__(16) float s_acc[NW][BWD_BATCH][BWD_ACC];
+  __shared__ uint32_t s_touched[NW][BWD_BATCH / 32];
   __shared__ __align__(8) uint64_t s_bar[2];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -79,7 +84,7 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
   const size_t HW = (size_t)H * W;
   const int bx = (warp & 1) * 8 + (lane & 7);
   const int by = (warp >> 1) * (4 * PPT) + (lane >> 3);
-  float fx[PPT], fy[PPT], T[PPT], Tf[PPT], g0[PPT], g1[PPT], g2[PPT], gop[PPT], bgdot[PPT];
+  float fx[PPT], fy[PPT], T[PPT], Tf[PPT], g0[PPT], g1[PPT], g2[PPT], gob[PPT];
   float a0[PPT], a1[PPT], a2[PPT], lc0[PPT], lc1[PPT], lc2[PPT], last_alpha[PPT];
   int nc[PPT];
   const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
@@ -96,13 +101,14 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
     g0[p] = inside ? dL_dpix[((size_t)view * 3 + 0) * HW + pix] : 0.f;
     g1[p] = inside ? dL_dpix[((size_t)view * 3 + 1) * HW + pix] : 0.f;
     g2[p] = inside ? dL_dpix[((size_t)view * 3 + 2) * HW + pix] : 0.f;
-    gop[p] = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
-    bgdot[p] = bg0 * g0[p] + bg1 * g1[p] + bg2 * g2[p];
+    const float gop = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
+    // d(out)/d(alpha_i) through the final transmittance: opacity map (+) and background (-)
+    gob[p] = Tf[p] * (gop - (bg0 * g0[p] + bg1 * g1[p] + bg2 * g2[p]));
     a0[p] = a1[p] = a2[p] = lc0[p] = lc1[p] = lc2[p] = last_alpha[p] = 0.f;
   }
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
 
-  // round r covers local list indices [lo_r, hi_r) with hi_r = mc - r*BATCH (back to front)
+  // round r covers culled-list indices [lo_r, hi_r) with hi_r = mc - r*BATCH (back to front)
   auto issue = [&](int r) {
     const int hi = mc - r * BWD_BATCH;
     const int lo = max(0, hi - BWD_BATCH);
@@ -115,8 +121,6 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
     mbar_init(&s_bar[1], 1);
     mbar_fence_init();
   }
-  for (int i = tid; i < BWD_BATCH * BWD_ACC; i += NT) (&s_acc[0][0])[i] = 0.f;
-  for (int i = tid; i < BWD_BATCH; i += NT) s_touched[i] = 0;
   __syncthreads();
   if (tid == 0) {
     issue(0);
@@ -130,80 +134,94 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
     const int cnt = hi - lo;
     mbar_wait(&s_bar[st], (r >> 1) & 1);
     const float4* rec4 = reinterpret_cast<const float4*>(&s_rec[st][0]);
+    uint32_t touched = 0;  // warp-uniform: bit (j & 31) set when this warp reduced record j
 
     for (int j = cnt - 1; j >= 0; j--) {
-      const int k = lo + j;  // position in the tile list; pixel p blended it iff k < nc[p] and tests pass
+      // pixel p blended this record iff its reference list position (b.z) <= n_contrib[p] and the tests pass
       const float4 a = rec4[3 * j], b = rec4[3 * j + 1];
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      float v8 = 0.f;
+      float dx[PPT], dy[PPT], G[PPT], alpha[PPT];
+      bool ok[PPT];
       bool any = false;
-      float2 c = make_float2(0.f, 0.f);
 #pragma unroll
       for (int p = 0; p < PPT; p++) {
-        const float dx = a.x - fx[p], dy = a.y - fy[p];
-        const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-        const float G = ex2_approx_b(power * 1.4426950408889634f);
-        const float alpha = fminf(0.99f, b.y * G);
-        const bool ok = k < nc[p] && power <= 0.0f && alpha >= 1.0f / 255.0f;
-        if (!ok) continue;
-        if (!any) c = *reinterpret_cast<const float2*>(&rec4[3 * j + 2]);
-        any = true;
-        const float rcp = __fdividef(1.f, 1.f - alpha);
-        T[p] *= rcp;
-        const float w = alpha * T[p];
-        a0[p] = last_alpha[p] * lc0[p] + (1.f - last_alpha[p]) * a0[p];
-        a1[p] = last_alpha[p] * lc1[p] + (1.f - last_alpha[p]) * a1[p];
-        a2[p] = last_alpha[p] * lc2[p] + (1.f - last_alpha[p]) * a2[p];
-        lc0[p] = b.w; lc1[p] = c.x; lc2[p] = c.y;
-        float dL_dalpha = (b.w - a0[p]) * g0[p] + (c.x - a1[p]) * g1[p] + (c.y - a2[p]) * g2[p];
-        dL_dalpha *= T[p];
-        last_alpha[p] = alpha;
-        dL_dalpha += (Tf[p] * rcp) * (gop[p] - bgdot[p]);
-        const float dL_dG = b.y * dL_dalpha;
-        const float gdx = G * dx, gdy = G * dy;
-        const float dG_ddelx = -gdx * a.z - gdy * a.w;
-        const float dG_ddely = -gdy * b.x - gdx * a.w;
-        v[0] += dL_dG * dG_ddelx * ddelx_dx;
-        v[1] += dL_dG * dG_ddely * ddely_dy;
-        v[2] += -0.5f * gdx * dx * dL_dG;
-        v[3] += -0.5f * gdx * dy * dL_dG;
-        v[4] += -0.5f * gdy * dy * dL_dG;
-        v[5] += G * dL_dalpha;
-        v[6] += w * g0[p];
-        v[7] += w * g1[p];
-        v8 += w * g2[p];
+        dx[p] = a.x - fx[p];
+        dy[p] = a.y - fy[p];
+        const float power = -0.5f * (a.z * dx[p] * dx[p] + b.x * dy[p] * dy[p]) - a.w * dx[p] * dy[p];
+        G[p] = ex2_approx_b(power * 1.4426950408889634f);
+        alpha[p] = fminf(0.99f, b.y * G[p]);
+        ok[p] = (int)__float_as_uint(b.z) <= nc[p] && power <= 0.0f && alpha[p] >= 1.0f / 255.0f;
+        any = any || ok[p];
       }
-      if (!__any_sync(0xffffffffu, any)) continue;
-      const float r8 = butterfly8(v, lane);
-      const float r1 = warp_sum(v8);
-      if ((lane & 3) == 0) atomicAdd(&s_acc[j][lane >> 2], r8);
-      if (lane == 1) {
-        atomicAdd(&s_acc[j][8], r1);
-        s_touched[j] = 1;
+      if (__any_sync(0xffffffffu, any)) {
+        const float2 c = *reinterpret_cast<const float2*>(&rec4[3 * j + 2]);
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float v8 = 0.f;
+#pragma unroll
+        for (int p = 0; p < PPT; p++) {
+          if (!ok[p]) continue;
+          const float rcp = __fdividef(1.f, 1.f - alpha[p]);
+          T[p] *= rcp;
+          const float w = alpha[p] * T[p];
+          a0[p] = last_alpha[p] * lc0[p] + (1.f - last_alpha[p]) * a0[p];
+          a1[p] = last_alpha[p] * lc1[p] + (1.f - last_alpha[p]) * a1[p];
+          a2[p] = last_alpha[p] * lc2[p] + (1.f - last_alpha[p]) * a2[p];
+          lc0[p] = b.w; lc1[p] = c.x; lc2[p] = c.y;
+          float dL_dalpha = (b.w - a0[p]) * g0[p] + (c.x - a1[p]) * g1[p] + (c.y - a2[p]) * g2[p];
+          dL_dalpha *= T[p];
+          last_alpha[p] = alpha[p];
+          dL_dalpha += gob[p] * rcp;
+          const float dL_dG = b.y * dL_dalpha;
+          const float gdx = G[p] * dx[p], gdy = G[p] * dy[p];
+          const float dG_ddelx = -gdx * a.z - gdy * a.w;
+          const float dG_ddely = -gdy * b.x - gdx * a.w;
+          v[0] += dL_dG * dG_ddelx * ddelx_dx;
+          v[1] += dL_dG * dG_ddely * ddely_dy;
+          v[2] += -0.5f * gdx * dx[p] * dL_dG;
+          v[3] += -0.5f * gdx * dy[p] * dL_dG;
+          v[4] += -0.5f * gdy * dy[p] * dL_dG;
+          v[5] += G[p] * dL_dalpha;
+          v[6] += w * g0[p];
+          v[7] += w * g1[p];
+          v8 += w * g2[p];
+        }
+        const float r8 = butterfly8(v, lane);
+        const float r1 = warp_sum(v8);
+        if ((lane & 3) == 0) s_acc[warp][j][lane >> 2] = r8;
+        if (lane == 1) s_acc[warp][j][8] = r1;
+        touched |= 1u << (j & 31);
+      }
+      if ((j & 31) == 0) {
+        if (lane == 0) s_touched[warp][j >> 5] = touched;
+        touched = 0;
       }
     }
-    __syncthreads();  // accumulators of this batch are complete
-    // flush: one thread per record (reads the ids still sitting in stage `st`)
+    __syncthreads();  // partial sums of this batch are complete
+    // flush: one thread per record adds the valid warp rows and issues the global reductions
     for (int j = tid; j < cnt; j += NT) {
-      if (!s_touched[j]) continue;
-      s_touched[j] = 0;
+      float q[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      bool hit = false;
+#pragma unroll
+      for (int w = 0; w < NW; w++) {
+        if ((s_touched[w][j >> 5] >> (j & 31)) & 1u) {
+          hit = true;
+          const float4 q0 = *reinterpret_cast<const float4*>(&s_acc[w][j][0]);
+          const float4 q1 = *reinterpret_cast<const float4*>(&s_acc[w][j][4]);
+          q[0] += q0.x; q[1] += q0.y; q[2] += q0.z; q[3] += q0.w;
+          q[4] += q1.x; q[5] += q1.y; q[6] += q1.z; q[7] += q1.w;
+          q[8] += s_acc[w][j][8];
+        }
+      }
+      if (!hit) continue;
       const uint32_t id = s_rec[st][j].id;
-      float* row = &s_acc[j][0];
-      const float4 q0 = *reinterpret_cast<const float4*>(row);
-      const float4 q1 = *reinterpret_cast<const float4*>(row + 4);
-      const float q2 = row[8];
-      *reinterpret_cast<float4*>(row) = make_float4(0.f, 0.f, 0.f, 0.f);
-      *reinterpret_cast<float4*>(row + 4) = make_float4(0.f, 0.f, 0.f, 0.f);
-      row[8] = 0.f;
       float* gg = ggrad + ((size_t)view * P + id) * OCRF_GGRAD_STRIDE;
-      atomicAdd(reinterpret_cast<float4*>(gg), q0);
-      atomicAdd(reinterpret_cast<float2*>(gg + 4), make_float2(q1.x, q1.y));
+      atomicAdd(reinterpret_cast<float4*>(gg), make_float4(q[0], q[1], q[2], q[3]));
+      atomicAdd(reinterpret_cast<float2*>(gg + 4), make_float2(q[4], q[5]));
       float* gc = dL_dcolors + ((size_t)(colors_per_view ? view : view / views_per_sample) * P + id) * 3;
-      atomicAdd(gc, q1.z);
-      atomicAdd(gc + 1, q1.w);
-      atomicAdd(gc + 2, q2);
+      atomicAdd(gc, q[6]);
+      atomicAdd(gc + 1, q[7]);
+      atomicAdd(gc + 2, q[8]);
     }
-    __syncthreads();  // stage `st` fully consumed: only now may round r+2 land in it
+    __syncthreads();  // stage `st` and the partial sums are consumed: only now may round r+2 land
     if (tid == 0 && r + 2 < rounds) issue(r + 2);
   }
 }
@@ -213,7 +231,7 @@ constexpr int BWDG_BATCH = 128;
 
 __global__ void __launch_bounds__(TILE_PIX) render_backward_generic_kernel(
     int W, int H, int C, int P, int views_per_sample, const uint2* __restrict__ ranges,
-    const RecordLite* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
+    const Record* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
     const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
     const uint32_t* __restrict__ max_contrib, const float* __restrict__ dL_dpix, const float* __restrict__ dL_dopa,
     float* __restrict__ ggrad, float* __restrict__ dL_dfeats) {
@@ -222,7 +240,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_generic_kernel(
   // on.  The per-channel suffix state "accum_rec" (C floats per pixel) lives in dynamic shared
   // memory; the "last colour" of the recurrence is re-read from the feature table through the id of
   // the previously blended record instead of being stored.
-  __shared__ __align__(16) RecordLite s_rec[BWDG_BATCH];
+  __shared__ __align__(16) Record s_rec[BWDG_BATCH];
   __shared__ __align__(16) float s_acc[BWDG_BATCH][8];
   extern __shared__ float s_dyn[];  // [TILE_PIX][C] suffix accumulators "accum_rec" (last colour is re-read)
 
@@ -268,12 +286,12 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_generic_kernel(
       const int k = lo + j;
       const float4 a = reinterpret_cast<const float4*>(&s_rec[j])[0];
       const float4 b = reinterpret_cast<const float4*>(&s_rec[j])[1];
-      const uint32_t id = __float_as_uint(b.w);
+      const uint32_t id = s_rec[j].id;
       const float dx = a.x - fx, dy = a.y - fy;
       const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
       const float G = ex2_approx_b(power * 1.4426950408889634f);
       const float alpha = fminf(0.99f, b.y * G);
-      const bool ok = k < nc && power <= 0.0f && alpha >= 1.0f / 255.0f;
+      const bool ok = (int)s_rec[j].orig <= nc && power <= 0.0f && alpha >= 1.0f / 255.0f;
       if (!__any_sync(0xffffffffu, ok)) continue;
       float rcp = 1.f, w = 0.f, dL_dalpha = 0.f;
       if (ok) {
@@ -351,14 +369,18 @@ extern "C" int ocrf_render_backward(void* stream, const OcrfShape* sh, uint64_t 
   if (rc) return rc;
   ocrf_image_layout(sh, &I);
   const dim3 grid(tiles_x(*sh), tiles_y(*sh), sh->V);
-  const uint2* ranges = at<uint2>(image_ws, I.ranges);
+  const uint2* ranges = at<uint2>(image_ws, I.ranges_render);
   const float* fT = at<float>(image_ws, I.final_T);
   const uint32_t* nc = at<uint32_t>(image_ws, I.n_contrib);
   const uint32_t* mc = at<uint32_t>(image_ws, I.max_contrib);
   if (sh->C == 3) {
-    static const int ppt = env_int_b("OCRF_BWD_PPT", 1);
+    static const int ppt = env_int_b("OCRF_BWD_PPT", 4);
     const Record* rec = at<Record>(bin_ws, B.records);
-    if (ppt == 2)
+    if (ppt == 4)
+      render_backward_c3_kernel<4><<<grid, TILE_PIX / 4, 0, st>>>(sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
+                                                                  ranges, rec, bg, fT, nc, mc, dL_dcolor,
+                                                                  dL_dopacity_map, ggrad, dL_dcolors);
+    else if (ppt == 2)
       render_backward_c3_kernel<2><<<grid, TILE_PIX / 2, 0, st>>>(sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
                                                                   ranges, rec, bg, fT, nc, mc, dL_dcolor,
                                                                   dL_dopacity_map, ggrad, dL_dcolors);
@@ -374,7 +396,7 @@ extern "C" int ocrf_render_backward(void* stream, const OcrfShape* sh, uint64_t 
                                          (int)dyn);
     if (e != cudaSuccess) return (int)e;
     render_backward_generic_kernel<<<grid, TILE_PIX, dyn, st>>>(
-        sh->W, sh->H, sh->C, sh->P, sh->views_per_sample, ranges, at<RecordLite>(bin_ws, B.records), colors, bg, fT, nc,
+        sh->W, sh->H, sh->C, sh->P, sh->views_per_sample, ranges, at<Record>(bin_ws, B.records), colors, bg, fT, nc,
         mc, dL_dcolor, dL_dopacity_map, ggrad, dL_dcolors);
   }
   OCRF_CHECK_LAST();

@@ -30,9 +30,10 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 template <int PPT>
 __global__ void __launch_bounds__(TILE_PIX / PPT) render_forward_c3_kernel(
-    int W, int H, const uint2* __restrict__ ranges, const Record* __restrict__ records, const float* __restrict__ bg,
-    float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ max_contrib,
-    float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_opacity) {
+    int W, int H, const uint2* __restrict__ ranges /* culled lists */, const Record* __restrict__ records,
+    const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+    uint32_t* __restrict__ max_contrib, float* __restrict__ out_color, float* __restrict__ out_depth,
+    float* __restrict__ out_opacity) {
   constexpr int NT = TILE_PIX / PPT;
   __shared__ __align__(128) Record s_rec[2][FWD_BATCH];
   __shared__ __align__(8) uint64_t s_bar[2];
@@ -81,7 +82,8 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_forward_c3_kernel(
   }
 
   float T[PPT], D[PPT], C0[PPT], C1[PPT], C2[PPT];
-  uint32_t last[PPT];
+  uint32_t last[PPT];   // reference numbering (position in the unculled list), stored as n_contrib
+  uint32_t lastc = 0;   // position in the culled list of the last record any of my pixels blended
 #pragma unroll
   for (int p = 0; p < PPT; p++) {
     T[p] = 1.f; D[p] = 15.f; C0[p] = C1[p] = C2[p] = 0.f; last[p] = 0;
@@ -114,7 +116,7 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_forward_c3_kernel(
           any_blend = any_blend || ok;
         }
         if (!__any_sync(0xffffffffu, any_blend)) continue;  // nobody in the warp blends this Gaussian
-        const float2 c = *reinterpret_cast<const float2*>(&rec4[3 * j + 2]);
+        const float4 c = rec4[3 * j + 2];  // g, b, id, depth
         bool newly_done = false;
 #pragma unroll
         for (int p = 0; p < PPT; p++) {
@@ -126,10 +128,11 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_forward_c3_kernel(
           C0[p] = fmaf(b.w, w, C0[p]);
           C1[p] = fmaf(c.x, w, C1[p]);
           C2[p] = fmaf(c.y, w, C2[p]);
-          if (blend && T[p] > 0.5f && test_T < 0.5f) D[p] = b.z;
+          if (blend && T[p] > 0.5f && test_T < 0.5f) D[p] = c.w;
           if (blend) {
             T[p] = test_T;
-            last[p] = (uint32_t)(r * FWD_BATCH + j + 1);
+            last[p] = __float_as_uint(b.z);
+            lastc = (uint32_t)(r * FWD_BATCH + j + 1);
           }
           done[p] = done[p] || stop;
           newly_done = newly_done || stop;
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_forward_c3_kernel(
     const size_t pix = (size_t)py[p] * W + px[p];
     final_T[view * HW + pix] = T[p];
     n_contrib[view * HW + pix] = last[p];
-    my_max = max(my_max, last[p]);
+    my_max = max(my_max, lastc);
     float* oc = out_color + (size_t)view * 3 * HW + pix;
     oc[0] = C0[p] + T[p] * bg[0];
     oc[HW] = C1[p] + T[p] * bg[1];
@@ -184,10 +187,10 @@ constexpr int FWDG_BATCH = 128;
 
 __global__ void __launch_bounds__(TILE_PIX) render_forward_generic_kernel(
     int W, int H, int C, int P, int views_per_sample, const uint2* __restrict__ ranges,
-    const RecordLite* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
+    const Record* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ max_contrib,
     float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_opacity) {
-  __shared__ __align__(16) RecordLite s_rec[FWDG_BATCH];
+  __shared__ __align__(16) Record s_rec[FWDG_BATCH];
   __shared__ __align__(16) float s_feat[FWDG_BATCH][FWD_CK];
   __shared__ uint32_t s_max;
 
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_generic_kernel(
     const int ck = min(FWD_CK, C - c0);
     bool done = !inside;
     float T = 1.f, D = 15.f;
-    uint32_t last = 0;
+    uint32_t last = 0, lastc = 0;
     float acc[FWD_CK];
 #pragma unroll
     for (int k = 0; k < FWD_CK; k++) acc[k] = 0.f;
@@ -221,35 +224,39 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_generic_kernel(
       if (num_done == TILE_PIX) break;
       const int cnt = min(FWDG_BATCH, n - r * FWDG_BATCH);
       if (tid < cnt) s_rec[tid] = records[range.x + r * FWDG_BATCH + tid];
-      // gather the feature chunk: 4 threads per Gaussian when the rows are 16-byte aligned
       for (int e = tid; e < cnt * FWD_CK; e += TILE_PIX) {
         const int j = e / FWD_CK, k = e - j * FWD_CK;
         const uint32_t id = records[range.x + r * FWDG_BATCH + j].id;
         s_feat[j][k] = k < ck ? __ldg(fbase + (size_t)id * C + c0 + k) : 0.f;
       }
       __syncthreads();
-      for (int j = 0; !done && j < cnt; j++) {
+      if (__all_sync(0xffffffffu, done)) continue;
+      for (int j = 0; j < cnt; j++) {  // warp-uniform control flow, see render_forward_c3_kernel
         const float4 a = reinterpret_cast<const float4*>(&s_rec[j])[0];
         const float4 b = reinterpret_cast<const float4*>(&s_rec[j])[1];
         const float dx = a.x - fx, dy = a.y - fy;
         const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-        if (power > 0.0f) continue;
         const float alpha = fminf(0.99f, b.y * ex2_approx(power * 1.4426950408889634f));
-        if (alpha < 1.0f / 255.0f) continue;
+        const bool ok = !done && power <= 0.0f && alpha >= 1.0f / 255.0f;
+        if (!__any_sync(0xffffffffu, ok)) continue;
         const float test_T = T * (1.f - alpha);
-        if (test_T < 0.0001f) {
-          done = true;
-          continue;
-        }
-        const float w = alpha * T;
+        const bool blend = ok && test_T >= 0.0001f;
+        const bool stop = ok && test_T < 0.0001f;
+        const float w = blend ? alpha * T : 0.f;
 #pragma unroll
         for (int k = 0; k < FWD_CK; k += 4) {
           const float4 f = *reinterpret_cast<const float4*>(&s_feat[j][k]);
-          acc[k] += f.x * w; acc[k + 1] += f.y * w; acc[k + 2] += f.z * w; acc[k + 3] += f.w * w;
+          acc[k] = fmaf(f.x, w, acc[k]); acc[k + 1] = fmaf(f.y, w, acc[k + 1]);
+          acc[k + 2] = fmaf(f.z, w, acc[k + 2]); acc[k + 3] = fmaf(f.w, w, acc[k + 3]);
         }
-        if (T > 0.5f && test_T < 0.5f) D = b.z;
-        T = test_T;
-        last = (uint32_t)(r * FWDG_BATCH + j + 1);
+        if (blend) {
+          if (T > 0.5f && test_T < 0.5f) D = s_rec[j].depth;
+          T = test_T;
+          last = s_rec[j].orig;
+          lastc = (uint32_t)(r * FWDG_BATCH + j + 1);
+        }
+        done = done || stop;
+        if (__any_sync(0xffffffffu, stop) && __all_sync(0xffffffffu, done)) break;
       }
     }
     if (inside) {
@@ -261,7 +268,7 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_generic_kernel(
         n_contrib[view * HW + pix] = last;
         if (out_depth) out_depth[view * HW + pix] = D;
         if (out_opacity) out_opacity[view * HW + pix] = 1.f - T;
-        atomicMax(&s_max, last);
+        atomicMax(&s_max, lastc);
       }
     }
     __syncthreads();
@@ -291,14 +298,17 @@ extern "C" int ocrf_render_forward(void* stream, const OcrfShape* sh, uint64_t p
   if (rc) return rc;
   ocrf_image_layout(sh, &I);
   const dim3 grid(tiles_x(*sh), tiles_y(*sh), sh->V);
-  const uint2* ranges = at<uint2>(image_ws, I.ranges);
+  const uint2* ranges = at<uint2>(image_ws, I.ranges_render);
   float* fT = at<float>(image_ws, I.final_T);
   uint32_t* nc = at<uint32_t>(image_ws, I.n_contrib);
   uint32_t* mc = at<uint32_t>(image_ws, I.max_contrib);
   if (sh->C == 3) {
-    static const int ppt = env_int("OCRF_FWD_PPT", 1);
+    static const int ppt = env_int("OCRF_FWD_PPT", 2);
     const Record* rec = at<Record>(bin_ws, B.records);
-    if (ppt == 2)
+    if (ppt == 4)
+      render_forward_c3_kernel<4><<<grid, TILE_PIX / 4, 0, st>>>(sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
+                                                                 out_depth, out_opacity);
+    else if (ppt == 2)
       render_forward_c3_kernel<2><<<grid, TILE_PIX / 2, 0, st>>>(sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
                                                                  out_depth, out_opacity);
     else
@@ -307,7 +317,7 @@ extern "C" int ocrf_render_forward(void* stream, const OcrfShape* sh, uint64_t p
   } else {
     (void)use_sh;
     render_forward_generic_kernel<<<grid, TILE_PIX, 0, st>>>(sh->W, sh->H, sh->C, sh->P, sh->views_per_sample, ranges,
-                                                             at<RecordLite>(bin_ws, B.records), colors, bg, fT, nc, mc,
+                                                             at<Record>(bin_ws, B.records), colors, bg, fT, nc, mc,
                                                              out_color, out_depth, out_opacity);
   }
   OCRF_CHECK_LAST();
