@@ -72,7 +72,7 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan_256(uint32_t v, uint32_t*
   return off + incl - v;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS) sort_onesweep_kernel(
+__global__ void __launch_bounds__(SORT_THREADS, 3) sort_onesweep_kernel(
     const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ n_dev, uint64_t n_cap, int shift, int bits,
     const uint32_t* __restrict__ hist /*[256] this pass*/, uint32_t* __restrict__ status /*[tiles][256] this pass*/,
@@ -99,18 +99,11 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_onesweep_kernel(
 
   // ---- load (warp-striped: item i of lane l sits at warp_base + i*32 + l, i.e. index order) ----
   uint64_t key[SORT_ITEMS];
-  uint32_t val[SORT_ITEMS];
   const uint32_t warp_base = warp * (32 * SORT_ITEMS);
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
     const uint32_t loc = warp_base + i * 32 + lane;
-    if (loc < n_valid) {
-      key[i] = keys_in[base + loc];
-      val[i] = vals_in[base + loc];
-    } else {
-      key[i] = ~0ull;  // padding ranks behind every valid key of the (last) tile
-      val[i] = 0;
-    }
+    key[i] = loc < n_valid ? keys_in[base + loc] : ~0ull;  // padding ranks behind every valid key of the (last) tile
   }
 
   // ---- rank inside the warp: match_any multi-split, one item row at a time (stable) ----
@@ -162,13 +155,13 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_onesweep_kernel(
   __syncthreads();
 
   // ---- reorder through shared memory, then write runs ----
-  uint32_t pos[SORT_ITEMS];
 #pragma unroll
   for (int i = 0; i < SORT_ITEMS; i++) {
     const uint32_t d = (uint32_t)(key[i] >> shift) & digit_mask;
-    pos[i] = s_tile_excl[d] + s_warp_hist[warp * 256 + d] + rank[i];
-    s_keys[pos[i]] = key[i];
-    s_vals[pos[i]] = val[i];
+    const uint32_t pos = s_tile_excl[d] + s_warp_hist[warp * 256 + d] + rank[i];
+    s_keys[pos] = key[i];
+    const uint32_t loc = warp_base + i * 32 + lane;
+    s_vals[pos] = loc < n_valid ? vals_in[base + loc] : 0u;  // values are only touched here (coalesced, L2-hot)
   }
   __syncthreads();
   for (uint32_t k = tid; k < n_valid; k += SORT_THREADS) {
