@@ -226,23 +226,58 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
   }
 }
 
-// Generic channel count (C != 3): 32-byte records, features and feature gradients by id.
-constexpr int BWDG_BATCH = 128;
+// Generic channel count (C != 3, e.g. the 80-channel feature rendering of GeoEnhDet).
+//
+// dL/dalpha of a (pixel, Gaussian) pair needs the sum over ALL channels of (c_k - A_k) g_k before the
+// geometry gradients can be formed, so channels cannot be tiled across sweeps as in the forward.
+// One thread per pixel keeps its upstream gradient g[CP] and the behind-colour A[CP] in REGISTERS
+// (CP = C rounded up to 16, fully unrolled; one CTA of 256 threads per SM has 255 registers per
+// thread to spend), the batch's feature rows sit in shared memory and are read as broadcast
+// LDS.128.  The recurrence is applied eagerly, A <- A + alpha (c - A) right after A is used, which is
+// the reference's lazy `last_alpha * last_color + (1 - last_alpha) * accum` evaluated one step
+// earlier -- no per-pixel "last colour" has to be remembered.  Per record the warp reduce-scatters
+// the CP colour gradients 16 at a time (16 shuffles per 16 channels instead of 80) and issues one
+// 64-byte-contiguous global reduction per 16 channels; geometry gradients follow the C = 3 scheme.
+constexpr int BWDG_BATCH = 64;
 
-__global__ void __launch_bounds__(TILE_PIX) render_backward_generic_kernel(
-    int W, int H, int C, int P, int views_per_sample, const uint2* __restrict__ ranges,
+// reduce-scatter of 16 values: afterwards lane L holds the warp total of value (L >> 1) & 15 (both lanes of a pair)
+__device__ __forceinline__ float butterfly16(const float* v, int lane) {
+  float w[8], u[4], t[2];
+  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    const float keep = h16 ? v[i + 8] : v[i], send = h16 ? v[i] : v[i + 8];
+    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const float keep = h8 ? w[i + 4] : w[i], send = h8 ? w[i] : w[i + 4];
+    u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; i++) {
+    const float keep = h4 ? u[i + 2] : u[i], send = h4 ? u[i] : u[i + 2];
+    t[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  const float keep = h2 ? t[1] : t[0], send = h2 ? t[0] : t[1];
+  float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;  // value index = h16*8 + h8*4 + h4*2 + h2
+}
+
+template <int CP>
+__global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
+    int W, int H, int C, int P, int views_per_sample, const uint2* __restrict__ ranges /* culled lists */,
     const Record* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
     const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
     const uint32_t* __restrict__ max_contrib, const float* __restrict__ dL_dpix, const float* __restrict__ dL_dopa,
     float* __restrict__ ggrad, float* __restrict__ dL_dfeats) {
-  // One sweep per tile.  dL/dalpha of a pair needs the sum over ALL channels before the geometry
-  // gradients can be formed, so each thread walks every channel of the current record before moving
-  // on.  The per-channel suffix state "accum_rec" (C floats per pixel) lives in dynamic shared
-  // memory; the "last colour" of the recurrence is re-read from the feature table through the id of
-  // the previously blended record instead of being stored.
-  __shared__ __align__(16) Record s_rec[BWDG_BATCH];
-  __shared__ __align__(16) float s_acc[BWDG_BATCH][8];
-  extern __shared__ float s_dyn[];  // [TILE_PIX][C] suffix accumulators "accum_rec" (last colour is re-read)
+  constexpr int NW = TILE_PIX / 32;
+  extern __shared__ __align__(16) unsigned char smem_g[];
+  Record* s_rec = reinterpret_cast<Record*>(smem_g);                                   // [BATCH]
+  float* s_feat = reinterpret_cast<float*>(smem_g + BWDG_BATCH * sizeof(Record));      // [BATCH][CP]
+  float* s_acc = s_feat + BWDG_BATCH * CP;                                             // [NW][BATCH][8]
+  __shared__ uint32_t s_touched[NW][BWDG_BATCH / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int tiles_x = gridDim.x, tiles_per_view = gridDim.x * gridDim.y;
@@ -263,16 +298,21 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_generic_kernel(
   const float fx = (float)px, fy = (float)py;
   const float Tf = inside ? final_T[view * HW + pix] : 0.f;
   const int nc = inside ? (int)n_contrib[view * HW + pix] : 0;
-  const float gop = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
+  float g[CP], A[CP];
   float bgdot = 0.f;
-  if (inside)
-    for (int ch = 0; ch < C; ch++) bgdot += bg[ch] * dL_dpix[((size_t)view * C + ch) * HW + pix];
-  float* my_accum = s_dyn + (size_t)tid * C;  // accum_rec per channel
-  for (int ch = 0; ch < C; ch++) my_accum[ch] = 0.f;
-  float T = Tf, last_alpha = 0.f;
-  int last_j_global = -1;  // list position of the previously blended Gaussian (its colour = "last colour")
+#pragma unroll
+  for (int k = 0; k < CP; k++) {
+    g[k] = (inside && k < C) ? dL_dpix[((size_t)view * C + k) * HW + pix] : 0.f;
+    A[k] = 0.f;
+    bgdot += (k < C ? bg[k] : 0.f) * g[k];
+  }
+  const float gop = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
+  const float gob = Tf * (gop - bgdot);
+  float T = Tf;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
   const int rounds = (mc + BWDG_BATCH - 1) / BWDG_BATCH;
+  // which 16-lane-pair slot of a 16-channel group this lane owns after butterfly16
+  const int my_slot = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 
   for (int r = 0; r < rounds; r++) {
     const int hi = mc - r * BWDG_BATCH;
@@ -280,71 +320,110 @@ __global__ void __launch_bounds__(TILE_PIX) render_backward_generic_kernel(
     const int cnt = hi - lo;
     __syncthreads();
     if (tid < cnt) s_rec[tid] = records[range.x + lo + tid];
-    for (int i = tid; i < BWDG_BATCH * 8; i += TILE_PIX) (&s_acc[0][0])[i] = 0.f;
+    for (int e = tid; e < cnt * (CP / 4); e += TILE_PIX) {  // feature rows, 16 bytes per thread
+      const int j = e / (CP / 4), k4 = (e - j * (CP / 4)) * 4;
+      const uint32_t id = records[range.x + lo + j].id;
+      float4 f;
+      f.x = k4 + 0 < C ? __ldg(fbase + (size_t)id * C + k4 + 0) : 0.f;
+      f.y = k4 + 1 < C ? __ldg(fbase + (size_t)id * C + k4 + 1) : 0.f;
+      f.z = k4 + 2 < C ? __ldg(fbase + (size_t)id * C + k4 + 2) : 0.f;
+      f.w = k4 + 3 < C ? __ldg(fbase + (size_t)id * C + k4 + 3) : 0.f;
+      *reinterpret_cast<float4*>(s_feat + j * CP + k4) = f;
+    }
     __syncthreads();
+    uint32_t touched = 0;
     for (int j = cnt - 1; j >= 0; j--) {
-      const int k = lo + j;
       const float4 a = reinterpret_cast<const float4*>(&s_rec[j])[0];
       const float4 b = reinterpret_cast<const float4*>(&s_rec[j])[1];
-      const uint32_t id = s_rec[j].id;
       const float dx = a.x - fx, dy = a.y - fy;
       const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
       const float G = ex2_approx_b(power * 1.4426950408889634f);
       const float alpha = fminf(0.99f, b.y * G);
-      const bool ok = (int)s_rec[j].orig <= nc && power <= 0.0f && alpha >= 1.0f / 255.0f;
-      if (!__any_sync(0xffffffffu, ok)) continue;
-      float rcp = 1.f, w = 0.f, dL_dalpha = 0.f;
-      if (ok) {
-        rcp = __fdividef(1.f, 1.f - alpha);
-        T *= rcp;
-        w = alpha * T;
-      }
-      // colour part, channel by channel: features of this Gaussian and of the previously blended one
-      const float* fcur = fbase + (size_t)id * C;
-      const uint32_t last_id = last_j_global >= 0 ? records[range.x + last_j_global].id : 0u;
-      const float* flast = fbase + (size_t)last_id * C;
-      for (int ch = 0; ch < C; ch++) {
-        float contrib = 0.f;
+      const bool ok = (int)__float_as_uint(b.z) <= nc && power <= 0.0f && alpha >= 1.0f / 255.0f;
+      if (__any_sync(0xffffffffu, ok)) {
+        float rcp = 1.f, w = 0.f, al = 0.f;
         if (ok) {
-          const float cval = __ldg(fcur + ch);
-          const float lcv = last_j_global >= 0 ? __ldg(flast + ch) : 0.f;
-          const float acc = last_alpha * lcv + (1.f - last_alpha) * my_accum[ch];
-          my_accum[ch] = acc;
-          const float gch = dL_dpix[((size_t)view * C + ch) * HW + pix];
-          dL_dalpha += (cval - acc) * gch;
-          contrib = w * gch;
+          rcp = __fdividef(1.f, 1.f - alpha);
+          T *= rcp;
+          w = alpha * T;
+          al = alpha;
         }
-        const float tot = warp_sum(contrib);
-        if (lane == 0 && tot != 0.f) atomicAdd(gfbase + (size_t)id * C + ch, tot);
+        const uint32_t id = s_rec[j].id;
+        const float* fj = s_feat + j * CP;
+        float dot = 0.f;
+#pragma unroll
+        for (int k0 = 0; k0 < CP; k0 += 16) {
+          float contrib[16];
+#pragma unroll
+          for (int k = 0; k < 16; k += 4) {
+            const float4 c = *reinterpret_cast<const float4*>(fj + k0 + k);
+            const float cc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const float d = cc[q] - A[k0 + k + q];
+              dot = fmaf(d, g[k0 + k + q], dot);
+              A[k0 + k + q] = fmaf(al, d, A[k0 + k + q]);  // lanes that did not blend have al = 0
+              contrib[k + q] = w * g[k0 + k + q];
+            }
+          }
+          const float tot = butterfly16(contrib, lane);
+          const int ch = k0 + my_slot;
+          if ((lane & 1) == 0 && ch < C && tot != 0.f) atomicAdd(gfbase + (size_t)id * C + ch, tot);
+        }
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (ok) {
+          const float dL_dalpha = dot * T + gob * rcp;
+          const float dL_dG = b.y * dL_dalpha;
+          const float gdx = G * dx, gdy = G * dy;
+          v[0] = dL_dG * (-gdx * a.z - gdy * a.w) * ddelx_dx;
+          v[1] = dL_dG * (-gdy * b.x - gdx * a.w) * ddely_dy;
+          v[2] = -0.5f * gdx * dx * dL_dG;
+          v[3] = -0.5f * gdx * dy * dL_dG;
+          v[4] = -0.5f * gdy * dy * dL_dG;
+          v[5] = G * dL_dalpha;
+        }
+        const float r8 = butterfly8(v, lane);
+        if ((lane & 3) == 0) s_acc[(warp * BWDG_BATCH + j) * 8 + (lane >> 2)] = r8;
+        touched |= 1u << (j & 31);
       }
-      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-      if (ok) {
-        dL_dalpha *= T;
-        last_alpha = alpha;
-        last_j_global = k;
-        dL_dalpha += (Tf * rcp) * (gop - bgdot);
-        const float dL_dG = b.y * dL_dalpha;
-        const float gdx = G * dx, gdy = G * dy;
-        v[0] = dL_dG * (-gdx * a.z - gdy * a.w) * ddelx_dx;
-        v[1] = dL_dG * (-gdy * b.x - gdx * a.w) * ddely_dy;
-        v[2] = -0.5f * gdx * dx * dL_dG;
-        v[3] = -0.5f * gdx * dy * dL_dG;
-        v[4] = -0.5f * gdy * dy * dL_dG;
-        v[5] = G * dL_dalpha;
+      if ((j & 31) == 0) {
+        if (lane == 0) s_touched[warp][j >> 5] = touched;
+        touched = 0;
       }
-      const float r8 = butterfly8(v, lane);
-      if ((lane & 3) == 0 && (lane >> 2) < 6) atomicAdd(&s_acc[j][lane >> 2], r8);
     }
     __syncthreads();
     for (int j = tid; j < cnt; j += TILE_PIX) {
-      const float4 q0 = *reinterpret_cast<const float4*>(&s_acc[j][0]);
-      const float2 q1 = *reinterpret_cast<const float2*>(&s_acc[j][4]);
-      if (q0.x == 0.f && q0.y == 0.f && q0.z == 0.f && q0.w == 0.f && q1.x == 0.f && q1.y == 0.f) continue;
+      float q[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      bool hit = false;
+#pragma unroll
+      for (int w2 = 0; w2 < NW; w2++)
+        if ((s_touched[w2][j >> 5] >> (j & 31)) & 1u) {
+          hit = true;
+          const float4 q0 = *reinterpret_cast<const float4*>(&s_acc[(w2 * BWDG_BATCH + j) * 8]);
+          const float2 q1 = *reinterpret_cast<const float2*>(&s_acc[(w2 * BWDG_BATCH + j) * 8 + 4]);
+          q[0] += q0.x; q[1] += q0.y; q[2] += q0.z; q[3] += q0.w; q[4] += q1.x; q[5] += q1.y;
+        }
+      if (!hit) continue;
       float* gg = ggrad + ((size_t)view * P + s_rec[j].id) * OCRF_GGRAD_STRIDE;
-      atomicAdd(reinterpret_cast<float4*>(gg), q0);
-      atomicAdd(reinterpret_cast<float2*>(gg + 4), q1);
+      atomicAdd(reinterpret_cast<float4*>(gg), make_float4(q[0], q[1], q[2], q[3]));
+      atomicAdd(reinterpret_cast<float2*>(gg + 4), make_float2(q[4], q[5]));
     }
   }
+}
+
+template <int CP>
+static int launch_backward_generic(cudaStream_t st, dim3 grid, const OcrfShape* sh, const uint2* ranges, const Record* rec,
+                                   const float* colors, const float* bg, const float* fT, const uint32_t* nc,
+                                   const uint32_t* mc, const float* dL_dcolor, const float* dL_dopa, float* ggrad,
+                                   float* dL_dcolors) {
+  const size_t dyn = BWDG_BATCH * sizeof(Record) + (size_t)BWDG_BATCH * CP * 4 + (size_t)(TILE_PIX / 32) * BWDG_BATCH * 8 * 4;
+  cudaError_t e = cudaFuncSetAttribute(render_backward_generic_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)dyn);
+  if (e != cudaSuccess) return (int)e;
+  render_backward_generic_kernel<CP><<<grid, TILE_PIX, dyn, st>>>(sh->W, sh->H, sh->C, sh->P, sh->views_per_sample, ranges,
+                                                                   rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopa, ggrad,
+                                                                   dL_dcolors);
+  return 0;
 }
 
 }  // namespace ocrf
@@ -390,14 +469,20 @@ extern "C" int ocrf_render_backward(void* stream, const OcrfShape* sh, uint64_t 
                                                               ggrad, dL_dcolors);
   } else {
     if (!colors) return OCRF_EINVAL;
-    const size_t dyn = (size_t)TILE_PIX * sh->C * sizeof(float);
-    if (dyn > 160 * 1024) return OCRF_ECAPACITY;
-    cudaError_t e = cudaFuncSetAttribute(render_backward_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)dyn);
-    if (e != cudaSuccess) return (int)e;
-    render_backward_generic_kernel<<<grid, TILE_PIX, dyn, st>>>(
-        sh->W, sh->H, sh->C, sh->P, sh->views_per_sample, ranges, at<Record>(bin_ws, B.records), colors, bg, fT, nc,
-        mc, dL_dcolor, dL_dopacity_map, ggrad, dL_dcolors);
+    const Record* rec = at<Record>(bin_ws, B.records);
+    int rc2;
+#define OCRF_BWDG(CPV)                                                                                              \
+  rc2 = launch_backward_generic<CPV>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopacity_map, \
+                                     ggrad, dL_dcolors)
+    if (sh->C <= 16) OCRF_BWDG(16);
+    else if (sh->C <= 32) OCRF_BWDG(32);
+    else if (sh->C <= 48) OCRF_BWDG(48);
+    else if (sh->C <= 64) OCRF_BWDG(64);
+    else if (sh->C <= 80) OCRF_BWDG(80);
+    else if (sh->C <= 96) OCRF_BWDG(96);
+    else return OCRF_ECAPACITY;  // more than 96 feature channels: not supported by the register-resident backward
+#undef OCRF_BWDG
+    if (rc2) return rc2;
   }
   OCRF_CHECK_LAST();
   return 0;

@@ -145,7 +145,7 @@ def test_batch_gradients_sum_over_views():
         assert e <= GRAD_TOL, "%s batched gradient rel err %.3g" % (k, e)
 
 
-@pytest.mark.parametrize("C", [1, 8, 19])
+@pytest.mark.parametrize("C", [1, 8, 19, 40, 80])
 def test_generic_channel_count(C):
     W, H = 96, 64
     g, cams = util.small_scene("frustum", P=1500, seed=8, W=W, H=H, channels=C)
