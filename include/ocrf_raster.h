@@ -72,6 +72,12 @@ typedef struct OcrfGeomLayout {
   size_t rgb;           /* float  [V*P*3]  (SH path only) */
   size_t clamped;       /* uint8  [V*P*3]  (SH path only) */
   size_t scan_status;   /* uint64 [blocks] decoupled look-back state of the fused scan */
+  size_t vis_keys;      /* uint64 [V*P] (view << 32 | depth bits) of the visible Gaussians, depth-sorted by ocrf_bin_forward */
+  size_t vis_vals;      /* uint32 [V*P] their global index view*P + i */
+  size_t vis_keys_tmp;  /* ping-pong halves of that sort */
+  size_t vis_vals_tmp;
+  size_t view_start;    /* uint32 [V+1] first visible slot of every view */
+  size_t vis_sort_ws;   /* workspace of the visible-Gaussian sort */
 } OcrfGeomLayout;
 
 typedef struct OcrfBinLayout {
@@ -85,6 +91,8 @@ typedef struct OcrfBinLayout {
   size_t records;       /* OCRF_RECORD_BYTES * N: per tile, the records that can reach a pixel of the tile */
   size_t histogram;     /* uint32 [8][256] */
   size_t sort_status;   /* uint32 [passes][sort_tiles][256] + tickets */
+  size_t split_counts;  /* uint32 [V][chunks][tiles] per-chunk tile counts of the depth-ordered tile split */
+  size_t split_tiles;   /* uint32 [2][V*tiles] tile totals and tile offsets */
 } OcrfBinLayout;
 
 typedef struct OcrfImageLayout {
@@ -120,7 +128,10 @@ int ocrf_preprocess_forward(void* stream, const OcrfShape* shape, const float* m
  * read on the device from the geom header, and exceeding the capacity sets header[1] bit 0 and
  * renders nothing rather than overrunning.  colors [S,P,C] (ignored when the SH path produced rgb). */
 int ocrf_bin_forward(void* stream, const OcrfShape* shape, uint64_t pair_capacity, const int32_t* radii,
-                     const float* colors, int use_sh, void* geom_ws, void* bin_ws, void* image_ws);
+                     const float* colors, int use_sh, uint32_t flags, void* geom_ws, void* bin_ws, void* image_ws);
+/* flags for ocrf_bin_forward */
+#define OCRF_BIN_PAIR_SORT 1u /* force the reference's algorithm (sort all (tile, Gaussian) pairs) instead of the
+                                 depth-ordered tile split; both produce bit-identical keys / point list / ranges */
 
 /* Stage 3 (forward.cu:261-374; median depth per the w-depth fork; opacity = 1 - final_T).
  * bg [C]; out_color [V,C,H,W]; out_depth, out_opacity [V,1,H,W] (either may be NULL). */

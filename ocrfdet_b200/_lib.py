@@ -15,6 +15,7 @@ OCRF_GGRAD_STRIDE = 8
 ABI_VERSION = 1
 OCRF_EINVAL = -1
 OCRF_ECAPACITY = -2
+OCRF_BIN_PAIR_SORT = 1
 
 EXPORTS = [
     "ocrf_abi_version", "ocrf_error_string", "ocrf_geom_layout", "ocrf_bin_layout", "ocrf_image_layout",
@@ -31,12 +32,14 @@ class OcrfShape(C.Structure):
 
 class OcrfGeomLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("total", "header", "depths", "xy", "conic_opacity", "tiles_touched",
-                                          "offsets", "rgb", "clamped", "scan_status")]
+                                          "offsets", "rgb", "clamped", "scan_status", "vis_keys", "vis_vals",
+                                          "vis_keys_tmp", "vis_vals_tmp", "view_start", "vis_sort_ws")]
 
 
 class OcrfBinLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("total", "keys", "point_list", "keys_tmp", "vals_tmp", "keys_unsorted",
-                                          "vals_unsorted", "records", "histogram", "sort_status")]
+                                          "vals_unsorted", "records", "histogram", "sort_status", "split_counts",
+                                          "split_tiles")]
 
 
 class OcrfImageLayout(C.Structure):
@@ -72,7 +75,7 @@ def lib():
     L.ocrf_image_layout.argtypes = [shp, C.POINTER(OcrfImageLayout)]
     L.ocrf_sort_end_bit.argtypes = [shp]
     L.ocrf_preprocess_forward.argtypes = [vp, shp, vp, vp, vp, vp, vp, vp, vp, f32, C.c_int, vp, vp]
-    L.ocrf_bin_forward.argtypes = [vp, shp, u64, vp, vp, C.c_int, vp, vp, vp]
+    L.ocrf_bin_forward.argtypes = [vp, shp, u64, vp, vp, C.c_int, C.c_uint32, vp, vp, vp]
     L.ocrf_render_forward.argtypes = [vp, shp, u64, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.ocrf_render_backward.argtypes = [vp, shp, u64, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ocrf_preprocess_backward.argtypes = [vp, shp, vp, vp, vp, vp, vp, vp, f32, vp, vp, vp, vp, vp, vp, vp, vp, vp,

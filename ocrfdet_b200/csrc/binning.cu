@@ -89,6 +89,31 @@ __global__ void __launch_bounds__(256) duplicate_with_keys_kernel(OcrfShape sh, 
 // rectangle (continuous relaxation, evaluated on the four edges) gives the largest possible alpha;
 // a record is dropped only if that bound, with a 1e-3 relative margin for rounding, is below 1/255.
 // Each record keeps its 1-based position in the full list so n_contrib is the reference's value.
+// Can Gaussian (mean p, conic A/B/C, opacity co.w) reach alpha >= 1/255 on any pixel of the rectangle
+// [px0,px1] x [py0,py1]?  Exact-safe: false only if the continuous minimum of the conic form over the
+// rectangle bounds alpha below 1/255 with a 1e-3 relative margin (NaN anywhere answers true).
+__device__ __forceinline__ bool tile_can_contribute(float2 p, float4 co, float px0, float px1, float py0, float py1) {
+  const float dxl = p.x - px1, dxh = p.x - px0, dyl = p.y - py1, dyh = p.y - py0;  // d = mean - pixel
+  float qmin = 0.f;
+  const bool inside = dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f;
+  if (!inside) {
+    const float A = co.x, B = co.y, Cc = co.z;
+    float q = INFINITY;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const float ex = e ? dxh : dxl;
+      const float sy = fminf(dyh, fmaxf(dyl, -B * ex / Cc));
+      q = fminf(q, A * ex * ex + 2.f * B * ex * sy + Cc * sy * sy);
+      const float ey = e ? dyh : dyl;
+      const float sx = fminf(dxh, fmaxf(dxl, -B * ey / A));
+      q = fminf(q, A * sx * sx + 2.f * B * sx * ey + Cc * ey * ey);
+    }
+    qmin = q;
+  }
+  const float alpha_max = co.w * __expf(-0.5f * qmin) * 1.001f;
+  return !(alpha_max < 1.0f / 255.0f);
+}
+
 __global__ void __launch_bounds__(256) ranges_cull_pack_kernel(OcrfShape sh, uint64_t n_cap, int use_sh, int has_rgb,
                                                                const uint32_t* __restrict__ header,
                                                                const uint64_t* __restrict__ keys,
@@ -141,26 +166,7 @@ __global__ void __launch_bounds__(256) ranges_cull_pack_kernel(OcrfShape sh, uin
       g = (size_t)v * sh.P + id;
       p = xy[g];
       co = conic_opacity[g];
-      // d = mean - pixel ranges over [dxl, dxh] x [dyl, dyh]
-      const float dxl = p.x - px1, dxh = p.x - px0, dyl = p.y - py1, dyh = p.y - py0;
-      float qmin = 0.f;
-      const bool inside = dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f;
-      if (!inside) {
-        const float A = co.x, B = co.y, Cc = co.z;
-        float q = INFINITY;
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-          const float ex = e ? dxh : dxl;
-          const float sy = fminf(dyh, fmaxf(dyl, -B * ex / Cc));
-          q = fminf(q, A * ex * ex + 2.f * B * ex * sy + Cc * sy * sy);
-          const float ey = e ? dyh : dyl;
-          const float sx = fminf(dxh, fmaxf(dxl, -B * ey / A));
-          q = fminf(q, A * sx * sx + 2.f * B * sx * ey + Cc * ey * ey);
-        }
-        qmin = q;
-      }
-      const float alpha_max = co.w * __expf(-0.5f * qmin) * 1.001f;
-      keep = !(alpha_max < 1.0f / 255.0f);  // NaN anywhere keeps the record
+      keep = tile_can_contribute(p, co, px0, px1, py0, py1);
     }
     const uint32_t bal = __ballot_sync(0xffffffffu, keep);
     if (lane == 0) s_warp[warp] = __popc(bal);
@@ -188,6 +194,144 @@ __global__ void __launch_bounds__(256) ranges_cull_pack_kernel(OcrfShape sh, uin
     __syncthreads();
   }
   if (tid == 0) ranges_render[vt] = make_uint2(lo, lo + kept_total);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depth-first binning: the default stage-2 algorithm.
+//
+// The reference emits its (tile | depth) pairs in Gaussian-index order and needs ceil((32+bits)/8)
+// = 6 radix passes over all N_dup pairs (3.85 M at the headline shape, 134 M at the 1 M-Gaussian
+// stress shape).  Here the ~19 k VISIBLE Gaussians of every view are first sorted by (view | depth)
+// with the same onesweep sort (ties keep Gaussian-index order, as in the stable pair sort), the pairs
+// are then emitted in THAT order, and only the tile bits [32, 32+bits) remain to be sorted: 2 stable
+// passes instead of 6.  A stable sort by tile of a depth-ordered sequence is exactly the reference's
+// order, so keys, point list and ranges are bit-identical (tests run both algorithms).
+// ------------------------------------------------------------------------------------------------
+constexpr unsigned long long SS_FLAG_LOCAL = 1ull << 62;
+constexpr unsigned long long SS_FLAG_INCL = 2ull << 62;
+constexpr unsigned long long SS_VALUE_MASK = (1ull << 62) - 1;
+
+// inclusive scan of tiles_touched over the depth-sorted visible Gaussians (decoupled look-back)
+__global__ void __launch_bounds__(256) scan_sorted_tiles_kernel(const uint32_t* __restrict__ header,
+                                                                const uint32_t* __restrict__ vis_vals,
+                                                                const uint32_t* __restrict__ tiles_touched,
+                                                                uint32_t* __restrict__ sorted_offsets,
+                                                                unsigned long long* __restrict__ status,
+                                                                uint32_t* __restrict__ ticket) {
+  __shared__ uint32_t s_warp[8];
+  __shared__ uint32_t s_bid, s_prefix;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t n = header[HDR_NUM_VIS];
+  if (tid == 0) s_bid = atomicAdd(ticket, 1u);
+  __syncthreads();
+  const uint32_t bid = s_bid;
+  if ((uint64_t)bid * 1024 >= n) return;
+  uint32_t x[4], sum = 0;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t j = bid * 1024 + tid * 4 + k;
+    x[k] = j < n ? tiles_touched[vis_vals[j]] : 0u;
+    sum += x[k];
+  }
+  uint32_t incl = sum;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += y;
+  }
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t warp_off = 0, total = 0;
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    const uint32_t y = s_warp[w];
+    if (w < warp) warp_off += y;
+    total += y;
+  }
+  if (tid == 0) {
+    unsigned long long excl = 0;
+    if (bid == 0) {
+      atomicExch(&status[0], SS_FLAG_INCL | total);
+    } else {
+      atomicExch(&status[bid], SS_FLAG_LOCAL | total);
+      int look = (int)bid - 1;
+      while (true) {
+        const unsigned long long st = *reinterpret_cast<volatile unsigned long long*>(&status[look]);
+        if ((st >> 62) == 0) continue;
+        excl += st & SS_VALUE_MASK;
+        if ((st >> 62) == 2) break;
+        look--;
+      }
+      atomicExch(&status[bid], SS_FLAG_INCL | (excl + total));
+    }
+    s_prefix = (uint32_t)excl;
+  }
+  __syncthreads();
+  uint32_t run = s_prefix + warp_off + incl - sum;
+#pragma unroll
+  for (int k = 0; k < 4; k++) {
+    const uint32_t j = bid * 1024 + tid * 4 + k;
+    run += x[k];
+    if (j < n) sorted_offsets[j] = run;
+  }
+}
+
+// duplicateWithKeys over the depth-sorted order: one thread per sorted Gaussian, large rectangles by the warp
+__global__ void __launch_bounds__(256) duplicate_sorted_kernel(OcrfShape sh, uint64_t n_cap,
+                                                               const int32_t* __restrict__ radii,
+                                                               uint32_t* __restrict__ header,
+                                                               const uint64_t* __restrict__ vis_keys,
+                                                               const uint32_t* __restrict__ vis_vals,
+                                                               const float2* __restrict__ xy,
+                                                               const uint32_t* __restrict__ sorted_offsets,
+                                                               uint64_t* __restrict__ keys,
+                                                               uint32_t* __restrict__ vals) {
+  const uint32_t total = header[HDR_NUM_PAIRS];
+  if ((uint64_t)total > n_cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(&header[HDR_ERROR], ERR_PAIR_OVERFLOW);
+    return;
+  }
+  const uint32_t n = header[HDR_NUM_VIS];
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gx = ceil_div(sh.W, TILE), gy = ceil_div(sh.H, TILE);
+  const int lane = threadIdx.x & 31;
+  int x0 = 0, y0 = 0, w = 0, cnt = 0;
+  uint32_t off = 0, dbits = 0, id = 0, tile_base = 0;
+  if (j < n) {
+    const uint32_t g = vis_vals[j];
+    const uint64_t vk = vis_keys[j];
+    const uint32_t v = (uint32_t)(vk >> 32);
+    id = g - v * (uint32_t)sh.P;
+    dbits = (uint32_t)vk;
+    off = j == 0 ? 0u : sorted_offsets[j - 1];
+    const float2 p = xy[g];
+    int x1, y1;
+    tile_rect_dev(p.x, p.y, radii[g], gx, gy, x0, y0, x1, y1);
+    w = x1 - x0;
+    cnt = w * (y1 - y0);
+    tile_base = v * (uint32_t)(gx * gy);
+  }
+  if (cnt > 0 && cnt <= 32) {
+    for (int k = 0; k < cnt; k++) {
+      const int ty = y0 + k / w, tx = x0 + k - (k / w) * w;
+      keys[off + k] = ((uint64_t)(tile_base + (uint32_t)(ty * gx + tx)) << 32) | dbits;
+      vals[off + k] = id;
+    }
+  }
+  uint32_t big = __ballot_sync(0xffffffffu, cnt > 32);
+  while (big) {
+    const int src = __ffs(big) - 1;
+    big &= big - 1;
+    const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+    const int bw = __shfl_sync(0xffffffffu, w, src), bcnt = __shfl_sync(0xffffffffu, cnt, src);
+    const uint32_t boff = __shfl_sync(0xffffffffu, off, src), bd = __shfl_sync(0xffffffffu, dbits, src);
+    const uint32_t bid = __shfl_sync(0xffffffffu, id, src), bt = __shfl_sync(0xffffffffu, tile_base, src);
+    for (int k = lane; k < bcnt; k += 32) {
+      const int ty = by0 + k / bw, tx = bx0 + k - (k / bw) * bw;
+      keys[boff + k] = ((uint64_t)(bt + (uint32_t)(ty * gx + tx)) << 32) | bd;
+      vals[boff + k] = bid;
+    }
+  }
 }
 
 }  // namespace ocrf
@@ -224,6 +368,9 @@ extern "C" int ocrf_bin_layout(const OcrfShape* sh, uint64_t num_pairs, OcrfBinL
   const SortWs w = sort_ws_layout(n);
   out->sort_status = off + w.status;
   off = align128(off + w.total + 128);
+  const size_t nvp = (size_t)sh->V * (sh->P > 0 ? sh->P : 1);
+  out->split_counts = off; off = align128(off + nvp * 4);                       // tiles_touched scanned in depth order
+  out->split_tiles = off;  off = align128(off + ((nvp + 1023) / 1024 + 1) * 8 + 128);  // look-back state + ticket
   out->total = off + 128;
   return 0;
 }
@@ -243,7 +390,8 @@ extern "C" int ocrf_image_layout(const OcrfShape* sh, OcrfImageLayout* out) {
 }
 
 extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair_capacity, const int32_t* radii,
-                                const float* colors, int use_sh, void* geom_ws, void* bin_ws, void* image_ws) {
+                                const float* colors, int use_sh, uint32_t flags, void* geom_ws, void* bin_ws,
+                                void* image_ws) {
   if (!sh || !radii || !geom_ws || !bin_ws || !image_ws) return OCRF_EINVAL;
   if (sh->C == 3 && !use_sh && !colors) return OCRF_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -262,19 +410,57 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
 
   uint32_t* header = at<uint32_t>(geom_ws, G.header);
   const size_t n = (size_t)sh->V * sh->P;
-  duplicate_with_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
-      *sh, pair_capacity, radii, header, at<float>(geom_ws, G.depths), at<float2>(geom_ws, G.xy),
-      at<uint32_t>(geom_ws, G.offsets), at<uint64_t>(bin_ws, B.keys_unsorted), at<uint32_t>(bin_ws, B.vals_unsorted));
+  const int gxh = tiles_x(*sh), gyh = tiles_y(*sh), tiles_v = gxh * gyh;
+  const bool split = !(flags & OCRF_BIN_PAIR_SORT);
+  (void)tiles_v; (void)gxh; (void)gyh;
+  if (split) {
+    // (1) depth-sort the visible Gaussians: same onesweep sort, ~30x fewer elements than the pair sort
+    const int vbit = vis_sort_end_bit(sh->V);
+    const int vpasses = (vbit + 7) / 8;
+    uint64_t* ka = at<uint64_t>(geom_ws, (vpasses & 1) ? G.vis_keys_tmp : G.vis_keys);
+    uint32_t* va = at<uint32_t>(geom_ws, (vpasses & 1) ? G.vis_vals_tmp : G.vis_vals);
+    uint64_t* kb = at<uint64_t>(geom_ws, (vpasses & 1) ? G.vis_keys : G.vis_keys_tmp);
+    uint32_t* vb = at<uint32_t>(geom_ws, (vpasses & 1) ? G.vis_vals : G.vis_vals_tmp);
+    rc = sort_pairs_device(st, header + HDR_NUM_VIS, n, 0, vbit, ka, va, kb, vb, at<char>(geom_ws, G.vis_sort_ws));
+    if (rc) return rc;
+    // (2) emit the pairs in depth order; (3) two stable passes over the tile bits only
+    const uint32_t* vvals = at<uint32_t>(geom_ws, G.vis_vals);
+    uint32_t* sorted_offsets = at<uint32_t>(bin_ws, B.split_counts);
+    unsigned long long* sstat = at<unsigned long long>(bin_ws, B.split_tiles);
+    const size_t sblocks = (n + 1023) / 1024;
+    uint32_t* sticket = reinterpret_cast<uint32_t*>(sstat + sblocks + 1);
+    cudaMemsetAsync(sstat, 0, (sblocks + 1) * 8 + 64, st);
+    scan_sorted_tiles_kernel<<<(unsigned)sblocks, 256, 0, st>>>(header, vvals, at<uint32_t>(geom_ws, G.tiles_touched),
+                                                                sorted_offsets, sstat, sticket);
+    const int end_bit = ocrf_sort_end_bit(sh);
+    const int tpasses = (end_bit - 32 + 7) / 8;
+    uint64_t* pka = at<uint64_t>(bin_ws, (tpasses & 1) ? B.keys_tmp : B.keys);
+    uint32_t* pva = at<uint32_t>(bin_ws, (tpasses & 1) ? B.vals_tmp : B.point_list);
+    uint64_t* pkb = at<uint64_t>(bin_ws, (tpasses & 1) ? B.keys : B.keys_tmp);
+    uint32_t* pvb = at<uint32_t>(bin_ws, (tpasses & 1) ? B.point_list : B.vals_tmp);
+    duplicate_sorted_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        *sh, pair_capacity, radii, header, at<uint64_t>(geom_ws, G.vis_keys), vvals, at<float2>(geom_ws, G.xy),
+        sorted_offsets, pka, pva);
+    rc = sort_pairs_device(st, header + HDR_NUM_PAIRS, pair_capacity, 32, end_bit, pka, pva, pkb, pvb,
+                           at<char>(bin_ws, B.histogram));
+    if (rc) return rc;
+  } else {
+  uint32_t* header = at<uint32_t>(geom_ws, G.header);
+    const size_t n = (size_t)sh->V * sh->P;
+    duplicate_with_keys_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(
+        *sh, pair_capacity, radii, header, at<float>(geom_ws, G.depths), at<float2>(geom_ws, G.xy),
+        at<uint32_t>(geom_ws, G.offsets), at<uint64_t>(bin_ws, B.keys_unsorted), at<uint32_t>(bin_ws, B.vals_unsorted));
 
-  const int end_bit = ocrf_sort_end_bit(sh);
-  const int passes = (end_bit + 7) / 8;
-  uint64_t* ka = at<uint64_t>(bin_ws, B.keys_unsorted);
-  uint32_t* va = at<uint32_t>(bin_ws, B.vals_unsorted);
-  uint64_t* kb = at<uint64_t>(bin_ws, (passes & 1) ? B.keys : B.keys_tmp);
-  uint32_t* vb = at<uint32_t>(bin_ws, (passes & 1) ? B.point_list : B.vals_tmp);
-  rc = sort_pairs_device(st, header + HDR_NUM_PAIRS, pair_capacity, end_bit, ka, va, kb, vb,
-                         at<char>(bin_ws, B.histogram));
-  if (rc) return rc;
+    const int end_bit = ocrf_sort_end_bit(sh);
+    const int passes = (end_bit + 7) / 8;
+    uint64_t* ka = at<uint64_t>(bin_ws, B.keys_unsorted);
+    uint32_t* va = at<uint32_t>(bin_ws, B.vals_unsorted);
+    uint64_t* kb = at<uint64_t>(bin_ws, (passes & 1) ? B.keys : B.keys_tmp);
+    uint32_t* vb = at<uint32_t>(bin_ws, (passes & 1) ? B.point_list : B.vals_tmp);
+    rc = sort_pairs_device(st, header + HDR_NUM_PAIRS, pair_capacity, 0, end_bit, ka, va, kb, vb,
+                           at<char>(bin_ws, B.histogram));
+    if (rc) return rc;
+  }
 
   ranges_cull_pack_kernel<<<(unsigned)tiles, 256, 0, st>>>(
       *sh, pair_capacity, use_sh, sh->C == 3, header, at<uint64_t>(bin_ws, B.keys), at<uint32_t>(bin_ws, B.point_list),

@@ -15,6 +15,7 @@ constexpr int NUM_SMS = 148;           // B200
 constexpr int HDR_NUM_PAIRS = 0;
 constexpr int HDR_ERROR = 1;
 constexpr int HDR_TICKET = 2;
+constexpr int HDR_NUM_VIS = 3;  // visible (view, Gaussian) pairs of the batch
 constexpr uint32_t ERR_PAIR_OVERFLOW = 1u;
 constexpr uint32_t ERR_PREFILTERED = 2u;
 
@@ -75,13 +76,22 @@ inline SortWs sort_ws_layout(uint64_t n) {
   w.total = off;
   return w;
 }
-// radix_sort.cu: data starts in (keys_a, vals_a); result in (keys_b, vals_b) when the pass count
-// ceil(end_bit/8) is odd, back in (keys_a, vals_a) when even.  n is read from *n_dev (<= n_cap).
-int sort_pairs_device(cudaStream_t st, const uint32_t* n_dev, uint64_t n_cap, int end_bit, uint64_t* keys_a,
-                      uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, void* ws);
+// radix_sort.cu: stable sort on key bits [begin_bit, end_bit).  Data starts in (keys_a, vals_a); result in
+// (keys_b, vals_b) when the pass count ceil((end_bit-begin_bit)/8) is odd, back in (keys_a, vals_a) when even.
+// n is read from *n_dev (<= n_cap).
+int sort_pairs_device(cudaStream_t st, const uint32_t* n_dev, uint64_t n_cap, int begin_bit, int end_bit,
+                      uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, void* ws);
 
 // ---- preprocess geometry ----
 constexpr int PRE_THREADS = 256;
+
+// ---- depth-first binning (binning.cu) ----
+inline int view_bits(int V) {            // bits needed for view indices 0..V-1
+  int b = 0;
+  while (b < 31 && ((V - 1) >> b)) b++;
+  return b;
+}
+inline int vis_sort_end_bit(int V) { return 32 + view_bits(V); }
 
 // ---- PTX helpers: mbarrier + 1D bulk async copy (TMA unit, SASS UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

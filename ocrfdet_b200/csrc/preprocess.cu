@@ -22,9 +22,9 @@
 
 namespace ocrf {
 
-constexpr uint64_t SCAN_FLAG_LOCAL = 1ull << 62;
-constexpr uint64_t SCAN_FLAG_INCL = 2ull << 62;
-constexpr uint64_t SCAN_VALUE_MASK = (1ull << 62) - 1;
+constexpr unsigned long long SCAN_FLAG_LOCAL = 1ull << 62;
+constexpr unsigned long long SCAN_FLAG_INCL = 2ull << 62;
+constexpr unsigned long long SCAN_VALUE_MASK = (1ull << 62) - 1;
 
 __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
     OcrfShape sh, int blocks_per_view, const float* __restrict__ means3D, const float* __restrict__ scales,
@@ -32,13 +32,14 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
     const float* __restrict__ shs, const Camera* __restrict__ cams, float scale_modifier, int prefiltered,
     int32_t* __restrict__ radii, uint32_t* __restrict__ header, float* __restrict__ depths, float2* __restrict__ xy,
     float4* __restrict__ conic_opacity, uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ offsets,
-    float* __restrict__ rgb, uint8_t* __restrict__ clamped, unsigned long long* __restrict__ scan_status) {
+    float* __restrict__ rgb, uint8_t* __restrict__ clamped, unsigned long long* __restrict__ scan_status,
+    uint64_t* __restrict__ vis_keys, uint32_t* __restrict__ vis_vals, uint32_t* __restrict__ view_start) {
   __shared__ __align__(16) float s_pos[PRE_THREADS * 3];
   __shared__ __align__(16) float s_scl[PRE_THREADS * 3];
   __shared__ Camera s_cam;
-  __shared__ uint32_t s_warp_tot[PRE_THREADS / 32];
+  __shared__ unsigned long long s_warp_tot[PRE_THREADS / 32];
   __shared__ uint32_t s_ticket;
-  __shared__ uint32_t s_prefix;
+  __shared__ unsigned long long s_prefix;
 
   const int tid = threadIdx.x;
   if (tid == 0) s_ticket = atomicAdd(&header[HDR_TICKET], 1u);
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
   __syncthreads();
 
   uint32_t my_tiles = 0;
+  float my_depth = 0.f;
   const size_t o = (size_t)v * sh.P + i0 + tid;  // index into the per-(view, Gaussian) arrays
   if (tid < n) {
     int rad_out = 0;
@@ -136,6 +138,7 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
             }
           }
           depths[o] = tz;
+          my_depth = tz;
           xy[o] = make_float2(px, py);
           conic_opacity[o] = make_float4(__fmul_rn(c, det_inv), __fmul_rn(b, -det_inv), __fmul_rn(a, det_inv),
                                          __ldg(opacities + gbase + tid));
@@ -150,32 +153,34 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
     tiles_touched[o] = my_tiles;
   }
 
-  // ---- CTA-wide inclusive scan of my_tiles, chained across CTAs by decoupled look-back ----
+  // ---- CTA-wide inclusive scan, chained across CTAs by decoupled look-back.  One 64-bit value carries
+  //      two counters: low word = tiles touched (-> offsets), high word = visible Gaussians (-> the
+  //      compact slot of every visible Gaussian in the (view | depth) sort input). ----
   const int lane = tid & 31, warp = tid >> 5;
-  uint32_t incl = my_tiles;
+  unsigned long long incl = ((unsigned long long)(my_tiles != 0) << 32) | my_tiles;
 #pragma unroll
   for (int d = 1; d < 32; d <<= 1) {
-    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, d);
     if (lane >= d) incl += t;
   }
   if (lane == 31) s_warp_tot[warp] = incl;
   __syncthreads();
-  uint32_t warp_off = 0, cta_total = 0;
+  unsigned long long warp_off = 0, cta_total = 0;
 #pragma unroll
   for (int w = 0; w < PRE_THREADS / 32; w++) {
-    const uint32_t t = s_warp_tot[w];
+    const unsigned long long t = s_warp_tot[w];
     if (w < warp) warp_off += t;
     cta_total += t;
   }
   if (tid == 0) {
-    uint64_t excl = 0;
+    unsigned long long excl = 0;
     if (bid == 0) {
-      atomicExch(&scan_status[0], SCAN_FLAG_INCL | (uint64_t)cta_total);
+      atomicExch(&scan_status[0], SCAN_FLAG_INCL | cta_total);
     } else {
-      atomicExch(&scan_status[bid], SCAN_FLAG_LOCAL | (uint64_t)cta_total);
+      atomicExch(&scan_status[bid], SCAN_FLAG_LOCAL | cta_total);
       int look = bid - 1;
       while (true) {
-        const uint64_t st = *reinterpret_cast<volatile unsigned long long*>(&scan_status[look]);
+        const unsigned long long st = *reinterpret_cast<volatile unsigned long long*>(&scan_status[look]);
         if ((st >> 62) == 0) continue;  // predecessor not published yet
         excl += st & SCAN_VALUE_MASK;
         if ((st >> 62) == 2) break;
@@ -183,11 +188,24 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
       }
       atomicExch(&scan_status[bid], SCAN_FLAG_INCL | (excl + cta_total));
     }
-    s_prefix = (uint32_t)excl;
-    if (bid == (int)gridDim.x - 1) header[HDR_NUM_PAIRS] = (uint32_t)(excl + cta_total);
+    s_prefix = excl;
+    if (i0 == 0) view_start[v] = (uint32_t)(excl >> 32);
+    if (bid == (int)gridDim.x - 1) {
+      header[HDR_NUM_PAIRS] = (uint32_t)(excl + cta_total);
+      header[HDR_NUM_VIS] = (uint32_t)((excl + cta_total) >> 32);
+      view_start[sh.V] = (uint32_t)((excl + cta_total) >> 32);
+    }
   }
   __syncthreads();
-  if (tid < n) offsets[o] = s_prefix + warp_off + incl;
+  if (tid < n) {
+    const unsigned long long mine = s_prefix + warp_off + incl;
+    offsets[o] = (uint32_t)mine;
+    if (my_tiles != 0) {
+      const uint32_t slot = (uint32_t)(mine >> 32) - 1;
+      vis_keys[slot] = ((uint64_t)(uint32_t)v << 32) | __float_as_uint(my_depth);
+      vis_vals[slot] = (uint32_t)o;
+    }
+  }
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
@@ -216,6 +234,12 @@ extern "C" int ocrf_geom_layout(const OcrfShape* sh, int use_sh, OcrfGeomLayout*
   out->offsets = off;       off = align128(off + n * 4);
   out->rgb = off;           off = align128(off + (use_sh ? n * 12 : 0));
   out->clamped = off;       off = align128(off + (use_sh ? n * 3 : 0));
+  out->vis_keys = off;      off = align128(off + n * 8);
+  out->vis_keys_tmp = off;  off = align128(off + n * 8);
+  out->vis_vals = off;      off = align128(off + n * 4);
+  out->vis_vals_tmp = off;  off = align128(off + n * 4);
+  out->view_start = off;    off = align128(off + ((size_t)sh->V + 1) * 4);
+  out->vis_sort_ws = off;   off = align128(off + sort_ws_layout(n ? n : 1).total + 128);
   out->total = off + 128;
   return 0;
 }
@@ -243,7 +267,11 @@ extern "C" int ocrf_preprocess_forward(void* stream, const OcrfShape* sh, const 
       scale_modifier, prefiltered, radii, at<uint32_t>(geom_ws, L.header), at<float>(geom_ws, L.depths),
       at<float2>(geom_ws, L.xy), at<float4>(geom_ws, L.conic_opacity), at<uint32_t>(geom_ws, L.tiles_touched),
       at<uint32_t>(geom_ws, L.offsets), at<float>(geom_ws, L.rgb), at<uint8_t>(geom_ws, L.clamped),
-      at<unsigned long long>(geom_ws, L.scan_status));
+      at<unsigned long long>(geom_ws, L.scan_status),
+      // the sort of the visible Gaussians ends in (vis_keys, vis_vals): start in the tmp half when its pass count is odd
+      at<uint64_t>(geom_ws, (((vis_sort_end_bit(sh->V) + 7) / 8) & 1) ? L.vis_keys_tmp : L.vis_keys),
+      at<uint32_t>(geom_ws, (((vis_sort_end_bit(sh->V) + 7) / 8) & 1) ? L.vis_vals_tmp : L.vis_vals),
+      at<uint32_t>(geom_ws, L.view_start));
   OCRF_CHECK_LAST();
   return 0;
 }

@@ -32,8 +32,8 @@ __device__ __forceinline__ uint32_t effective_n(const uint32_t* n_dev, uint64_t 
 
 __global__ void __launch_bounds__(SORT_THREADS) sort_histogram_kernel(const uint64_t* __restrict__ keys,
                                                                       const uint32_t* __restrict__ n_dev,
-                                                                      uint64_t n_cap, int passes, int end_bit,
-                                                                      uint32_t* __restrict__ hist) {
+                                                                      uint64_t n_cap, int passes, int begin_bit,
+                                                                      int end_bit, uint32_t* __restrict__ hist) {
   __shared__ uint32_t s_hist[SORT_MAX_PASSES * 256];
   const uint32_t n = effective_n(n_dev, n_cap);
   for (int i = threadIdx.x; i < passes * 256; i += SORT_THREADS) s_hist[i] = 0;
@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_histogram_kernel(const uint
   for (uint64_t i = (uint64_t)blockIdx.x * SORT_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * SORT_THREADS) {
     const uint64_t k = keys[i];
     for (int p = 0; p < passes; p++) {
-      const int shift = p * 8;
+      const int shift = begin_bit + p * 8;
       const int bits = min(8, end_bit - shift);
       atomicAdd(&s_hist[p * 256 + (uint32_t)((k >> shift) & ((1u << bits) - 1))], 1u);
     }
@@ -177,10 +177,10 @@ constexpr size_t SORT_SMEM_BYTES = SORT_TILE * 12 + (SORT_WARPS * 256 + 256 + 25
 
 // Sorts n_cap-bounded pairs; data starts in (keys_a, vals_a) and the result lands in (keys_b, vals_b)
 // when `passes` is odd, in (keys_a, vals_a) when it is even -- callers pick a/b accordingly.
-int sort_pairs_device(cudaStream_t st, const uint32_t* n_dev, uint64_t n_cap, int end_bit, uint64_t* keys_a,
-                               uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, void* ws) {
-  if (end_bit <= 0 || end_bit > 64) return OCRF_EINVAL;
-  const int passes = (end_bit + 7) / 8;
+int sort_pairs_device(cudaStream_t st, const uint32_t* n_dev, uint64_t n_cap, int begin_bit, int end_bit,
+                      uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, void* ws) {
+  if (begin_bit < 0 || end_bit <= begin_bit || end_bit > 64) return OCRF_EINVAL;
+  const int passes = (end_bit - begin_bit + 7) / 8;
   if (n_cap == 0) return 0;
   static bool attr_set = false;
   if (!attr_set) {
@@ -194,13 +194,13 @@ int sort_pairs_device(cudaStream_t st, const uint32_t* n_dev, uint64_t n_cap, in
   cudaMemsetAsync(ws, 0, L.status + (size_t)passes * (tiles + 1) * 256 * 4, st);
   uint32_t* hist = at<uint32_t>(ws, L.hist);
   const int hgrid = (int)min((uint64_t)NUM_SMS * 8, (n_cap + SORT_THREADS * 4 - 1) / (SORT_THREADS * 4));
-  sort_histogram_kernel<<<hgrid, SORT_THREADS, 0, st>>>(keys_a, n_dev, n_cap, passes, end_bit, hist);
+  sort_histogram_kernel<<<hgrid, SORT_THREADS, 0, st>>>(keys_a, n_dev, n_cap, passes, begin_bit, end_bit, hist);
   uint64_t* kin = keys_a;
   uint32_t* vin = vals_a;
   uint64_t* kout = keys_b;
   uint32_t* vout = vals_b;
   for (int p = 0; p < passes; p++) {
-    const int shift = p * 8;
+    const int shift = begin_bit + p * 8;
     const int bits = end_bit - shift < 8 ? end_bit - shift : 8;
     sort_onesweep_kernel<<<(unsigned)tiles, SORT_THREADS, SORT_SMEM_BYTES, st>>>(
         kin, vin, kout, vout, n_dev, n_cap, shift, bits, hist + p * 256,
@@ -241,6 +241,6 @@ extern "C" int ocrf_sort_pairs(void* stream, uint64_t n, int end_bit, const uint
   uint32_t* n_dev = at<uint32_t>(ws, L.total);
   int rc = 0;
   store_u32_kernel<<<1, 1, 0, st>>>(n_dev, (uint32_t)n);
-  rc = sort_pairs_device(st, n_dev, n, end_bit, ka, va, kb, vb, ws);
+  rc = sort_pairs_device(st, n_dev, n, 0, end_bit, ka, va, kb, vb, ws);
   return rc;
 }

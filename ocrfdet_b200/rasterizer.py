@@ -18,6 +18,7 @@ PyTorch is plumbing here (device memory, streams, autograd glue); all compute is
 libocrf_raster.so and there is no CPU / eager fallback.
 """
 import ctypes as C
+import os
 from typing import NamedTuple, Optional
 
 import torch
@@ -138,6 +139,7 @@ class _RasterizeBatch(torch.autograd.Function):
         binl = _Workspaces.bin_layout(shape, capacity)
         binning = torch.empty(binl.total, dtype=torch.uint8, device=dev)
         check(L.ocrf_bin_forward(stream, C.byref(shape), C.c_uint64(capacity), ptr(radii), ptr(colors), int(use_sh),
+                                 C.c_uint32(_lib.OCRF_BIN_PAIR_SORT if cfg.get("binning") == "pairsort" else 0),
                                  ptr(geom), ptr(binning), ptr(image)), "ocrf_bin_forward")
         _stage("binning")
         check(L.ocrf_render_forward(stream, C.byref(shape), C.c_uint64(capacity), ptr(colors), int(use_sh), ptr(bg),
@@ -149,7 +151,8 @@ class _RasterizeBatch(torch.autograd.Function):
         _LAST_HEADER = geom[ws.geom.header:ws.geom.header + 8]
         if KEEP_STATE:
             _LAST_STATE = dict(shape=shape, layouts=(ws.geom, binl, ws.image), geom=geom, binning=binning, image=image,
-                               radii=radii, capacity=capacity)
+                               radii=radii, capacity=capacity, colors=colors, use_sh=use_sh,
+                               binning_mode="pairsort" if cfg.get("binning") == "pairsort" else "split")
         ctx.shape, ctx.cfg, ctx.capacity, ctx.use_sh = shape, cfg, capacity, use_sh
         ctx.num_rendered = num_pairs
         ctx.layouts = (ws.geom, binl, ws.image)
@@ -206,10 +209,13 @@ def _stage(name):
         STAGE_HOOK(name)
 
 
-def last_state():
+def last_state(reference_lists=False):
     """Typed views into the workspaces of the most recent forward (requires KEEP_STATE = True).
 
     Mirrors what the reference keeps in its geomBuffer / binningBuffer / imgBuffer blobs (PKG:97).
+    With `reference_lists=True` and the default (depth-first) binning, the reference's own algorithm --
+    sort every (tile | depth) pair -- is additionally run on the same geometry state and its results are
+    returned as `keys_ref`, `point_list_ref`, `records_ref`, `ranges_ref`, `ranges_render_ref`.
     Reading `num_pairs` synchronises.
     """
     st = _LAST_STATE
@@ -225,33 +231,50 @@ def last_state():
         nbytes = count * torch.empty((), dtype=dtype).element_size()
         return buf[off:off + nbytes].view(dtype).view(*dims)
 
-    hdr = view(geom, g.header, 2, torch.int32, 2).cpu()
+    hdr = view(geom, g.header, 4, torch.int32, 4).cpu()
     N = int(hdr[0]) & 0xFFFFFFFF
     if N > st["capacity"]:
         N = 0
     out = dict(
-        num_pairs=N, error=int(hdr[1]), radii=st["radii"],
+        num_pairs=N, error=int(hdr[1]), num_visible=int(hdr[3]) & 0xFFFFFFFF, radii=st["radii"], binning=st["binning_mode"],
         depths=view(geom, g.depths, n, torch.float32, V, P), xy=view(geom, g.xy, 2 * n, torch.float32, V, P, 2),
         conic_opacity=view(geom, g.conic_opacity, 4 * n, torch.float32, V, P, 4),
         tiles_touched=view(geom, g.tiles_touched, n, torch.int32, V, P),
         offsets=view(geom, g.offsets, n, torch.int32, V * P),
-        keys=view(binning, b.keys, N, torch.int64, N), point_list=view(binning, b.point_list, N, torch.int32, N),
         ranges=view(image, im.ranges, 2 * V * tiles, torch.int32, V, tiles, 2),
+        ranges_render=view(image, im.ranges_render, 2 * V * tiles, torch.int32, V, tiles, 2),
+        records=view(binning, b.records, 12 * N, torch.int32, N, 12),
         final_T=view(image, im.final_T, V * H * W, torch.float32, V, H, W),
         n_contrib=view(image, im.n_contrib, V * H * W, torch.int32, V, H, W),
         max_contrib=view(image, im.max_contrib, V * tiles, torch.int32, V, tiles))
+    out["keys"] = view(binning, b.keys, N, torch.int64, N)
+    out["point_list"] = view(binning, b.point_list, N, torch.int32, N)
+    if reference_lists and st["binning_mode"] != "pairsort":
+        L = _lib.lib()
+        bin2 = torch.empty_like(binning)
+        img2 = torch.empty_like(image)
+        check(L.ocrf_bin_forward(current_stream(), C.byref(shape), C.c_uint64(st["capacity"]), ptr(st["radii"]),
+                                 ptr(st["colors"]), int(st["use_sh"]), C.c_uint32(_lib.OCRF_BIN_PAIR_SORT), ptr(geom),
+                                 ptr(bin2), ptr(img2)), "ocrf_bin_forward(pair sort)")
+        out["keys_ref"] = view(bin2, b.keys, N, torch.int64, N)
+        out["point_list_ref"] = view(bin2, b.point_list, N, torch.int32, N)
+        out["records_ref"] = view(bin2, b.records, 12 * N, torch.int32, N, 12)
+        out["ranges_ref"] = view(img2, im.ranges, 2 * V * tiles, torch.int32, V, tiles, 2)
+        out["ranges_render_ref"] = view(img2, im.ranges_render, 2 * V * tiles, torch.int32, V, tiles, 2)
     return out
 
 
 def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors_precomp=None, shs=None, scales=None,
                  rotations=None, cov3D_precomp=None, means2D=None, scale_modifier=1.0, sh_degree=0, prefiltered=False,
-                 pair_capacity: Optional[int] = None):
+                 pair_capacity: Optional[int] = None, binning: Optional[str] = None):
     """Render V = cams.shape[0] views of S = means3D.shape[0] samples in one launch sequence.
 
     means3D [S,P,3]; opacities [S,P,1]; colors_precomp [S,P,C] or shs [S,P,M,3]; scales [S,P,3] and
     rotations [S,P,4], or cov3D_precomp [S,P,6]; cams from `pack_cameras`, view v looks at sample
     v // (V // S).  Returns (color [V,C,H,W], radii [V,P], depth [V,1,H,W], opacity [V,1,H,W]).
     `means2D` ([V,P,3] zeros, requires_grad) receives dL/dmean2D as in the reference.
+    `binning`: None / "split" = depth-sort the visible Gaussians, then split them stably into tiles (default);
+    "pairsort" = the reference's algorithm (sort every (tile, Gaussian) pair).  Identical keys / lists / images.
     `pair_capacity`: if given, the binning workspace is sized for that many (tile, Gaussian) pairs
     and NO host synchronisation happens (CUDA-graph friendly); an overflow renders background and
     raises on the next `check_overflow`.
@@ -272,7 +295,8 @@ def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors
     if means2D is None:
         means2D = torch.zeros((V, P, 3), dtype=torch.float32, device=means3D.device)
     cfg = dict(W=int(image_width), H=int(image_height), scale_modifier=float(scale_modifier), sh_degree=int(sh_degree),
-               prefiltered=bool(prefiltered), pair_capacity=pair_capacity)
+               prefiltered=bool(prefiltered), pair_capacity=pair_capacity,
+               binning=binning if binning is not None else os.environ.get("OCRF_BINNING", "split"))
     if P == 0:
         Cc = 3 if shs is not None else colors_precomp.shape[-1]
         z = lambda c: torch.zeros((V, c, cfg["H"], cfg["W"]), dtype=torch.float32, device=means3D.device)  # noqa

@@ -39,13 +39,17 @@ SCENES = [
 ]
 
 
+@pytest.mark.parametrize("binning", ["split", "pairsort"])
 @pytest.mark.parametrize("kind,kw", SCENES)
-def test_preprocess_and_binning_bit_exact(kind, kw):
+def test_preprocess_and_binning_bit_exact(kind, kw, binning, monkeypatch):
+    # both stage-2 algorithms (depth-ordered tile split / the reference's pair sort) must give the same bits
+    monkeypatch.setenv("OCRF_BINNING", binning)
     g, cams = util.small_scene(kind, **kw)
     cam, W, H = cams[0], kw["W"], kw["H"]
     bg = [0.0, 0.0, 0.0]
     (_color, radii, _depth, _op), _, _ = _render_single(g, cam, bg)
-    st = R.last_state()
+    st = R.last_state(reference_lists=True)
+    assert st["binning"] == binning
     want, wst = util.oracle_forward(g, cam, W, H, bg)
     pre, b = wst["pre"], wst["bin"]
     vis = pre["radii"] > 0
@@ -60,6 +64,19 @@ def test_preprocess_and_binning_bit_exact(kind, kw):
     assert np.array_equal(st["keys"].cpu().numpy().view(np.uint64), b["keys"])
     assert np.array_equal(st["point_list"].cpu().numpy().view(np.uint32), b["point_list"])
     assert np.array_equal(st["ranges"][0].cpu().numpy().view(np.uint32), b["ranges"])
+    if binning == "split":
+        # depth-first binning vs the reference's pair sort on the same geometry state: identical bits everywhere
+        for k in ("keys", "point_list", "ranges", "ranges_render"):
+            assert torch.equal(st[k], st[k + "_ref"]), k
+        rr = st["ranges_render"][0].cpu().numpy()
+        rec, ref = st["records"].cpu().numpy(), st["records_ref"].cpu().numpy()
+        full = st["ranges"][0].cpu().numpy()
+        for (lo, hi), (flo, fhi) in zip(rr, full):
+            assert np.array_equal(rec[lo:hi], ref[lo:hi])
+            # culled records are a sub-list of the tile's reference list: "orig" strictly increases and indexes it
+            orig = rec[lo:hi, 6]
+            assert np.all(np.diff(orig) > 0) and (hi == lo or (orig[0] >= 1 and orig[-1] <= fhi - flo))
+            assert np.array_equal(rec[lo:hi, 10], b["point_list"][flo:fhi][orig - 1].astype(np.int32))
 
 
 @pytest.mark.parametrize("kind,kw", SCENES)
@@ -103,7 +120,9 @@ def test_backward_gradients(kind, kw):
     assert float(means2D.grad[:, 2].abs().max()) == 0.0
 
 
-def test_batch_matches_single_views():
+@pytest.mark.parametrize("binning", ["split", "pairsort"])
+def test_batch_matches_single_views(binning, monkeypatch):
+    monkeypatch.setenv("OCRF_BINNING", binning)
     W, H = 352, 128
     g, cams = util.small_scene("ring", P=20000, seed=5, W=W, H=H, n_views=6)
     bg = [0.0, 0.0, 0.0]

@@ -15,7 +15,9 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not ref.available(), reason="o
 @pytest.mark.parametrize("kind,kw", [("frustum", dict(P=10000, seed=21, W=704, H=256)),
                                      ("ring", dict(P=30000, seed=22, W=704, H=256)),
                                      ("frustum", dict(P=800, seed=23, W=90, H=70))])
-def test_against_reference_cuda(kind, kw):
+@pytest.mark.parametrize("binning", ["split", "pairsort"])
+def test_against_reference_cuda(kind, kw, binning, monkeypatch):
+    monkeypatch.setenv("OCRF_BINNING", binning)
     g, cams = util.small_scene(kind, **kw)
     cam, W, H = cams[0], kw["W"], kw["H"]
     bg = [0.4, 0.3, 0.2]
@@ -33,7 +35,7 @@ def test_against_reference_cuda(kind, kw):
     color, radii, _depth = R.GaussianRasterizer(st)(means3D=gc["means3D"], means2D=means2D, opacities=gc["opacities"],
                                                     colors_precomp=gc["colors"], scales=gc["scales"],
                                                     rotations=gc["rotations"])
-    ms = R.last_state()
+    ms = R.last_state(reference_lists=True)
     # ---- integer / index state: bit-exact ----
     assert ms["num_pairs"] == rN
     assert torch.equal(radii, rradii)
