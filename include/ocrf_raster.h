@@ -43,8 +43,11 @@ extern "C" {
 #define OCRF_CAM_STRIDE 40
 /* bytes per packed (tile, Gaussian) record consumed by the blend kernels */
 #define OCRF_RECORD_BYTES 48
-/* floats per (view, Gaussian) screen-space gradient record: dmean2D.xy, dconic.ABC, dopacity, pad[2] */
-#define OCRF_GGRAD_STRIDE 8
+/* DOUBLES per (view, Gaussian) screen-space gradient record: dmean2D.xy, dconic.ABC, dopacity.
+ * Per-tile partial sums are formed in fp32 (fixed order); the sum over the tiles a Gaussian touches -- the part
+ * whose order is undefined because it goes through global reductions -- is accumulated in fp64, which makes the
+ * gradients reproducible run to run to fp32 precision and keeps the ill-conditioned conic chain well fed. */
+#define OCRF_GGRAD_STRIDE 6
 
 typedef struct OcrfShape {
   int32_t S;                /* samples (independent Gaussian sets) */
@@ -145,7 +148,7 @@ int ocrf_render_forward(void* stream, const OcrfShape* shape, uint64_t pair_capa
 int ocrf_render_backward(void* stream, const OcrfShape* shape, uint64_t pair_capacity, const float* colors,
                          int use_sh, const float* bg, const void* geom_ws, const void* bin_ws,
                          const void* image_ws, const float* dL_dcolor, const float* dL_dopacity_map,
-                         float* ggrad, float* dL_dcolors);
+                         double* ggrad, float* dL_dcolors);
 
 /* backward.cu:144-396: screen-space gradients -> dL_dmeans3D [S,P,3], dL_dmeans2D [V,P,3],
  * dL_dopacities [S,P], dL_dscales [S,P,3] + dL_drotations [S,P,4] (or dL_dcov3D [S,P,6] when
@@ -154,7 +157,7 @@ int ocrf_render_backward(void* stream, const OcrfShape* shape, uint64_t pair_cap
 int ocrf_preprocess_backward(void* stream, const OcrfShape* shape, const float* means3D, const float* scales,
                              const float* rotations, const float* cov3D_precomp, const float* shs,
                              const float* cams, float scale_modifier, const int32_t* radii, const void* geom_ws,
-                             const float* ggrad, const float* dL_dcolors_view, float* dL_dmeans3D,
+                             const double* ggrad, const float* dL_dcolors_view, float* dL_dmeans3D,
                              float* dL_dmeans2D, float* dL_dopacities, float* dL_dscales, float* dL_drotations,
                              float* dL_dcov3D, float* dL_dshs);
 

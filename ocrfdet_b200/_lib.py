@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "libocrf_raster.so")
 
 OCRF_CAM_STRIDE = 40
 OCRF_RECORD_BYTES = 48
-OCRF_GGRAD_STRIDE = 8
+OCRF_GGRAD_STRIDE = 6
 ABI_VERSION = 1
 OCRF_EINVAL = -1
 OCRF_ECAPACITY = -2

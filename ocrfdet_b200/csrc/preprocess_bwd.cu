@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
     OcrfShape sh, const float* __restrict__ means3D, const float* __restrict__ scales,
     const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp, const float* __restrict__ shs,
     const Camera* __restrict__ cams, float scale_modifier, const int32_t* __restrict__ radii,
-    const uint8_t* __restrict__ clamped, const float* __restrict__ ggrad, const float* __restrict__ dL_dcolors_view,
+    const uint8_t* __restrict__ clamped, const double* __restrict__ ggrad, const float* __restrict__ dL_dcolors_view,
     float* __restrict__ dL_dmeans3D, float* __restrict__ dL_dmeans2D, float* __restrict__ dL_dopacities,
     float* __restrict__ dL_dscales, float* __restrict__ dL_drotations, float* __restrict__ dL_dcov3D,
     float* __restrict__ dL_dshs) {
@@ -84,7 +84,10 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
   } else {
     q = *reinterpret_cast<const float4*>(rotations + gi * 4);
     sc[0] = scales[3 * gi]; sc[1] = scales[3 * gi + 1]; sc[2] = scales[3 * gi + 2];
-    cov3d_f64(sc, scale_modifier, q, c6);
+    float c6f[6];  // the forward's own float32 covariance: gradients are taken at the point the forward evaluated
+    cov3d_from_scale_rot(sc[0], sc[1], sc[2], scale_modifier, q, c6f);
+#pragma unroll
+    for (int k = 0; k < 6; k++) c6[k] = c6f[k];
   }
   const double S[3][3] = {{c6[0], c6[1], c6[2]}, {c6[1], c6[3], c6[4]}, {c6[2], c6[4], c6[5]}};
 
@@ -102,10 +105,9 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
       const Camera& cam = s_cams[lv];
       const float* vm = cam.view;
       const float* pm = cam.proj;
-      const float4 ga = *reinterpret_cast<const float4*>(ggrad + o * OCRF_GGRAD_STRIDE);      // dmx dmy dA dB
-      const float2 gb = *reinterpret_cast<const float2*>(ggrad + o * OCRF_GGRAD_STRIDE + 4);  // dC dOp
-      g2x = ga.x; g2y = ga.y;
-      gop += gb.y;
+      const double* gr = ggrad + o * OCRF_GGRAD_STRIDE;  // dmx dmy dA dB dC dOp
+      g2x = gr[0]; g2y = gr[1];
+      gop += gr[5];
       const double fy = sh.H / (2.0 * cam.tanfovy), fx = sh.W / (2.0 * cam.tanfovx);
       // ---- conic -> cov2D -> cov3D and view-space mean ----
       double t[3];
@@ -133,7 +135,7 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
       const double a = (T0[0] * ST0[0] + T0[1] * ST0[1] + T0[2] * ST0[2]) + (double)0.3f;
       const double b = T0[0] * ST1[0] + T0[1] * ST1[1] + T0[2] * ST1[2];
       const double c = (T1[0] * ST1[0] + T1[1] * ST1[1] + T1[2] * ST1[2]) + (double)0.3f;
-      const double gA = ga.z, gB = ga.w, gC = gb.x;
+      const double gA = gr[2], gB = gr[3], gC = gr[4];
       const double denom = a * c - b * b;
       const double d2i = 1.0 / ((denom * denom) + (double)0.0000001f);
       double da = 0., db = 0., dc = 0.;
@@ -254,7 +256,7 @@ using namespace ocrf;
 extern "C" int ocrf_preprocess_backward(void* stream, const OcrfShape* sh, const float* means3D, const float* scales,
                                         const float* rotations, const float* cov3D_precomp, const float* shs,
                                         const float* cams, float scale_modifier, const int32_t* radii,
-                                        const void* geom_ws, const float* ggrad, const float* dL_dcolors_view,
+                                        const void* geom_ws, const double* ggrad, const float* dL_dcolors_view,
                                         float* dL_dmeans3D, float* dL_dmeans2D, float* dL_dopacities, float* dL_dscales,
                                         float* dL_drotations, float* dL_dcov3D, float* dL_dshs) {
   if (!sh || !means3D || !cams || !radii || !geom_ws || !ggrad || !dL_dmeans3D || !dL_dopacities) return OCRF_EINVAL;

@@ -8,7 +8,7 @@
 //     with a 14-shuffle butterfly (8-value reduce-scatter + one scalar), only when at least one
 //     lane contributed;
 //   * warps then combine in shared memory, and each record issues ONE set of global reductions per
-//     tile: a 16-byte and an 8-byte vector red for (dmean2D, dconic, dopacity) and three scalar
+//     tile: six fp64 reds for (dmean2D, dconic, dopacity) and three scalar
 //     reds for the colour -- 256x fewer global atomics than the reference in the dense case.
 // The arithmetic follows SURVEY.md appendix A5 (T recovered by division, suffix colour recurrence,
 // background term, no clamp mask) plus the opacity-map term  +T_final/(1-alpha) * dL/dO.
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
     int W, int H, int P, int views_per_sample, int colors_per_view, const uint2* __restrict__ ranges /* culled lists */,
     const Record* __restrict__ records, const float* __restrict__ bg, const float* __restrict__ final_T,
     const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ max_contrib,
-    const float* __restrict__ dL_dpix, const float* __restrict__ dL_dopa, float* __restrict__ ggrad,
+    const float* __restrict__ dL_dpix, const float* __restrict__ dL_dopa, double* __restrict__ ggrad,
     float* __restrict__ dL_dcolors) {
   constexpr int NT = TILE_PIX / PPT;
   constexpr int NW = NT / 32;
@@ -170,19 +170,19 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
           dL_dalpha *= T[p];
           last_alpha[p] = alpha[p];
           dL_dalpha += gob[p] * rcp;
-          const float dL_dG = b.y * dL_dalpha;
-          const float gdx = G[p] * dx[p], gdy = G[p] * dy[p];
-          const float dG_ddelx = -gdx * a.z - gdy * a.w;
-          const float dG_ddely = -gdy * b.x - gdx * a.w;
-          v[0] += dL_dG * dG_ddelx * ddelx_dx;
-          v[1] += dL_dG * dG_ddely * ddely_dy;
-          v[2] += -0.5f * gdx * dx[p] * dL_dG;
-          v[3] += -0.5f * gdx * dy[p] * dL_dG;
-          v[4] += -0.5f * gdy * dy[p] * dL_dG;
-          v[5] += G[p] * dL_dalpha;
-          v[6] += w * g0[p];
-          v[7] += w * g1[p];
-          v8 += w * g2[p];
+          // raw moments of t = dL/dG * G about the Gaussian's mean; the per-record factors (conic, -1/2,
+          // NDC scale, 1/opacity) are applied once per record in the flush instead of once per pixel
+          const float t = b.y * dL_dalpha * G[p];
+          const float tdx = t * dx[p], tdy = t * dy[p];
+          v[0] += t;
+          v[1] += tdx;
+          v[2] += tdy;
+          v[3] = fmaf(tdx, dx[p], v[3]);
+          v[4] = fmaf(tdx, dy[p], v[4]);
+          v[5] = fmaf(tdy, dy[p], v[5]);
+          v[6] = fmaf(w, g0[p], v[6]);
+          v[7] = fmaf(w, g1[p], v[7]);
+          v8 = fmaf(w, g2[p], v8);
         }
         const float r8 = butterfly8(v, lane);
         const float r1 = warp_sum(v8);
@@ -212,10 +212,18 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
         }
       }
       if (!hit) continue;
-      const uint32_t id = s_rec[st][j].id;
-      float* gg = ggrad + ((size_t)view * P + id) * OCRF_GGRAD_STRIDE;
-      atomicAdd(reinterpret_cast<float4*>(gg), make_float4(q[0], q[1], q[2], q[3]));
-      atomicAdd(reinterpret_cast<float2*>(gg + 4), make_float2(q[4], q[5]));
+      const Record rec = s_rec[st][j];
+      const uint32_t id = rec.id;
+      // q = (m0, mx, my, mxx, mxy, myy): dmean2D = -(conic . m1) * NDC scale, dconic = -1/2 m2, dopacity = m0 / opacity
+      const float gmx = -(rec.cA * q[1] + rec.cB * q[2]) * ddelx_dx;
+      const float gmy = -(rec.cC * q[2] + rec.cB * q[1]) * ddely_dy;
+      double* gg = ggrad + ((size_t)view * P + id) * OCRF_GGRAD_STRIDE;
+      atomicAdd(gg + 0, (double)gmx);
+      atomicAdd(gg + 1, (double)gmy);
+      atomicAdd(gg + 2, (double)(-0.5f * q[3]));
+      atomicAdd(gg + 3, (double)(-0.5f * q[4]));
+      atomicAdd(gg + 4, (double)(-0.5f * q[5]));
+      atomicAdd(gg + 5, (double)__fdividef(q[0], rec.op));
       float* gc = dL_dcolors + ((size_t)(colors_per_view ? view : view / views_per_sample) * P + id) * 3;
       atomicAdd(gc, q[6]);
       atomicAdd(gc + 1, q[7]);
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
     const Record* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
     const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
     const uint32_t* __restrict__ max_contrib, const float* __restrict__ dL_dpix, const float* __restrict__ dL_dopa,
-    float* __restrict__ ggrad, float* __restrict__ dL_dfeats) {
+    double* __restrict__ ggrad, float* __restrict__ dL_dfeats) {
   constexpr int NW = TILE_PIX / 32;
   extern __shared__ __align__(16) unsigned char smem_g[];
   Record* s_rec = reinterpret_cast<Record*>(smem_g);                                   // [BATCH]
@@ -404,9 +412,9 @@ __global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
           q[0] += q0.x; q[1] += q0.y; q[2] += q0.z; q[3] += q0.w; q[4] += q1.x; q[5] += q1.y;
         }
       if (!hit) continue;
-      float* gg = ggrad + ((size_t)view * P + s_rec[j].id) * OCRF_GGRAD_STRIDE;
-      atomicAdd(reinterpret_cast<float4*>(gg), make_float4(q[0], q[1], q[2], q[3]));
-      atomicAdd(reinterpret_cast<float2*>(gg + 4), make_float2(q[4], q[5]));
+      double* gg = ggrad + ((size_t)view * P + s_rec[j].id) * OCRF_GGRAD_STRIDE;
+#pragma unroll
+      for (int e = 0; e < 6; e++) atomicAdd(gg + e, (double)q[e]);
     }
   }
 }
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
 template <int CP>
 static int launch_backward_generic(cudaStream_t st, dim3 grid, const OcrfShape* sh, const uint2* ranges, const Record* rec,
                                    const float* colors, const float* bg, const float* fT, const uint32_t* nc,
-                                   const uint32_t* mc, const float* dL_dcolor, const float* dL_dopa, float* ggrad,
+                                   const uint32_t* mc, const float* dL_dcolor, const float* dL_dopa, double* ggrad,
                                    float* dL_dcolors) {
   const size_t dyn = BWDG_BATCH * sizeof(Record) + (size_t)BWDG_BATCH * CP * 4 + (size_t)(TILE_PIX / 32) * BWDG_BATCH * 8 * 4;
   cudaError_t e = cudaFuncSetAttribute(render_backward_generic_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -438,7 +446,7 @@ static int env_int_b(const char* name, int dflt) {
 extern "C" int ocrf_render_backward(void* stream, const OcrfShape* sh, uint64_t pair_capacity, const float* colors,
                                     int use_sh, const float* bg, const void* geom_ws, const void* bin_ws,
                                     const void* image_ws, const float* dL_dcolor, const float* dL_dopacity_map,
-                                    float* ggrad, float* dL_dcolors) {
+                                    double* ggrad, float* dL_dcolors) {
   if (!sh || !bg || !bin_ws || !image_ws || !dL_dcolor || !ggrad || !dL_dcolors) return OCRF_EINVAL;
   (void)geom_ws;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
