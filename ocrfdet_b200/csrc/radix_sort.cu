@@ -106,6 +106,17 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) sort_onesweep_kernel(
     key[i] = loc < n_valid ? keys_in[base + loc] : ~0ull;  // padding ranks behind every valid key of the (last) tile
   }
 
+  // ---- publish this tile's digit counts EARLY (cheap shared-memory histogram) so that successors can
+  //      resolve their look-back while we are still ranking; the stable ranks come afterwards ----
+  s_tile_excl[tid] = 0;  // reused as the counting histogram until the scan below
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < SORT_ITEMS; i++) atomicAdd(&s_tile_excl[(uint32_t)(key[i] >> shift) & digit_mask], 1u);
+  __syncthreads();
+  const uint32_t tile_count = s_tile_excl[tid];
+  uint32_t* my_status = status + (size_t)tile * 256 + tid;
+  atomicExch(my_status, (tile == 0 ? LB_FLAG_INCL : LB_FLAG_LOCAL) | tile_count);
+
   // ---- rank inside the warp: match_any multi-split, one item row at a time (stable) ----
   uint32_t rank[SORT_ITEMS];
   uint32_t* my_hist = s_warp_hist + warp * 256;
@@ -122,19 +133,15 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) sort_onesweep_kernel(
   }
   __syncthreads();
 
-  // ---- per digit (thread t owns digit t): warp offsets, tile count, look-back ----
-  uint32_t tile_count = 0;
+  // ---- per digit (thread t owns digit t): exclusive warp offsets ----
+  {
+    uint32_t run = 0;
 #pragma unroll
-  for (int w = 0; w < SORT_WARPS; w++) {
-    const uint32_t c = s_warp_hist[w * 256 + tid];
-    s_warp_hist[w * 256 + tid] = tile_count;  // exclusive offset of warp w for this digit
-    tile_count += c;
-  }
-  uint32_t* my_status = status + (size_t)tile * 256 + tid;
-  if (tile == 0) {
-    atomicExch(my_status, LB_FLAG_INCL | tile_count);
-  } else {
-    atomicExch(my_status, LB_FLAG_LOCAL | tile_count);
+    for (int w = 0; w < SORT_WARPS; w++) {
+      const uint32_t c = s_warp_hist[w * 256 + tid];
+      s_warp_hist[w * 256 + tid] = run;  // exclusive offset of warp w for this digit
+      run += c;
+    }
   }
   const uint32_t tile_excl = cta_exclusive_scan_256(tile_count, s_scan);
   const uint32_t global_digit_excl = cta_exclusive_scan_256(hist[tid], s_scan);
