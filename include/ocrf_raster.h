@@ -94,8 +94,9 @@ typedef struct OcrfBinLayout {
   size_t records;       /* OCRF_RECORD_BYTES * N: per tile, the records that can reach a pixel of the tile */
   size_t histogram;     /* uint32 [8][256] */
   size_t sort_status;   /* uint32 [passes][sort_tiles][256] + tickets */
-  size_t split_counts;  /* uint32 [V][chunks][tiles] per-chunk tile counts of the depth-ordered tile split */
-  size_t split_tiles;   /* uint32 [2][V*tiles] tile totals and tile offsets */
+  size_t split_counts;  /* depth-first: scanned tiles_touched; multi-split: uint32 [2][V][chunks][tiles] chunk x tile counts */
+  size_t split_tiles;   /* depth-first: look-back state; multi-split: uint32 [3][V*tiles] totals (full, kept), offsets */
+  size_t split_words;   /* capacity of split_counts in 32-bit words */
 } OcrfBinLayout;
 
 typedef struct OcrfImageLayout {
@@ -133,8 +134,11 @@ int ocrf_preprocess_forward(void* stream, const OcrfShape* shape, const float* m
 int ocrf_bin_forward(void* stream, const OcrfShape* shape, uint64_t pair_capacity, const int32_t* radii,
                      const float* colors, int use_sh, uint32_t flags, void* geom_ws, void* bin_ws, void* image_ws);
 /* flags for ocrf_bin_forward */
-#define OCRF_BIN_PAIR_SORT 1u /* force the reference's algorithm (sort all (tile, Gaussian) pairs) instead of the
-                                 depth-ordered tile split; both produce bit-identical keys / point list / ranges */
+#define OCRF_BIN_PAIR_SORT 1u   /* the reference's algorithm: sort all (tile | depth) pairs */
+#define OCRF_BIN_DEPTH_FIRST 2u /* sort the visible Gaussians by depth, emit pairs in that order, sort the tile bits only */
+/* default (0): depth-sort the visible Gaussians, then ONE stable multi-split of the pair stream by tile that writes
+ * the culled records directly; the key / point lists are not materialised on that path.  All three produce
+ * bit-identical records and range tables. */
 
 /* Stage 3 (forward.cu:261-374; median depth per the w-depth fork; opacity = 1 - final_T).
  * bg [C]; out_color [V,C,H,W]; out_depth, out_opacity [V,1,H,W] (either may be NULL). */

@@ -16,6 +16,7 @@ ABI_VERSION = 1
 OCRF_EINVAL = -1
 OCRF_ECAPACITY = -2
 OCRF_BIN_PAIR_SORT = 1
+OCRF_BIN_DEPTH_FIRST = 2
 
 EXPORTS = [
     "ocrf_abi_version", "ocrf_error_string", "ocrf_geom_layout", "ocrf_bin_layout", "ocrf_image_layout",
@@ -39,7 +40,7 @@ class OcrfGeomLayout(C.Structure):
 class OcrfBinLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("total", "keys", "point_list", "keys_tmp", "vals_tmp", "keys_unsorted",
                                           "vals_unsorted", "records", "histogram", "sort_status", "split_counts",
-                                          "split_tiles")]
+                                          "split_tiles", "split_words")]
 
 
 class OcrfImageLayout(C.Structure):

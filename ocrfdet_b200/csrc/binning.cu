@@ -369,8 +369,15 @@ extern "C" int ocrf_bin_layout(const OcrfShape* sh, uint64_t num_pairs, OcrfBinL
   out->sort_status = off + w.status;
   off = align128(off + w.total + 128);
   const size_t nvp = (size_t)sh->V * (sh->P > 0 ? sh->P : 1);
-  out->split_counts = off; off = align128(off + nvp * 4);                       // tiles_touched scanned in depth order
-  out->split_tiles = off;  off = align128(off + ((nvp + 1023) / 1024 + 1) * 8 + 128);  // look-back state + ticket
+  const size_t tiles_v = (size_t)tiles_x(*sh) * tiles_y(*sh);
+  const uint32_t Q = multisplit_chunk_pairs(n);
+  const size_t chunks_max = (n + Q - 1) / Q + 1;
+  const size_t table_words = 2 * (size_t)sh->V * chunks_max * tiles_v;
+  out->split_words = table_words;
+  out->split_counts = off;  // [V*P] tiles_touched scanned in depth order | multi-split chunk x tile tables
+  off = align128(off + (nvp + table_words) * 4);
+  out->split_tiles = off;   // look-back state + ticket of that scan | [3][V*tiles] tile totals / offsets
+  off = align128(off + align128(((nvp + 1023) / 1024 + 1) * 8 + 128) + 3 * (size_t)sh->V * tiles_v * 4);
   out->total = off + 128;
   return 0;
 }
@@ -411,9 +418,10 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
   uint32_t* header = at<uint32_t>(geom_ws, G.header);
   const size_t n = (size_t)sh->V * sh->P;
   const int gxh = tiles_x(*sh), gyh = tiles_y(*sh), tiles_v = gxh * gyh;
-  const bool split = !(flags & OCRF_BIN_PAIR_SORT);
-  (void)tiles_v; (void)gxh; (void)gyh;
-  if (split) {
+  const bool pairsort = (flags & OCRF_BIN_PAIR_SORT) != 0;
+  const bool multisplit = !pairsort && !(flags & OCRF_BIN_DEPTH_FIRST) && tiles_v <= 4096;
+  (void)gxh; (void)gyh;
+  if (!pairsort) {
     // (1) depth-sort the visible Gaussians: same onesweep sort, ~30x fewer elements than the pair sort
     const int vbit = vis_sort_end_bit(sh->V);
     const int vpasses = (vbit + 7) / 8;
@@ -423,7 +431,7 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
     uint32_t* vb = at<uint32_t>(geom_ws, (vpasses & 1) ? G.vis_vals : G.vis_vals_tmp);
     rc = sort_pairs_device(st, header + HDR_NUM_VIS, n, 0, vbit, ka, va, kb, vb, at<char>(geom_ws, G.vis_sort_ws));
     if (rc) return rc;
-    // (2) emit the pairs in depth order; (3) two stable passes over the tile bits only
+    // (2) inclusive scan of tiles_touched in depth order: where every Gaussian's pairs sit in the pair stream
     const uint32_t* vvals = at<uint32_t>(geom_ws, G.vis_vals);
     uint32_t* sorted_offsets = at<uint32_t>(bin_ws, B.split_counts);
     unsigned long long* sstat = at<unsigned long long>(bin_ws, B.split_tiles);
@@ -432,6 +440,17 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
     cudaMemsetAsync(sstat, 0, (sblocks + 1) * 8 + 64, st);
     scan_sorted_tiles_kernel<<<(unsigned)sblocks, 256, 0, st>>>(header, vvals, at<uint32_t>(geom_ws, G.tiles_touched),
                                                                 sorted_offsets, sstat, sticket);
+    if (multisplit) {
+      // (3) one stable multi-split of the pair stream by tile, culled records written directly
+      uint32_t* tile_arrays = at<uint32_t>(bin_ws, B.split_tiles + align128((sblocks + 1) * 8 + 128));
+      rc = multisplit_bin(st, sh, pair_capacity, use_sh, radii, colors, header, at<uint32_t>(geom_ws, G.view_start),
+                          sorted_offsets, vvals, at<float2>(geom_ws, G.xy), at<float4>(geom_ws, G.conic_opacity),
+                          at<float>(geom_ws, G.depths), at<float>(geom_ws, G.rgb), sorted_offsets + n, B.split_words,
+                          tile_arrays, at<uint2>(bin_ws, B.keys), at<uint2>(image_ws, I.ranges),
+                          at<uint2>(image_ws, I.ranges_render), at<Record>(bin_ws, B.records));
+      return rc;
+    }
+    // (3') emit the pairs in depth order, then two stable passes over the tile bits only
     const int end_bit = ocrf_sort_end_bit(sh);
     const int tpasses = (end_bit - 32 + 7) / 8;
     uint64_t* pka = at<uint64_t>(bin_ws, (tpasses & 1) ? B.keys_tmp : B.keys);

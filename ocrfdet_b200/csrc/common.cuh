@@ -92,6 +92,17 @@ inline int view_bits(int V) {            // bits needed for view indices 0..V-1
   return b;
 }
 inline int vis_sort_end_bit(int V) { return 32 + view_bits(V); }
+// multisplit.cu
+struct Record;
+int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity, int use_sh, const int32_t* radii,
+                   const float* colors, uint32_t* header, const uint32_t* view_start, const uint32_t* sorted_offsets,
+                   const uint32_t* vis_vals, const float2* xy, const float4* conic_opacity, const float* depths,
+                   const float* rgb, uint32_t* tables, size_t table_words, uint32_t* tile_arrays, uint2* items,
+                   uint2* ranges, uint2* ranges_render, Record* records);
+inline uint32_t multisplit_chunk_pairs(uint64_t pair_capacity) {  // pairs per chunk: multiples of 4096, <= ~2048 chunks
+  uint64_t rounds = (pair_capacity + 4096ull * 2048 - 1) / (4096ull * 2048);
+  return (uint32_t)((rounds < 1 ? 1 : rounds) * 4096);
+}
 
 // ---- PTX helpers: mbarrier + 1D bulk async copy (TMA unit, SASS UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

@@ -1,0 +1,418 @@
+// Stage 2, fastest algorithm: ONE stable multi-split of the depth-ordered pair stream by tile.
+//
+// After the visible Gaussians of every view are sorted by (view | depth) (binning.cu), the sequence
+//     S = for g in depth order: for tile in rect(g) (row-major): (g, tile)
+// only has to be split STABLY by tile to obtain the reference's per-tile lists
+// (cuda_rasterizer/rasterizer_impl.cu:70-138,303-318: a stable sort by tile of a depth-ordered sequence
+// is the (tile | depth) order, ties in Gaussian-index order).  No pair is ever sorted:
+//   (A) ms_count:   the stream is cut into chunks of equal PAIR count (so the screen-filling Gaussians
+//                   that depth order packs together do not make a serial tail); every chunk enumerates
+//                   its pairs, applies the exact tile cull (binning.cu: tile_can_contribute), counts
+//                   pairs / kept pairs per tile and stores (tile, keep, g) per pair;
+//   (B) two small scans: over the chunks of every tile, and over the tiles -> both range tables;
+//   (C) ms_scatter: every chunk ranks its pairs per tile (warp match_any multi-split, the stable ranking
+//                   of the onesweep sort) and writes the KEPT pairs as 48-byte blend records straight to
+//                   their final slot, with their 1-based position in the tile's full list ("orig").
+// The reference's key / point lists are not materialised on this path; the records and both range tables
+// are bit-identical to what the pair-sort and depth-first paths produce from the same geometry state
+// (tests/test_gpu_parity.py compares them), and `last_state(reference_lists=True)` materialises the
+// reference lists on demand.
+#include "common.cuh"
+
+namespace ocrf {
+
+constexpr int MS_THREADS = 256;
+constexpr int MS_ITEMS = 16;
+constexpr int MS_ROUND = MS_THREADS * MS_ITEMS;  // pairs per round of a chunk
+constexpr int MS_WARPS = MS_THREADS / 32;
+constexpr uint32_t MS_KEEP = 0x80000000u;
+
+__device__ __forceinline__ bool ms_tile_can_contribute(float2 p, float4 co, float px0, float px1, float py0, float py1) {
+  // identical arithmetic to binning.cu:tile_can_contribute (kept in sync by the record-equality tests)
+  const float dxl = p.x - px1, dxh = p.x - px0, dyl = p.y - py1, dyh = p.y - py0;
+  float qmin = 0.f;
+  const bool inside = dxl <= 0.f && dxh >= 0.f && dyl <= 0.f && dyh >= 0.f;
+  if (!inside) {
+    const float A = co.x, B = co.y, Cc = co.z;
+    float q = INFINITY;
+#pragma unroll
+    for (int e = 0; e < 2; e++) {
+      const float ex = e ? dxh : dxl;
+      const float sy = fminf(dyh, fmaxf(dyl, -B * ex / Cc));
+      q = fminf(q, A * ex * ex + 2.f * B * ex * sy + Cc * sy * sy);
+      const float ey = e ? dyh : dyl;
+      const float sx = fminf(dxh, fmaxf(dxl, -B * ey / A));
+      q = fminf(q, A * sx * sx + 2.f * B * sx * ey + Cc * ey * ey);
+    }
+    qmin = q;
+  }
+  const float alpha_max = co.w * __expf(-0.5f * qmin) * 1.001f;
+  return !(alpha_max < 1.0f / 255.0f);
+}
+
+__device__ __forceinline__ void ms_tile_rect(float px, float py, int radius, int gx, int gy, int& x0, int& y0, int& x1,
+                                             int& y1) {
+  const float r = (float)radius;
+  x0 = min(gx, max(0, (int)__fmul_rn(__fsub_rn(px, r), 0.0625f)));
+  y0 = min(gy, max(0, (int)__fmul_rn(__fsub_rn(py, r), 0.0625f)));
+  x1 = min(gx, max(0, (int)__fmul_rn(__fsub_rn(__fadd_rn(__fadd_rn(px, r), 16.f), 1.f), 0.0625f)));
+  y1 = min(gy, max(0, (int)__fmul_rn(__fsub_rn(__fadd_rn(__fadd_rn(py, r), 16.f), 1.f), 0.0625f)));
+}
+
+// first / one-past-last pair of view v in the depth-ordered stream (sorted_offsets = inclusive scan)
+__device__ __forceinline__ void ms_view_pairs(int v, const uint32_t* view_start, const uint32_t* sorted_offsets,
+                                              uint32_t& pb, uint32_t& pe) {
+  const uint32_t j0 = view_start[v], j1 = view_start[v + 1];
+  pb = j0 ? sorted_offsets[j0 - 1] : 0u;
+  pe = j1 ? sorted_offsets[j1 - 1] : 0u;
+}
+
+// (A) enumerate + cull + count + store items.  grid (chunks_max, V).
+__global__ void __launch_bounds__(MS_THREADS) ms_count_kernel(
+    OcrfShape sh, int chunks_max, uint32_t Q, uint64_t n_cap, uint32_t* __restrict__ header,
+    const uint32_t* __restrict__ view_start, const uint32_t* __restrict__ sorted_offsets,
+    const uint32_t* __restrict__ vis_vals, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
+    const float4* __restrict__ conic_opacity, uint32_t* __restrict__ cnt_full, uint32_t* __restrict__ cnt_kept,
+    uint2* __restrict__ items) {
+  extern __shared__ uint32_t s_dyn[];  // [2][tiles] counters, then [MS_ROUND/2] packed u16 Gaussian offsets
+  __shared__ uint32_t s_jf, s_jl;
+  __shared__ uint32_t s_wtot[MS_WARPS];
+  const int v = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ((uint64_t)header[HDR_NUM_PAIRS] > n_cap) {
+    if (c == 0 && v == 0 && tid == 0) atomicOr(&header[HDR_ERROR], ERR_PAIR_OVERFLOW);
+    return;
+  }
+  uint32_t pb, pe;
+  ms_view_pairs(v, view_start, sorted_offsets, pb, pe);
+  const uint64_t cb64 = (uint64_t)pb + (uint64_t)c * Q;
+  if (cb64 >= pe) return;
+  const uint32_t cb = (uint32_t)cb64, ce = (uint32_t)min((uint64_t)pe, cb64 + Q);
+  const int gx = ceil_div(sh.W, TILE), gy = ceil_div(sh.H, TILE), tiles = gx * gy;
+  uint32_t* s_cnt = s_dyn;
+  uint16_t* s_j = reinterpret_cast<uint16_t*>(s_dyn + 2 * tiles);
+  for (int t = tid; t < 2 * tiles; t += MS_THREADS) s_cnt[t] = 0;
+  const uint32_t jv0 = view_start[v], jv1 = view_start[v + 1];
+
+  for (uint32_t rb = cb; rb < ce; rb += MS_ROUND) {
+    const uint32_t n_items = min((uint32_t)MS_ROUND, ce - rb);
+    __syncthreads();
+    if (tid < 2) {  // Gaussian holding the first / last pair of the round: smallest j with sorted_offsets[j] > target
+      const uint32_t target = tid == 0 ? rb : rb + n_items - 1;
+      uint32_t lo = jv0, hi = jv1;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (sorted_offsets[mid] > target) hi = mid; else lo = mid + 1;
+      }
+      if (tid == 0) s_jf = lo; else s_jl = lo;
+    }
+    for (int i = tid; i < MS_ROUND / 2; i += MS_THREADS) reinterpret_cast<uint32_t*>(s_j)[i] = 0;
+    __syncthreads();
+    const uint32_t jf = s_jf, jl = s_jl;
+    // flag the first pair of every Gaussian that starts inside the round, then scan -> Gaussian offset per pair
+    for (uint32_t j = jf + 1 + tid; j <= jl; j += MS_THREADS) s_j[sorted_offsets[j - 1] - rb] = 1;
+    __syncthreads();
+    {
+      uint32_t* mine = reinterpret_cast<uint32_t*>(s_j) + tid * (MS_ITEMS / 2);
+      uint32_t w[MS_ITEMS / 2];
+      uint32_t sum = 0;
+#pragma unroll
+      for (int i = 0; i < MS_ITEMS / 2; i++) {
+        w[i] = mine[i];
+        sum += (w[i] & 0xffffu) + (w[i] >> 16);
+      }
+      uint32_t incl = sum;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+      }
+      if (lane == 31) s_wtot[warp] = incl;
+      __syncthreads();
+      uint32_t run = incl - sum;
+#pragma unroll
+      for (int q = 0; q < MS_WARPS; q++)
+        if (q < warp) run += s_wtot[q];
+#pragma unroll
+      for (int i = 0; i < MS_ITEMS / 2; i++) {
+        const uint32_t a = run + (w[i] & 0xffffu);
+        const uint32_t b = a + (w[i] >> 16);
+        mine[i] = a | (b << 16);
+        run = b;
+      }
+    }
+    __syncthreads();
+    // every pair: its Gaussian, its tile, the exact cull
+#pragma unroll 4
+    for (int i = 0; i < MS_ITEMS; i++) {
+      const uint32_t pos = warp * (32 * MS_ITEMS) + i * 32 + lane;
+      if (pos >= n_items) continue;
+      const uint32_t j = jf + s_j[pos];
+      const uint32_t excl = j ? sorted_offsets[j - 1] : 0u;
+      const int k = (int)(rb + pos - excl);
+      const uint32_t g = vis_vals[j];
+      const float2 p = xy[g];
+      int x0, y0, x1, y1;
+      ms_tile_rect(p.x, p.y, radii[g], gx, gy, x0, y0, x1, y1);
+      const int w = x1 - x0;
+      const int ty = y0 + k / w, tx = x0 + k - (k / w) * w;
+      const int t = ty * gx + tx;
+      const float px0 = (float)(tx * TILE), px1 = (float)min(tx * TILE + TILE - 1, sh.W - 1);
+      const float py0 = (float)(ty * TILE), py1 = (float)min(ty * TILE + TILE - 1, sh.H - 1);
+      const bool keep = ms_tile_can_contribute(p, conic_opacity[g], px0, px1, py0, py1);
+      atomicAdd(&s_cnt[t], 1u);
+      if (keep) atomicAdd(&s_cnt[tiles + t], 1u);
+      items[rb + pos] = make_uint2((uint32_t)t | (keep ? MS_KEEP : 0u), g);
+    }
+  }
+  __syncthreads();
+  const size_t row = ((size_t)v * chunks_max + c) * tiles;
+  for (int t = tid; t < tiles; t += MS_THREADS) {
+    cnt_full[row + t] = s_cnt[t];
+    cnt_kept[row + t] = s_cnt[tiles + t];
+  }
+}
+
+// (B1) exclusive scan over the chunks of every tile (in place) + tile totals, for both tables
+__global__ void __launch_bounds__(256) ms_scan_chunks_kernel(OcrfShape sh, int chunks_max, uint32_t Q,
+                                                             const uint32_t* __restrict__ view_start,
+                                                             const uint32_t* __restrict__ sorted_offsets,
+                                                             uint32_t* __restrict__ cnt_full,
+                                                             uint32_t* __restrict__ cnt_kept,
+                                                             uint32_t* __restrict__ tot_full,
+                                                             uint32_t* __restrict__ tot_kept) {
+  const int v = blockIdx.y;
+  const int tiles = ceil_div(sh.W, TILE) * ceil_div(sh.H, TILE);
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= tiles) return;
+  uint32_t pb, pe;
+  ms_view_pairs(v, view_start, sorted_offsets, pb, pe);
+  const int nchunks = (int)(((uint64_t)(pe - pb) + Q - 1) / Q);
+  uint32_t* cf = cnt_full + (size_t)v * chunks_max * tiles + t;
+  uint32_t* ck = cnt_kept + (size_t)v * chunks_max * tiles + t;
+  uint32_t rf = 0, rk = 0;
+  for (int c0 = 0; c0 < nchunks; c0 += 8) {  // independent loads in flight per round trip
+    uint32_t xf[8], xk[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      xf[k] = c0 + k < nchunks ? cf[(size_t)(c0 + k) * tiles] : 0u;
+      xk[k] = c0 + k < nchunks ? ck[(size_t)(c0 + k) * tiles] : 0u;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      if (c0 + k < nchunks) {
+        cf[(size_t)(c0 + k) * tiles] = rf;
+        ck[(size_t)(c0 + k) * tiles] = rk;
+      }
+      rf += xf[k];
+      rk += xk[k];
+    }
+  }
+  tot_full[(size_t)v * tiles + t] = rf;
+  tot_kept[(size_t)v * tiles + t] = rk;
+}
+
+// (B2) exclusive scan of the full tile totals over the batch -> tile offsets and both range tables
+__global__ void __launch_bounds__(1024) ms_scan_tiles_kernel(int n_tiles, const uint32_t* __restrict__ header,
+                                                             uint64_t n_cap, const uint32_t* __restrict__ tot_full,
+                                                             const uint32_t* __restrict__ tot_kept,
+                                                             uint32_t* __restrict__ tile_offset,
+                                                             uint2* __restrict__ ranges,
+                                                             uint2* __restrict__ ranges_render) {
+  __shared__ uint32_t s_warp[32];
+  __shared__ uint32_t s_carry;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ((uint64_t)header[HDR_NUM_PAIRS] > n_cap) {  // capacity overflow: nothing was binned, render background only
+    for (int i = tid; i < n_tiles; i += 1024) {
+      ranges[i] = make_uint2(0u, 0u);
+      ranges_render[i] = make_uint2(0u, 0u);
+    }
+    return;
+  }
+  if (tid == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < n_tiles; base += 1024) {
+    const int i = base + tid;
+    const uint32_t x = i < n_tiles ? tot_full[i] : 0u;
+    uint32_t incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += y;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t off = s_carry;
+    for (int w = 0; w < warp; w++) off += s_warp[w];
+    if (i < n_tiles) {
+      const uint32_t first = off + incl - x;
+      tile_offset[i] = first;
+      ranges[i] = x ? make_uint2(first, first + x) : make_uint2(0u, 0u);  // empty tiles read (0,0) like the reference
+      ranges_render[i] = make_uint2(first, first + tot_kept[i]);
+    }
+    __syncthreads();
+    if (tid == 1023) s_carry = off + incl;
+    __syncthreads();
+  }
+}
+
+// (C) stable ranks per tile + direct record writes.  grid (chunks_max, V).
+__global__ void __launch_bounds__(MS_THREADS) ms_scatter_kernel(
+    OcrfShape sh, int chunks_max, uint32_t Q, uint64_t n_cap, int use_sh, int has_rgb,
+    const uint32_t* __restrict__ header, const uint32_t* __restrict__ view_start,
+    const uint32_t* __restrict__ sorted_offsets, const uint2* __restrict__ items, const float2* __restrict__ xy,
+    const float4* __restrict__ conic_opacity, const float* __restrict__ depths, const float* __restrict__ rgb,
+    const float* __restrict__ colors, const uint32_t* __restrict__ cnt_full, const uint32_t* __restrict__ cnt_kept,
+    const uint32_t* __restrict__ tile_offset, Record* __restrict__ records) {
+  extern __shared__ uint32_t s_dyn[];  // [2][tiles] running bases (full: relative to the tile list, kept: record slot)
+                                       // then [MS_WARPS][2][tiles] u16 per-warp counts / prefixes of the round, [2][tiles] u16 round totals
+  const int v = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if ((uint64_t)header[HDR_NUM_PAIRS] > n_cap) return;
+  uint32_t pb, pe;
+  ms_view_pairs(v, view_start, sorted_offsets, pb, pe);
+  const uint64_t cb64 = (uint64_t)pb + (uint64_t)c * Q;
+  if (cb64 >= pe) return;
+  const uint32_t cb = (uint32_t)cb64, ce = (uint32_t)min((uint64_t)pe, cb64 + Q);
+  const int tiles = ceil_div(sh.W, TILE) * ceil_div(sh.H, TILE);
+  uint32_t* s_base = s_dyn;
+  uint16_t* s_wc = reinterpret_cast<uint16_t*>(s_dyn + 2 * tiles);
+  uint16_t* s_rt = s_wc + (size_t)MS_WARPS * 2 * tiles;  // [2][tiles] totals of the current round
+  uint16_t* my_full = s_wc + (size_t)warp * 2 * tiles;
+  uint16_t* my_kept = my_full + tiles;
+  const size_t row = ((size_t)v * chunks_max + c) * tiles;
+  const uint32_t* toff = tile_offset + (size_t)v * tiles;
+  for (int t = tid; t < tiles; t += MS_THREADS) {
+    s_base[t] = cnt_full[row + t];
+    s_base[tiles + t] = toff[t] + cnt_kept[row + t];
+  }
+  const uint32_t lt_mask = (1u << lane) - 1;
+  const size_t sample_base = (size_t)(v / sh.views_per_sample) * sh.P;
+  const uint32_t gv0 = (uint32_t)v * (uint32_t)sh.P;
+
+  for (uint32_t rb = cb; rb < ce; rb += MS_ROUND) {
+    const uint32_t n_items = min((uint32_t)MS_ROUND, ce - rb);
+    __syncthreads();
+    for (int i = tid; i < MS_WARPS * tiles; i += MS_THREADS) reinterpret_cast<uint32_t*>(s_wc)[i] = 0;  // 2 u16 per word
+    __syncthreads();
+    // rank inside the warp, one row of 32 consecutive pairs at a time (stable)
+    uint32_t st[MS_ITEMS];  // tile | rank_full << 13 | rank_kept << 22 | keep << 31   (ranks < 512 per warp-round)
+    uint32_t gi[MS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < MS_ITEMS; i++) {
+      const uint32_t pos = warp * (32 * MS_ITEMS) + i * 32 + lane;
+      const bool valid = pos < n_items;
+      uint2 it = make_uint2(0xffffu, 0u);
+      if (valid) it = items[rb + pos];
+      const uint32_t t = it.x & 0x1fffu;
+      const bool keep = valid && (it.x & MS_KEEP);
+      gi[i] = it.y;
+      const uint32_t peers = __match_any_sync(0xffffffffu, valid ? t : 0xffff0000u | lane);
+      const uint32_t kpeers = __match_any_sync(0xffffffffu, keep ? t : 0xffff0000u | lane);
+      uint32_t bf = 0, bk = 0;
+      if (valid) {
+        bf = my_full[t];
+        bk = my_kept[t];
+      }
+      __syncwarp();
+      if (valid && (peers & lt_mask) == 0) my_full[t] = (uint16_t)(bf + __popc(peers));
+      if (keep && (kpeers & lt_mask) == 0) my_kept[t] = (uint16_t)(bk + __popc(kpeers));
+      __syncwarp();
+      const uint32_t rf = bf + __popc(peers & lt_mask), rk = bk + __popc(kpeers & lt_mask);
+      st[i] = valid ? (t | (rf << 13) | (rk << 22) | (keep ? MS_KEEP : 0u)) : 0xffffffffu;
+    }
+    __syncthreads();
+    // per tile: exclusive prefix over the warps (stored back into the per-warp slots) and the round totals
+    for (int t = tid; t < tiles; t += MS_THREADS) {
+      uint32_t rf = 0, rk = 0;
+#pragma unroll
+      for (int w = 0; w < MS_WARPS; w++) {
+        uint16_t* f = s_wc + (size_t)w * 2 * tiles;
+        const uint32_t xf = f[t], xk = f[tiles + t];
+        f[t] = (uint16_t)rf;
+        f[tiles + t] = (uint16_t)rk;
+        rf += xf;
+        rk += xk;
+      }
+      s_rt[t] = (uint16_t)rf;
+      s_rt[tiles + t] = (uint16_t)rk;
+    }
+    __syncthreads();
+    // write the kept pairs of this round
+#pragma unroll 4
+    for (int i = 0; i < MS_ITEMS; i++) {
+      const uint32_t s = st[i];
+      if (s == 0xffffffffu || !(s & MS_KEEP)) continue;
+      const uint32_t t = s & 0x1fffu, rf = (s >> 13) & 0x1ffu, rk = (s >> 22) & 0x1ffu;
+      const uint32_t orig = s_base[t] + my_full[t] + rf + 1;          // 1-based position in the tile's full list
+      const uint32_t dst = s_base[tiles + t] + my_kept[t] + rk;       // record slot
+      const uint32_t g = gi[i];
+      const float2 p = xy[g];
+      const float4 co = conic_opacity[g];
+      const uint32_t id = g - gv0;
+      float r = 0.f, gg = 0.f, bb = 0.f;
+      if (has_rgb) {
+        const float* col = use_sh ? rgb + (size_t)g * 3 : colors + (sample_base + id) * 3;
+        r = __ldg(col); gg = __ldg(col + 1); bb = __ldg(col + 2);
+      }
+      float4* out = reinterpret_cast<float4*>(records + dst);
+      out[0] = make_float4(p.x, p.y, co.x, co.y);
+      out[1] = make_float4(co.z, co.w, __uint_as_float(orig), r);
+      out[2] = make_float4(gg, bb, __uint_as_float(id), depths[g]);
+    }
+    __syncthreads();
+    for (int t = tid; t < tiles; t += MS_THREADS) {  // advance the running bases past this round
+      s_base[t] += s_rt[t];
+      s_base[tiles + t] += s_rt[tiles + t];
+    }
+  }
+}
+
+}  // namespace ocrf
+
+using namespace ocrf;
+
+namespace ocrf {
+// Host entry used by ocrf_bin_forward (binning.cu).  Returns 0, a cudaError_t, or OCRF_E*.
+int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity, int use_sh, const int32_t* radii,
+                   const float* colors, uint32_t* header, const uint32_t* view_start, const uint32_t* sorted_offsets,
+                   const uint32_t* vis_vals, const float2* xy, const float4* conic_opacity, const float* depths,
+                   const float* rgb, uint32_t* tables, size_t table_words, uint32_t* tile_arrays, uint2* items,
+                   uint2* ranges, uint2* ranges_render, Record* records) {
+  const int tiles_v = tiles_x(*sh) * tiles_y(*sh);
+  if (tiles_v > 8191) return OCRF_ECAPACITY;
+  // chunk size: multiples of MS_ROUND pairs, at most ~2048 chunks for the whole capacity
+  uint64_t rounds = (pair_capacity + (uint64_t)MS_ROUND * 2048 - 1) / ((uint64_t)MS_ROUND * 2048);
+  if (rounds < 1) rounds = 1;
+  const uint32_t Q = (uint32_t)(rounds * MS_ROUND);
+  const int chunks_max = (int)((pair_capacity + Q - 1) / Q) + 1;
+  if ((size_t)2 * sh->V * chunks_max * tiles_v > table_words) return OCRF_ECAPACITY;
+  uint32_t* cnt_full = tables;
+  uint32_t* cnt_kept = tables + (size_t)sh->V * chunks_max * tiles_v;
+  uint32_t* tot_full = tile_arrays;
+  uint32_t* tot_kept = tot_full + (size_t)sh->V * tiles_v;
+  uint32_t* tile_offset = tot_kept + (size_t)sh->V * tiles_v;
+  const size_t smem_a = (size_t)2 * tiles_v * 4 + MS_ROUND * 2;
+  const size_t smem_c = (size_t)2 * tiles_v * 4 + (size_t)(MS_WARPS + 1) * 2 * tiles_v * 2;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(ms_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    e = cudaFuncSetAttribute(ms_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return (int)e;
+    attr = true;
+  }
+  if (smem_a > 100 * 1024 || smem_c > 200 * 1024) return OCRF_ECAPACITY;
+  const dim3 grid(chunks_max, sh->V);
+  ms_count_kernel<<<grid, MS_THREADS, smem_a, st>>>(*sh, chunks_max, Q, pair_capacity, header, view_start, sorted_offsets,
+                                                    vis_vals, radii, xy, conic_opacity, cnt_full, cnt_kept, items);
+  ms_scan_chunks_kernel<<<dim3(ceil_div(tiles_v, 256), sh->V), 256, 0, st>>>(*sh, chunks_max, Q, view_start,
+                                                                             sorted_offsets, cnt_full, cnt_kept, tot_full,
+                                                                             tot_kept);
+  ms_scan_tiles_kernel<<<1, 1024, 0, st>>>(sh->V * tiles_v, header, pair_capacity, tot_full, tot_kept, tile_offset, ranges,
+                                           ranges_render);
+  ms_scatter_kernel<<<grid, MS_THREADS, smem_c, st>>>(*sh, chunks_max, Q, pair_capacity, use_sh, sh->C == 3, header,
+                                                      view_start, sorted_offsets, items, xy, conic_opacity, depths, rgb,
+                                                      colors, cnt_full, cnt_kept, tile_offset, records);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : (int)e;
+}
+}  // namespace ocrf

@@ -139,7 +139,8 @@ class _RasterizeBatch(torch.autograd.Function):
         binl = _Workspaces.bin_layout(shape, capacity)
         binning = torch.empty(binl.total, dtype=torch.uint8, device=dev)
         check(L.ocrf_bin_forward(stream, C.byref(shape), C.c_uint64(capacity), ptr(radii), ptr(colors), int(use_sh),
-                                 C.c_uint32(_lib.OCRF_BIN_PAIR_SORT if cfg.get("binning") == "pairsort" else 0),
+                                 C.c_uint32({"pairsort": _lib.OCRF_BIN_PAIR_SORT, "depthfirst": _lib.OCRF_BIN_DEPTH_FIRST}
+                                            .get(cfg.get("binning"), 0)),
                                  ptr(geom), ptr(binning), ptr(image)), "ocrf_bin_forward")
         _stage("binning")
         check(L.ocrf_render_forward(stream, C.byref(shape), C.c_uint64(capacity), ptr(colors), int(use_sh), ptr(bg),
@@ -152,7 +153,8 @@ class _RasterizeBatch(torch.autograd.Function):
         if KEEP_STATE:
             _LAST_STATE = dict(shape=shape, layouts=(ws.geom, binl, ws.image), geom=geom, binning=binning, image=image,
                                radii=radii, capacity=capacity, colors=colors, use_sh=use_sh,
-                               binning_mode="pairsort" if cfg.get("binning") == "pairsort" else "split")
+                               binning_mode=cfg.get("binning") if cfg.get("binning") in ("pairsort", "depthfirst")
+                               else "split")
         ctx.shape, ctx.cfg, ctx.capacity, ctx.use_sh = shape, cfg, capacity, use_sh
         ctx.num_rendered = num_pairs
         ctx.layouts = (ws.geom, binl, ws.image)
@@ -247,8 +249,9 @@ def last_state(reference_lists=False):
         final_T=view(image, im.final_T, V * H * W, torch.float32, V, H, W),
         n_contrib=view(image, im.n_contrib, V * H * W, torch.int32, V, H, W),
         max_contrib=view(image, im.max_contrib, V * tiles, torch.int32, V, tiles))
-    out["keys"] = view(binning, b.keys, N, torch.int64, N)
-    out["point_list"] = view(binning, b.point_list, N, torch.int32, N)
+    if st["binning_mode"] != "split":  # the multi-split path never materialises the pair lists
+        out["keys"] = view(binning, b.keys, N, torch.int64, N)
+        out["point_list"] = view(binning, b.point_list, N, torch.int32, N)
     if reference_lists and st["binning_mode"] != "pairsort":
         L = _lib.lib()
         bin2 = torch.empty_like(binning)
@@ -273,8 +276,10 @@ def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors
     rotations [S,P,4], or cov3D_precomp [S,P,6]; cams from `pack_cameras`, view v looks at sample
     v // (V // S).  Returns (color [V,C,H,W], radii [V,P], depth [V,1,H,W], opacity [V,1,H,W]).
     `means2D` ([V,P,3] zeros, requires_grad) receives dL/dmean2D as in the reference.
-    `binning`: None / "split" = depth-sort the visible Gaussians, then split them stably into tiles (default);
-    "pairsort" = the reference's algorithm (sort every (tile, Gaussian) pair).  Identical keys / lists / images.
+    `binning`: None / "split" = depth-sort the visible Gaussians, then ONE stable multi-split of the pair stream by
+    tile writing the culled records directly (default; the pair lists are not materialised); "depthfirst" = same
+    depth sort, pairs emitted in depth order, tile bits sorted (2 passes); "pairsort" = the reference's algorithm
+    (sort every (tile | depth) pair).  All three give bit-identical records, range tables and images.
     `pair_capacity`: if given, the binning workspace is sized for that many (tile, Gaussian) pairs
     and NO host synchronisation happens (CUDA-graph friendly); an overflow renders background and
     raises on the next `check_overflow`.
