@@ -102,10 +102,10 @@ __device__ __forceinline__ bool tile_can_contribute(float2 p, float4 co, float p
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const float ex = e ? dxh : dxl;
-      const float sy = fminf(dyh, fmaxf(dyl, -B * ex / Cc));
+      const float sy = fminf(dyh, fmaxf(dyl, __fdividef(-B * ex, Cc)));
       q = fminf(q, A * ex * ex + 2.f * B * ex * sy + Cc * sy * sy);
       const float ey = e ? dyh : dyl;
-      const float sx = fminf(dxh, fmaxf(dxl, -B * ey / A));
+      const float sx = fminf(dxh, fmaxf(dxl, __fdividef(-B * ey, A)));
       q = fminf(q, A * sx * sx + 2.f * B * sx * ey + Cc * ey * ey);
     }
     qmin = q;

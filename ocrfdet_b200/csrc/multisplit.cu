@@ -38,10 +38,10 @@ __device__ __forceinline__ bool ms_tile_can_contribute(float2 p, float4 co, floa
 #pragma unroll
     for (int e = 0; e < 2; e++) {
       const float ex = e ? dxh : dxl;
-      const float sy = fminf(dyh, fmaxf(dyl, -B * ex / Cc));
+      const float sy = fminf(dyh, fmaxf(dyl, __fdividef(-B * ex, Cc)));
       q = fminf(q, A * ex * ex + 2.f * B * ex * sy + Cc * sy * sy);
       const float ey = e ? dyh : dyl;
-      const float sx = fminf(dxh, fmaxf(dxl, -B * ey / A));
+      const float sx = fminf(dxh, fmaxf(dxl, __fdividef(-B * ey, A)));
       q = fminf(q, A * sx * sx + 2.f * B * sx * ey + Cc * ey * ey);
     }
     qmin = q;
@@ -172,7 +172,9 @@ __global__ void __launch_bounds__(MS_THREADS) ms_count_kernel(
   }
 }
 
-// (B1) exclusive scan over the chunks of every tile (in place) + tile totals, for both tables
+// (B1) exclusive scan over the chunks of every tile (in place) + tile totals, for both tables.
+// One WARP per tile: the lanes take 32 consecutive chunks, so a tile's column is read in
+// ceil(chunks/32) parallel round trips instead of one dependent load per chunk.
 __global__ void __launch_bounds__(256) ms_scan_chunks_kernel(OcrfShape sh, int chunks_max, uint32_t Q,
                                                              const uint32_t* __restrict__ view_start,
                                                              const uint32_t* __restrict__ sorted_offsets,
@@ -182,7 +184,8 @@ __global__ void __launch_bounds__(256) ms_scan_chunks_kernel(OcrfShape sh, int c
                                                              uint32_t* __restrict__ tot_kept) {
   const int v = blockIdx.y;
   const int tiles = ceil_div(sh.W, TILE) * ceil_div(sh.H, TILE);
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   if (t >= tiles) return;
   uint32_t pb, pe;
   ms_view_pairs(v, view_start, sorted_offsets, pb, pe);
@@ -190,25 +193,27 @@ __global__ void __launch_bounds__(256) ms_scan_chunks_kernel(OcrfShape sh, int c
   uint32_t* cf = cnt_full + (size_t)v * chunks_max * tiles + t;
   uint32_t* ck = cnt_kept + (size_t)v * chunks_max * tiles + t;
   uint32_t rf = 0, rk = 0;
-  for (int c0 = 0; c0 < nchunks; c0 += 8) {  // independent loads in flight per round trip
-    uint32_t xf[8], xk[8];
+  for (int c0 = 0; c0 < nchunks; c0 += 32) {
+    const int c = c0 + lane;
+    const uint32_t xf = c < nchunks ? cf[(size_t)c * tiles] : 0u;
+    const uint32_t xk = c < nchunks ? ck[(size_t)c * tiles] : 0u;
+    uint32_t inf = xf, ink = xk;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-      xf[k] = c0 + k < nchunks ? cf[(size_t)(c0 + k) * tiles] : 0u;
-      xk[k] = c0 + k < nchunks ? ck[(size_t)(c0 + k) * tiles] : 0u;
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t yf = __shfl_up_sync(0xffffffffu, inf, d), yk = __shfl_up_sync(0xffffffffu, ink, d);
+      if (lane >= d) { inf += yf; ink += yk; }
     }
-#pragma unroll
-    for (int k = 0; k < 8; k++) {
-      if (c0 + k < nchunks) {
-        cf[(size_t)(c0 + k) * tiles] = rf;
-        ck[(size_t)(c0 + k) * tiles] = rk;
-      }
-      rf += xf[k];
-      rk += xk[k];
+    if (c < nchunks) {
+      cf[(size_t)c * tiles] = rf + inf - xf;
+      ck[(size_t)c * tiles] = rk + ink - xk;
     }
+    rf += __shfl_sync(0xffffffffu, inf, 31);
+    rk += __shfl_sync(0xffffffffu, ink, 31);
   }
-  tot_full[(size_t)v * tiles + t] = rf;
-  tot_kept[(size_t)v * tiles + t] = rk;
+  if (lane == 0) {
+    tot_full[(size_t)v * tiles + t] = rf;
+    tot_kept[(size_t)v * tiles + t] = rk;
+  }
 }
 
 // (B2) exclusive scan of the full tile totals over the batch -> tile offsets and both range tables
@@ -404,7 +409,7 @@ int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity,
   const dim3 grid(chunks_max, sh->V);
   ms_count_kernel<<<grid, MS_THREADS, smem_a, st>>>(*sh, chunks_max, Q, pair_capacity, header, view_start, sorted_offsets,
                                                     vis_vals, radii, xy, conic_opacity, cnt_full, cnt_kept, items);
-  ms_scan_chunks_kernel<<<dim3(ceil_div(tiles_v, 256), sh->V), 256, 0, st>>>(*sh, chunks_max, Q, view_start,
+  ms_scan_chunks_kernel<<<dim3(ceil_div(tiles_v, 8), sh->V), 256, 0, st>>>(*sh, chunks_max, Q, view_start,
                                                                              sorted_offsets, cnt_full, cnt_kept, tot_full,
                                                                              tot_kept);
   ms_scan_tiles_kernel<<<1, 1024, 0, st>>>(sh->V * tiles_v, header, pair_capacity, tot_full, tot_kept, tile_offset, ranges,
