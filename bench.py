@@ -159,15 +159,20 @@ def run_ours(args, rank, world, device):
         torch.cuda.synchronize()
     end_bit = _lib.lib().ocrf_sort_end_bit(_lib.C.byref(_lib.OcrfShape(1, P, VIEWS, VIEWS, W, H, C, 0, 0)))
     passes = (end_bit + 7) // 8
-    if os.environ.get("OCRF_BINNING", "split") == "pairsort":
+    binning = os.environ.get("OCRF_BINNING", "split")
+    vis_passes = (32 + max(VIEWS - 1, 0).bit_length() + 7) // 8
+    if binning == "pairsort":
         # preprocess, duplicate, histogram, `passes` onesweep passes, cull/pack, blend fwd, blend bwd, preprocess bwd
         launches_per_step = 7 + passes
-    else:
-        # depth-first binning: preprocess | histogram + passes over (view|depth) of the visible Gaussians |
-        # scan + duplicate in depth order | histogram + passes over the tile bits | cull/pack | fwd | bwd | preprocess bwd
-        vis_passes = (32 + max(VIEWS - 1, 0).bit_length() + 7) // 8
+    elif binning == "depthfirst":
+        # preprocess | histogram + passes over (view|depth) of the visible Gaussians | scan + duplicate in depth
+        # order | histogram + passes over the tile bits | cull/pack | fwd | bwd | preprocess bwd
         tile_passes = (end_bit - 32 + 7) // 8
         launches_per_step = 1 + (1 + vis_passes) + 2 + (1 + tile_passes) + 1 + 3
+    else:
+        # default multi-split: preprocess | histogram + passes over (view|depth) | scan | count, scan chunks,
+        # scan tiles, scatter | fwd | bwd | preprocess bwd
+        launches_per_step = 1 + (1 + vis_passes) + 1 + 4 + 3
 
     # ---- device-resident throughput ----
     if world > 1:

@@ -187,6 +187,24 @@ int ocrf_opacity_mask_backward(void* stream, int32_t B, int32_t C, int32_t H, in
                                const float* w, const float* mask, const float* stats, const float* g_out,
                                float* g_x, float* g_w, float* g_opacity_bev, float* scratch);
 
+/* Stage 0 (scope row a12, "next" f-1): OcRF Gaussian construction, the four MLP heads of
+ * view_transformer_ocrf.py:272-320 evaluated at :1130-1133, in one pass over the voxel features.
+ * feat [n,F] (F <= 125), rgb [n,3].  Packed parameters (input-major first layer):
+ *   w1t [F+3,16]: columns 0-3 S_MLP.fc1, 4-7 R_MLP.fc1, 8-11 A_MLP.fc1 (their 3 rgb rows zero), 12-15 C_MLP.fc1
+ *   b1 [16];  w2 [11,4]: rows 0-2 S_MLP.fc2, 3-6 R_MLP.fc2, 7 A_MLP.fc2, 8-10 C_MLP.fc2;  b2 [11].
+ * Outputs: opacity [n] (sigmoid), scales [n,3] (softplus), rotations [n,4] (unit), colors [n,3] (sigmoid),
+ * hidden [n,16] (post-ReLU, kept for backward).  rotations and hidden must be 16-byte aligned; feat 16-byte
+ * aligned with F % 4 == 0 takes the bulk-copy path, anything else a slower plain-load path. */
+int ocrf_gaussian_heads_forward(void* stream, int64_t n, int32_t F, const float* feat, const float* rgb,
+                                const float* w1t, const float* b1, const float* w2, const float* b2, float* opacity,
+                                float* scales, float* rotations, float* colors, float* hidden);
+/* g_feat [n,F] is written; g_w1t [F+3,16], g_b1 [16], g_w2 [11,4], g_b2 [11] are ACCUMULATED (zero them first). */
+int ocrf_gaussian_heads_backward(void* stream, int64_t n, int32_t F, const float* feat, const float* rgb,
+                                 const float* w1t, const float* w2, const float* b2, const float* hidden,
+                                 const float* g_opacity, const float* g_scales, const float* g_rotations,
+                                 const float* g_colors, float* g_feat, float* g_w1t, float* g_b1, float* g_w2,
+                                 float* g_b2);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,487 @@
+// Scope row a12 ("next" f-1): OcRF Gaussian construction as ONE pass over the voxel features.
+//
+// Replaces the four tiny MLP heads of the OcRF head
+// (/root/reference/mmdet3d/models/necks/view_transformer_ocrf.py:272-320, called at :1130-1133):
+//     opacity  = sigmoid (A.fc2(relu(A.fc1(feat))))                 [n,1]
+//     scaling  = softplus(S.fc2(relu(S.fc1(feat))))                 [n,3]
+//     rotation = normalize(R.fc2(relu(R.fc1(feat))))                [n,4]
+//     color    = sigmoid (C.fc2(relu(C.fc1(cat(feat, rgb)))))       [n,3]
+// The reference reads voxel_feat [212992, 80] (68 MB per sample) four times and launches ~16 small
+// kernels; here the 16 hidden units of all four heads are one [n, F+3] x [F+3, 16] product evaluated
+// while the feature tile sits in shared memory, so the features are read from HBM exactly once
+// (forward) / once more (backward).  Algorithmic bytes per Gaussian (F = 80): forward 332 read + 108 written
+// (44 outputs + 64 hidden kept for backward); backward 332 + 64 + 44 read, 320 written.
+//
+// Data movement: every 128-Gaussian tile is fetched with one 1-D bulk copy per row (TMA unit, SASS UBLKCP) into
+// rows padded to an odd number of 16-byte words, so that "thread t reads row t" with LDS.128 is bank-conflict
+// free; backward sends dL/dfeat back with bulk stores from the same rows.  Each thread owns TWO rows, so one
+// broadcast LDS.128 of weights feeds 8 FFMAs: the inner loop is FP32-issue bound, not shared-memory bound.
+//
+// Packed parameters (built by ocrfdet_b200/gaussian_heads.py from the reference's parameter tensors):
+//   w1t [F+3][16]  input-major: columns 0-3 S.fc1, 4-7 R.fc1, 8-11 A.fc1 (their 3 rgb rows zero), 12-15 C.fc1;  b1 [16]
+//   w2  [11][4]    rows 0-2 S.fc2, 3-6 R.fc2, 7 A.fc2, 8-10 C.fc2;                                               b2 [11]
+#include "common.cuh"
+
+namespace ocrf {
+
+constexpr int GH_ROWS = 128;     // Gaussians per tile
+constexpr int GH_THREADS = 64;   // two rows per thread
+constexpr int GH_HID = 16;
+constexpr int GH_OUT = 11;
+constexpr int GH_MAXK = 128;     // F + 3 <= 128: every input column has an owner thread slot in backward
+
+__host__ __device__ inline int gh_row_stride(int F) {  // floats; [feat F | rgb 3 | pad], an odd number of float4s
+  int f4 = (F + 3 + 3) / 4;
+  if ((f4 & 1) == 0) f4++;
+  return 4 * f4;
+}
+
+__device__ __forceinline__ int gh_hidden_base(int i) { return i < 3 ? 0 : (i < 7 ? 4 : (i < 8 ? 8 : 12)); }
+
+__device__ __forceinline__ void gh_second_layer(const float* h, const float* s_w2, const float* s_b2, float* z) {
+  // S rows 0-2 use hidden 0-3, R rows 3-6 hidden 4-7, A row 7 hidden 8-11, C rows 8-10 hidden 12-15
+#pragma unroll
+  for (int i = 0; i < GH_OUT; i++) {
+    const int hb = gh_hidden_base(i);
+    float acc = s_b2[i];
+#pragma unroll
+    for (int j = 0; j < 4; j++) acc = fmaf(s_w2[i * 4 + j], h[hb + j], acc);
+    z[i] = acc;
+  }
+}
+
+__device__ __forceinline__ float gh_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float gh_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); }  // torch: beta 1, threshold 20
+
+// Fetch one tile: rows [base, base+rows) of feat -> s_x rows (stride XS); rgb -> columns F..F+2.
+// fast: feat 16-byte aligned and F % 4 == 0 (bulk copies, completion on `bar`); otherwise plain loads.
+__device__ __forceinline__ void gh_fetch_tile(const float* __restrict__ feat, const float* __restrict__ rgb,
+                                              long long base, int rows, int F, int XS, float* s_x, uint64_t* bar,
+                                              bool fast) {
+  const int tid = threadIdx.x;
+  if (fast) {
+    if (tid == 0) mbar_expect_tx(bar, (uint32_t)rows * F * 4u);
+#pragma unroll
+    for (int r = tid; r < GH_ROWS; r += GH_THREADS)
+      if (r < rows) bulk_g2s(s_x + r * XS, feat + (base + r) * F, (uint32_t)F * 4u, bar);
+  } else {
+    for (int r = 0; r < rows; r++)
+      for (int k = tid; k < F; k += GH_THREADS) s_x[r * XS + k] = __ldg(feat + (base + r) * F + k);
+  }
+#pragma unroll
+  for (int r = tid; r < GH_ROWS; r += GH_THREADS) {
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f;
+    if (r < rows) {
+      c0 = __ldg(rgb + (base + r) * 3 + 0);
+      c1 = __ldg(rgb + (base + r) * 3 + 1);
+      c2 = __ldg(rgb + (base + r) * 3 + 2);
+    }
+    s_x[r * XS + F + 0] = c0;
+    s_x[r * XS + F + 1] = c1;
+    s_x[r * XS + F + 2] = c2;
+  }
+}
+
+#define GH_FMA16(acc, XV, WA, WB, WC, WD)                                                                \
+  acc[0] = fmaf(XV, WA.x, acc[0]); acc[1] = fmaf(XV, WA.y, acc[1]); acc[2] = fmaf(XV, WA.z, acc[2]);       \
+  acc[3] = fmaf(XV, WA.w, acc[3]); acc[4] = fmaf(XV, WB.x, acc[4]); acc[5] = fmaf(XV, WB.y, acc[5]);       \
+  acc[6] = fmaf(XV, WB.z, acc[6]); acc[7] = fmaf(XV, WB.w, acc[7]); acc[8] = fmaf(XV, WC.x, acc[8]);       \
+  acc[9] = fmaf(XV, WC.y, acc[9]); acc[10] = fmaf(XV, WC.z, acc[10]); acc[11] = fmaf(XV, WC.w, acc[11]);   \
+  acc[12] = fmaf(XV, WD.x, acc[12]); acc[13] = fmaf(XV, WD.y, acc[13]); acc[14] = fmaf(XV, WD.z, acc[14]); \
+  acc[15] = fmaf(XV, WD.w, acc[15]);
+
+__global__ void __launch_bounds__(GH_THREADS) gaussian_heads_forward_kernel(
+    long long n, int F, int fast, const float* __restrict__ feat, const float* __restrict__ rgb,
+    const float* __restrict__ w1t, const float* __restrict__ b1, const float* __restrict__ w2,
+    const float* __restrict__ b2, float* __restrict__ opacity, float* __restrict__ scales,
+    float* __restrict__ rotations, float* __restrict__ colors, float* __restrict__ hidden) {
+  extern __shared__ __align__(128) float s_mem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int XS = gh_row_stride(F);
+  const int K = F + 3;
+  float* s_x = s_mem;                       // [GH_ROWS][XS]
+  float* s_w1 = s_x + GH_ROWS * XS;         // [K][16]
+  float* s_b1 = s_w1 + K * GH_HID;          // [16]
+  float* s_w2 = s_b1 + GH_HID;              // [11][4]
+  float* s_b2 = s_w2 + GH_OUT * 4;          // [11]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * GH_HID; i += GH_THREADS) s_w1[i] = w1t[i];
+  if (tid < GH_HID) s_b1[tid] = b1[tid];
+  if (tid < GH_OUT * 4) s_w2[tid] = w2[tid];
+  if (tid < GH_OUT) s_b2[tid] = b2[tid];
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  const long long tiles = (n + GH_ROWS - 1) / GH_ROWS;
+  uint32_t phase = 0;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long base = tile * GH_ROWS;
+    const int rows = (int)min((long long)GH_ROWS, n - base);
+    gh_fetch_tile(feat, rgb, base, rows, F, XS, s_x, &s_bar, fast != 0);
+    if (fast) {
+      mbar_wait(&s_bar, phase);
+      phase ^= 1;
+    }
+    __syncthreads();  // rgb columns (and the slow path's rows) are written by other threads
+
+    float h0[GH_HID], h1[GH_HID];
+#pragma unroll
+    for (int j = 0; j < GH_HID; j++) h0[j] = h1[j] = s_b1[j];
+    const float* x0p = s_x + tid * XS;
+    const float* x1p = s_x + (tid + GH_THREADS) * XS;
+    const int k4n = K >> 2;
+    for (int k4 = 0; k4 < k4n; k4++) {
+      const float4 xa = *reinterpret_cast<const float4*>(x0p + 4 * k4);
+      const float4 xb = *reinterpret_cast<const float4*>(x1p + 4 * k4);
+      const float xav[4] = {xa.x, xa.y, xa.z, xa.w};
+      const float xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const float4* w = reinterpret_cast<const float4*>(s_w1 + (4 * k4 + q) * GH_HID);
+        const float4 wa = w[0], wb = w[1], wc = w[2], wd = w[3];
+        GH_FMA16(h0, xav[q], wa, wb, wc, wd)
+        GH_FMA16(h1, xbv[q], wa, wb, wc, wd)
+      }
+    }
+    for (int k = k4n << 2; k < K; k++) {
+      const float xa = x0p[k], xb = x1p[k];
+      const float4* w = reinterpret_cast<const float4*>(s_w1 + k * GH_HID);
+      const float4 wa = w[0], wb = w[1], wc = w[2], wd = w[3];
+      GH_FMA16(h0, xa, wa, wb, wc, wd)
+      GH_FMA16(h1, xb, wa, wb, wc, wd)
+    }
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      float* h = half ? h1 : h0;
+      const int r = tid + half * GH_THREADS;
+      if (r < rows) {  // rows past the end of a partial tile hold stale shared memory: computed, never stored
+        const long long g = base + r;
+#pragma unroll
+        for (int j = 0; j < GH_HID; j++) h[j] = fmaxf(h[j], 0.f);
+        float z[GH_OUT];
+        gh_second_layer(h, s_w2, s_b2, z);
+        scales[g * 3 + 0] = gh_softplus(z[0]);
+        scales[g * 3 + 1] = gh_softplus(z[1]);
+        scales[g * 3 + 2] = gh_softplus(z[2]);
+        const float nrm = fmaxf(sqrtf(z[3] * z[3] + z[4] * z[4] + z[5] * z[5] + z[6] * z[6]), 1e-12f);  // F.normalize eps
+        reinterpret_cast<float4*>(rotations)[g] = make_float4(z[3] / nrm, z[4] / nrm, z[5] / nrm, z[6] / nrm);
+        opacity[g] = gh_sigmoid(z[7]);
+        colors[g * 3 + 0] = gh_sigmoid(z[8]);
+        colors[g * 3 + 1] = gh_sigmoid(z[9]);
+        colors[g * 3 + 2] = gh_sigmoid(z[10]);
+        float4* hp = reinterpret_cast<float4*>(hidden + g * GH_HID);
+        hp[0] = make_float4(h[0], h[1], h[2], h[3]);
+        hp[1] = make_float4(h[4], h[5], h[6], h[7]);
+        hp[2] = make_float4(h[8], h[9], h[10], h[11]);
+        hp[3] = make_float4(h[12], h[13], h[14], h[15]);
+      }
+    }
+    __syncthreads();  // every row has been consumed before the next tile lands in s_x
+  }
+}
+
+// Backward.  Persistent CTAs: each keeps its share of the weight gradients in registers across all its tiles and
+// adds them to the global sums once at the end.  Per tile:
+//   (1) per row: z2 from the saved hidden, activation derivatives -> dL/dz2 [11] -> dL/dhidden [16] (ReLU-masked);
+//       runs while the feature tile is still in flight
+//   (2) weight gradients: thread u owns input columns k = u and u + 64 (16 sums each); the second warp also owns
+//       b1 (16 sums) and w2/b2 (11 rows)
+//   (3) dL/dfeat rows overwrite the feature rows in shared memory and leave through bulk stores.
+__global__ void __launch_bounds__(GH_THREADS) gaussian_heads_backward_kernel(
+    long long n, int F, int fast, const float* __restrict__ feat, const float* __restrict__ rgb,
+    const float* __restrict__ w1t, const float* __restrict__ w2, const float* __restrict__ b2,
+    const float* __restrict__ hidden, const float* __restrict__ g_opacity, const float* __restrict__ g_scales,
+    const float* __restrict__ g_rotations, const float* __restrict__ g_colors, float* __restrict__ g_feat,
+    float* __restrict__ g_w1t, float* __restrict__ g_b1, float* __restrict__ g_w2, float* __restrict__ g_b2) {
+  extern __shared__ __align__(128) float s_mem[];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int XS = gh_row_stride(F);
+  const int K = F + 3;
+  float* s_x = s_mem;                        // [GH_ROWS][XS]   features (+rgb), later dL/dfeat
+  float* s_gh = s_x + GH_ROWS * XS;          // [GH_ROWS][16]   dL/dhidden
+  float* s_hh = s_gh + GH_ROWS * GH_HID;     // [GH_ROWS][16]   hidden
+  float* s_gz = s_hh + GH_ROWS * GH_HID;     // [GH_ROWS][12]   dL/dz2
+  float* s_w1 = s_gz + GH_ROWS * 12;         // [K][16]
+  float* s_w2 = s_w1 + K * GH_HID;           // [11][4]
+  float* s_b2 = s_w2 + GH_OUT * 4;           // [11]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < K * GH_HID; i += GH_THREADS) s_w1[i] = w1t[i];
+  if (tid < GH_OUT * 4) s_w2[tid] = w2[tid];
+  if (tid < GH_OUT) s_b2[tid] = b2[tid];
+  if (tid == 0) {
+    mbar_init(&s_bar, 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  float acc_a[GH_HID], acc_b[GH_HID];  // dL/dw1t rows k = tid and k = tid + 64
+#pragma unroll
+  for (int j = 0; j < GH_HID; j++) acc_a[j] = acc_b[j] = 0.f;
+  float acc_small[5] = {0.f, 0.f, 0.f, 0.f, 0.f};  // second warp: lane < 16 -> b1[lane]; 16 <= lane < 27 -> w2 row, b2
+  const int ka = tid, kb = tid + GH_THREADS;
+  const bool dual = ((tid & ~31) + GH_THREADS) < K;  // warp-uniform: does this warp own any second column?
+
+  const long long tiles = (n + GH_ROWS - 1) / GH_ROWS;
+  uint32_t phase = 0;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long base = tile * GH_ROWS;
+    const int rows = (int)min((long long)GH_ROWS, n - base);
+    gh_fetch_tile(feat, rgb, base, rows, F, XS, s_x, &s_bar, fast != 0);
+
+    // ---- (1) ----
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const int r = tid + half * GH_THREADS;
+      float gh[GH_HID], h[GH_HID], gz[12];
+#pragma unroll
+      for (int j = 0; j < GH_HID; j++) gh[j] = h[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < 12; i++) gz[i] = 0.f;
+      if (r < rows) {
+        const long long g = base + r;
+        const float4* hp = reinterpret_cast<const float4*>(hidden + g * GH_HID);
+        const float4 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2), h3 = __ldg(hp + 3);
+        h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+        h[8] = h2.x; h[9] = h2.y; h[10] = h2.z; h[11] = h2.w; h[12] = h3.x; h[13] = h3.y; h[14] = h3.z; h[15] = h3.w;
+        float z[GH_OUT];
+        gh_second_layer(h, s_w2, s_b2, z);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float sg = z[c] > 20.f ? 1.f : gh_sigmoid(z[c]);  // d softplus
+          gz[c] = __ldg(g_scales + g * 3 + c) * sg;
+        }
+        {
+          const float4 gr = __ldg(reinterpret_cast<const float4*>(g_rotations) + g);
+          const float n2 = z[3] * z[3] + z[4] * z[4] + z[5] * z[5] + z[6] * z[6];
+          const float nrm = sqrtf(n2);
+          if (nrm > 1e-12f) {
+            const float inv = 1.f / nrm;
+            const float dotv = (gr.x * z[3] + gr.y * z[4] + gr.z * z[5] + gr.w * z[6]) * inv * inv;
+            gz[3] = (gr.x - z[3] * dotv) * inv;
+            gz[4] = (gr.y - z[4] * dotv) * inv;
+            gz[5] = (gr.z - z[5] * dotv) * inv;
+            gz[6] = (gr.w - z[6] * dotv) * inv;
+          } else {  // clamped norm: y = z / eps
+            gz[3] = gr.x * 1e12f; gz[4] = gr.y * 1e12f; gz[5] = gr.z * 1e12f; gz[6] = gr.w * 1e12f;
+          }
+        }
+        {
+          const float y = gh_sigmoid(z[7]);
+          gz[7] = __ldg(g_opacity + g) * y * (1.f - y);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float y = gh_sigmoid(z[8 + c]);
+          gz[8 + c] = __ldg(g_colors + g * 3 + c) * y * (1.f - y);
+        }
+#pragma unroll
+        for (int i = 0; i < GH_OUT; i++) {
+          const int hb = gh_hidden_base(i);
+#pragma unroll
+          for (int j = 0; j < 4; j++) gh[hb + j] = fmaf(s_w2[i * 4 + j], gz[i], gh[hb + j]);
+        }
+#pragma unroll
+        for (int j = 0; j < GH_HID; j++) gh[j] = h[j] > 0.f ? gh[j] : 0.f;
+      }
+      float4* ghp = reinterpret_cast<float4*>(s_gh + r * GH_HID);
+      float4* hhp = reinterpret_cast<float4*>(s_hh + r * GH_HID);
+      float4* gzp = reinterpret_cast<float4*>(s_gz + r * 12);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        ghp[q] = make_float4(gh[4 * q], gh[4 * q + 1], gh[4 * q + 2], gh[4 * q + 3]);
+        hhp[q] = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+      }
+#pragma unroll
+      for (int q = 0; q < 3; q++) gzp[q] = make_float4(gz[4 * q], gz[4 * q + 1], gz[4 * q + 2], gz[4 * q + 3]);
+    }
+    if (fast) {
+      mbar_wait(&s_bar, phase);
+      phase ^= 1;
+    }
+    __syncthreads();
+
+    // ---- (2) weight gradients over the tile's valid rows ----
+    if (ka < K) {
+      if (dual) {
+        const bool vb = kb < K;
+        for (int t = 0; t < rows; t++) {
+          const float xa = s_x[t * XS + ka];
+          const float xb = vb ? s_x[t * XS + kb] : 0.f;
+          const float4* gp = reinterpret_cast<const float4*>(s_gh + t * GH_HID);
+          const float4 wa = gp[0], wb = gp[1], wc = gp[2], wd = gp[3];
+          GH_FMA16(acc_a, xa, wa, wb, wc, wd)
+          GH_FMA16(acc_b, xb, wa, wb, wc, wd)
+        }
+      } else {
+        for (int t = 0; t < rows; t++) {
+          const float xa = s_x[t * XS + ka];
+          const float4* gp = reinterpret_cast<const float4*>(s_gh + t * GH_HID);
+          const float4 wa = gp[0], wb = gp[1], wc = gp[2], wd = gp[3];
+          GH_FMA16(acc_a, xa, wa, wb, wc, wd)
+        }
+      }
+    }
+    if (tid >= 32) {
+      const int lane = tid - 32;
+      if (lane < GH_HID) {
+        float s = 0.f;
+        for (int t = 0; t < rows; t++) s += s_gh[t * GH_HID + lane];
+        acc_small[0] += s;
+      } else if (lane < GH_HID + GH_OUT) {
+        const int i = lane - GH_HID;
+        const int hb = gh_hidden_base(i);
+        for (int t = 0; t < rows; t++) {
+          const float gzi = s_gz[t * 12 + i];
+          const float4 hv = *reinterpret_cast<const float4*>(s_hh + t * GH_HID + hb);
+          acc_small[0] = fmaf(gzi, hv.x, acc_small[0]);
+          acc_small[1] = fmaf(gzi, hv.y, acc_small[1]);
+          acc_small[2] = fmaf(gzi, hv.z, acc_small[2]);
+          acc_small[3] = fmaf(gzi, hv.w, acc_small[3]);
+          acc_small[4] += gzi;
+        }
+      }
+    }
+    __syncthreads();
+
+    // ---- (3) dL/dfeat = w1t . dL/dhidden, written over this thread's two rows ----
+    {
+      float g0[GH_HID], g1[GH_HID];
+      const float4* p0 = reinterpret_cast<const float4*>(s_gh + tid * GH_HID);
+      const float4* p1 = reinterpret_cast<const float4*>(s_gh + (tid + GH_THREADS) * GH_HID);
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const float4 a = p0[q], b = p1[q];
+        g0[4 * q] = a.x; g0[4 * q + 1] = a.y; g0[4 * q + 2] = a.z; g0[4 * q + 3] = a.w;
+        g1[4 * q] = b.x; g1[4 * q + 1] = b.y; g1[4 * q + 2] = b.z; g1[4 * q + 3] = b.w;
+      }
+      float* x0p = s_x + tid * XS;
+      float* x1p = s_x + (tid + GH_THREADS) * XS;
+      const int k4n = K >> 2;  // 4 * k4n >= F: covers every feature column; the rgb columns are scratch
+      for (int k4 = 0; k4 < k4n; k4++) {
+        float o0[4], o1[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const float4* w = reinterpret_cast<const float4*>(s_w1 + (4 * k4 + q) * GH_HID);
+          const float4 wa = w[0], wb = w[1], wc = w[2], wd = w[3];
+          const float wv[16] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w, wd.x, wd.y, wd.z, wd.w};
+          float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;  // two partial chains per row
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            a0 = fmaf(wv[j], g0[j], a0);
+            c0 = fmaf(wv[8 + j], g0[8 + j], c0);
+            a1 = fmaf(wv[j], g1[j], a1);
+            c1 = fmaf(wv[8 + j], g1[8 + j], c1);
+          }
+          o0[q] = a0 + c0;
+          o1[q] = a1 + c1;
+        }
+        *reinterpret_cast<float4*>(x0p + 4 * k4) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+        *reinterpret_cast<float4*>(x1p + 4 * k4) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+      }
+    }
+    if (fast) {
+      fence_proxy_async();
+      __syncthreads();
+#pragma unroll
+      for (int r = tid; r < GH_ROWS; r += GH_THREADS)
+        if (r < rows) bulk_s2g(g_feat + (base + r) * F, s_x + r * XS, (uint32_t)F * 4u);
+      bulk_commit();
+      bulk_wait_read();
+    } else {
+      __syncthreads();
+      for (int r = 0; r < rows; r++)
+        for (int k = tid; k < F; k += GH_THREADS) g_feat[(base + r) * F + k] = s_x[r * XS + k];
+    }
+    __syncthreads();  // s_x, s_gh, s_hh, s_gz are free again
+  }
+
+  // ---- add this CTA's sums to the global gradients (lane-contiguous atomics through shared memory) ----
+  float* s_out = s_x;  // [K][16]
+  if (ka < K) {
+#pragma unroll
+    for (int j = 0; j < GH_HID; j++) s_out[ka * GH_HID + j] = acc_a[j];
+    if (kb < K) {
+#pragma unroll
+      for (int j = 0; j < GH_HID; j++) s_out[kb * GH_HID + j] = acc_b[j];
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < K * GH_HID; i += GH_THREADS) {
+    const float v = s_out[i];
+    const bool structural_zero = (i >> 4) >= F && (i & 15) < 12;  // S/R/A heads do not see rgb: keep those weights' gradient 0
+    if (v != 0.f && !structural_zero) atomicAdd(g_w1t + i, v);
+  }
+  if (tid >= 32) {
+    const int lane = tid - 32;
+    if (lane < GH_HID) {
+      atomicAdd(g_b1 + lane, acc_small[0]);
+    } else if (lane < GH_HID + GH_OUT) {
+      const int i = lane - GH_HID;
+#pragma unroll
+      for (int j = 0; j < 4; j++) atomicAdd(g_w2 + i * 4 + j, acc_small[j]);
+      atomicAdd(g_b2 + i, acc_small[4]);
+    }
+  }
+}
+
+}  // namespace ocrf
+
+using namespace ocrf;
+
+static size_t gh_fwd_smem(int F) {
+  return ((size_t)GH_ROWS * gh_row_stride(F) + (size_t)(F + 3) * GH_HID + GH_HID + GH_OUT * 4 + 12) * 4;
+}
+static size_t gh_bwd_smem(int F) {
+  return ((size_t)GH_ROWS * gh_row_stride(F) + (size_t)GH_ROWS * (GH_HID * 2 + 12) + (size_t)(F + 3) * GH_HID +
+          GH_OUT * 4 + 12) * 4;
+}
+static bool gh_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static int gh_grid(long long n, size_t smem) {
+  const long long tiles = (n + GH_ROWS - 1) / GH_ROWS;
+  const int per_sm = (int)((220 * 1024) / (smem + 1024));
+  const long long cap = (long long)NUM_SMS * (per_sm < 1 ? 1 : per_sm);
+  return (int)(tiles < cap ? tiles : cap);
+}
+
+extern "C" int ocrf_gaussian_heads_forward(void* stream, int64_t n, int32_t F, const float* feat, const float* rgb,
+                                           const float* w1t, const float* b1, const float* w2, const float* b2,
+                                           float* opacity, float* scales, float* rotations, float* colors,
+                                           float* hidden) {
+  if (n < 0 || F <= 0 || F + 3 > GH_MAXK) return OCRF_EINVAL;
+  if (n == 0) return 0;
+  if (!feat || !rgb || !w1t || !b1 || !w2 || !b2 || !opacity || !scales || !rotations || !colors || !hidden) return OCRF_EINVAL;
+  if (!gh_aligned16(rotations) || !gh_aligned16(hidden)) return OCRF_EINVAL;
+  const size_t smem = gh_fwd_smem(F);
+  cudaError_t e = cudaFuncSetAttribute(gaussian_heads_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int fast = (F % 4 == 0) && gh_aligned16(feat);
+  gaussian_heads_forward_kernel<<<gh_grid(n, smem), GH_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      n, F, fast, feat, rgb, w1t, b1, w2, b2, opacity, scales, rotations, colors, hidden);
+  OCRF_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int ocrf_gaussian_heads_backward(void* stream, int64_t n, int32_t F, const float* feat, const float* rgb,
+                                            const float* w1t, const float* w2, const float* b2, const float* hidden,
+                                            const float* g_opacity, const float* g_scales, const float* g_rotations,
+                                            const float* g_colors, float* g_feat, float* g_w1t, float* g_b1,
+                                            float* g_w2, float* g_b2) {
+  if (n < 0 || F <= 0 || F + 3 > GH_MAXK) return OCRF_EINVAL;
+  if (n == 0) return 0;
+  if (!feat || !rgb || !w1t || !w2 || !b2 || !hidden || !g_opacity || !g_scales || !g_rotations || !g_colors || !g_feat ||
+      !g_w1t || !g_b1 || !g_w2 || !g_b2)
+    return OCRF_EINVAL;
+  if (!gh_aligned16(g_rotations) || !gh_aligned16(hidden)) return OCRF_EINVAL;
+  const size_t smem = gh_bwd_smem(F);
+  cudaError_t e = cudaFuncSetAttribute(gaussian_heads_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return (int)e;
+  const int fast = (F % 4 == 0) && gh_aligned16(feat) && gh_aligned16(g_feat);
+  gaussian_heads_backward_kernel<<<gh_grid(n, smem), GH_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+      n, F, fast, feat, rgb, w1t, w2, b2, hidden, g_opacity, g_scales, g_rotations, g_colors, g_feat, g_w1t, g_b1,
+      g_w2, g_b2);
+  OCRF_CHECK_LAST();
+  return 0;
+}

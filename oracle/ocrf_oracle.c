@@ -595,3 +595,126 @@ void ocrf_oracle_opacity_mask_backward(int B, int C, int H, int W, int K, const 
   for (int i = 0; i < 2 * K * K; i++) g_w[i] = (float)gw[i];
   free(gw); free(gz); free(gst);
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Stage 0: OcRF Gaussian construction heads (view_transformer_ocrf.py:272-320; built with
+ * input_dim 80, hidden_dim 4 at :611-622; evaluated at :1130-1133).  Parameters are given per head
+ * in torch's nn.Linear layout (weight [out,in], bias [out]), NOT packed:
+ *   head order S (softplus, 3 outputs), R (normalize, 4), A (sigmoid, 1), C (sigmoid, 3; input = cat(feat, rgb)).
+ * fc1_w[h] [4, in_h], fc1_b[h] [4], fc2_w[h] [out_h, 4], fc2_b[h] [out_h];  in_h = F (S,R,A) or F+3 (C).
+ * ------------------------------------------------------------------------------------------ */
+static const int GH_OUTS[4] = {3, 4, 1, 3};
+
+static float gh_softplus(float x) { return x > 20.f ? x : log1pf(expf(x)); } /* nn.Softplus(beta=1, threshold=20) */
+static float gh_sigmoid(float x) { return 1.f / (1.f + expf(-x)); }
+
+void ocrf_oracle_gaussian_heads_forward(long long n, int F, const float* feat, const float* rgb,
+                                        const float* const* fc1_w, const float* const* fc1_b,
+                                        const float* const* fc2_w, const float* const* fc2_b, float* opacity,
+                                        float* scales, float* rotations, float* colors) {
+  for (long long g = 0; g < n; g++) {
+    float z[4][4];
+    for (int hd = 0; hd < 4; hd++) {
+      const int in = hd == 3 ? F + 3 : F;
+      float hdn[4];
+      for (int j = 0; j < 4; j++) {
+        float acc = fc1_b[hd][j];
+        for (int k = 0; k < F; k++) acc += feat[g * F + k] * fc1_w[hd][j * in + k];
+        if (hd == 3)
+          for (int c = 0; c < 3; c++) acc += rgb[g * 3 + c] * fc1_w[hd][j * in + F + c];
+        hdn[j] = acc > 0.f ? acc : 0.f;
+      }
+      for (int i = 0; i < GH_OUTS[hd]; i++) {
+        float acc = fc2_b[hd][i];
+        for (int j = 0; j < 4; j++) acc += fc2_w[hd][i * 4 + j] * hdn[j];
+        z[hd][i] = acc;
+      }
+    }
+    for (int c = 0; c < 3; c++) scales[g * 3 + c] = gh_softplus(z[0][c]);
+    float nrm = sqrtf(z[1][0] * z[1][0] + z[1][1] * z[1][1] + z[1][2] * z[1][2] + z[1][3] * z[1][3]);
+    if (nrm < 1e-12f) nrm = 1e-12f; /* F.normalize eps */
+    for (int c = 0; c < 4; c++) rotations[g * 4 + c] = z[1][c] / nrm;
+    opacity[g] = gh_sigmoid(z[2][0]);
+    for (int c = 0; c < 3; c++) colors[g * 3 + c] = gh_sigmoid(z[3][c]);
+  }
+}
+
+/* Backward in double accumulation for the parameter sums (order-independent reference values).
+ * g_fc1_w[h] etc. are written (not accumulated). */
+void ocrf_oracle_gaussian_heads_backward(long long n, int F, const float* feat, const float* rgb,
+                                         const float* const* fc1_w, const float* const* fc1_b,
+                                         const float* const* fc2_w, const float* const* fc2_b,
+                                         const float* g_opacity, const float* g_scales, const float* g_rotations,
+                                         const float* g_colors, float* g_feat, float* const* g_fc1_w,
+                                         float* const* g_fc1_b, float* const* g_fc2_w, float* const* g_fc2_b) {
+  double* a1w[4];
+  double a1b[4][4] = {{0}}, a2w[4][16] = {{0}}, a2b[4][4] = {{0}};
+  for (int hd = 0; hd < 4; hd++) a1w[hd] = (double*)calloc((size_t)4 * (F + 3), sizeof(double));
+  for (long long g = 0; g < n; g++) {
+    for (int k = 0; k < F; k++) g_feat[g * F + k] = 0.f;
+    for (int hd = 0; hd < 4; hd++) {
+      const int in = hd == 3 ? F + 3 : F;
+      float pre[4], hdn[4], z[4], gz[4] = {0, 0, 0, 0};
+      for (int j = 0; j < 4; j++) {
+        float acc = fc1_b[hd][j];
+        for (int k = 0; k < F; k++) acc += feat[g * F + k] * fc1_w[hd][j * in + k];
+        if (hd == 3)
+          for (int c = 0; c < 3; c++) acc += rgb[g * 3 + c] * fc1_w[hd][j * in + F + c];
+        pre[j] = acc;
+        hdn[j] = acc > 0.f ? acc : 0.f;
+      }
+      for (int i = 0; i < GH_OUTS[hd]; i++) {
+        float acc = fc2_b[hd][i];
+        for (int j = 0; j < 4; j++) acc += fc2_w[hd][i * 4 + j] * hdn[j];
+        z[i] = acc;
+      }
+      if (hd == 0) {
+        for (int c = 0; c < 3; c++) gz[c] = g_scales[g * 3 + c] * (z[c] > 20.f ? 1.f : gh_sigmoid(z[c]));
+      } else if (hd == 1) {
+        const float n2 = z[0] * z[0] + z[1] * z[1] + z[2] * z[2] + z[3] * z[3];
+        const float nrm = sqrtf(n2);
+        const float* gr = g_rotations + g * 4;
+        if (nrm > 1e-12f) {
+          const float dotv = (gr[0] * z[0] + gr[1] * z[1] + gr[2] * z[2] + gr[3] * z[3]) / n2;
+          for (int c = 0; c < 4; c++) gz[c] = (gr[c] - z[c] * dotv) / nrm;
+        } else {
+          for (int c = 0; c < 4; c++) gz[c] = gr[c] * 1e12f;
+        }
+      } else if (hd == 2) {
+        const float y = gh_sigmoid(z[0]);
+        gz[0] = g_opacity[g] * y * (1.f - y);
+      } else {
+        for (int c = 0; c < 3; c++) {
+          const float y = gh_sigmoid(z[c]);
+          gz[c] = g_colors[g * 3 + c] * y * (1.f - y);
+        }
+      }
+      float gh[4] = {0, 0, 0, 0};
+      for (int i = 0; i < GH_OUTS[hd]; i++) {
+        a2b[hd][i] += gz[i];
+        for (int j = 0; j < 4; j++) {
+          a2w[hd][i * 4 + j] += (double)gz[i] * hdn[j];
+          gh[j] += fc2_w[hd][i * 4 + j] * gz[i];
+        }
+      }
+      for (int j = 0; j < 4; j++) {
+        if (!(pre[j] > 0.f)) continue;
+        a1b[hd][j] += gh[j];
+        for (int k = 0; k < F; k++) {
+          a1w[hd][j * in + k] += (double)gh[j] * feat[g * F + k];
+          g_feat[g * F + k] += gh[j] * fc1_w[hd][j * in + k];
+        }
+        if (hd == 3)
+          for (int c = 0; c < 3; c++) a1w[hd][j * in + F + c] += (double)gh[j] * rgb[g * 3 + c];
+      }
+    }
+  }
+  for (int hd = 0; hd < 4; hd++) {
+    const int in = hd == 3 ? F + 3 : F;
+    for (int i = 0; i < 4 * in; i++) g_fc1_w[hd][i] = (float)a1w[hd][i];
+    for (int j = 0; j < 4; j++) g_fc1_b[hd][j] = (float)a1b[hd][j];
+    for (int i = 0; i < GH_OUTS[hd] * 4; i++) g_fc2_w[hd][i] = (float)a2w[hd][i];
+    for (int i = 0; i < GH_OUTS[hd]; i++) g_fc2_b[hd][i] = (float)a2b[hd][i];
+    free(a1w[hd]);
+  }
+}

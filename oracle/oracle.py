@@ -232,3 +232,42 @@ def opacity_mask_backward(x, w, mask, stats, g_out):
                                             _ptr(_f32(mask)), _ptr(_f32(stats)), _ptr(_f32(g_out)), _ptr(gx), _ptr(gw),
                                             _ptr(gop))
     return gx, gw, gop
+
+
+HEAD_ORDER = ("S_MLP", "R_MLP", "A_MLP", "C_MLP")
+HEAD_OUTS = (3, 4, 1, 3)
+
+
+def _head_ptrs(params, key, shapes=None):
+    arrs = [_f32(params[h][key]) for h in HEAD_ORDER]
+    return arrs, (C.c_void_p * 4)(*[a.ctypes.data for a in arrs])
+
+
+def gaussian_heads_forward(feat, rgb, params):
+    """params: {"S_MLP": {"fc1.weight": [4,F], "fc1.bias": [4], "fc2.weight": [3,4], "fc2.bias": [3]}, "R_MLP": ..,
+    "A_MLP": .., "C_MLP": {"fc1.weight": [4,F+3], ..}} in nn.Linear layout (view_transformer_ocrf.py:272-320)."""
+    feat, rgb = _f32(feat), _f32(rgb)
+    n, F = feat.shape
+    keep = [_head_ptrs(params, k) for k in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")]
+    op, sc = np.zeros((n, 1), np.float32), np.zeros((n, 3), np.float32)
+    rot, col = np.zeros((n, 4), np.float32), np.zeros((n, 3), np.float32)
+    lib().ocrf_oracle_gaussian_heads_forward(C.c_longlong(n), C.c_int(F), _ptr(feat), _ptr(rgb), keep[0][1], keep[1][1],
+                                             keep[2][1], keep[3][1], _ptr(op), _ptr(sc), _ptr(rot), _ptr(col))
+    return op, sc, rot, col
+
+
+def gaussian_heads_backward(feat, rgb, params, g_opacity, g_scales, g_rotations, g_colors):
+    feat, rgb = _f32(feat), _f32(rgb)
+    n, F = feat.shape
+    keep = [_head_ptrs(params, k) for k in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")]
+    grads = {h: {"fc1.weight": np.zeros((4, F + 3 if h == "C_MLP" else F), np.float32), "fc1.bias": np.zeros(4, np.float32),
+                 "fc2.weight": np.zeros((o, 4), np.float32), "fc2.bias": np.zeros(o, np.float32)}
+             for h, o in zip(HEAD_ORDER, HEAD_OUTS)}
+    gp = [(C.c_void_p * 4)(*[grads[h][k].ctypes.data for h in HEAD_ORDER])
+          for k in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")]
+    g_feat = np.zeros((n, F), np.float32)
+    gs = [_f32(g_opacity), _f32(g_scales), _f32(g_rotations), _f32(g_colors)]
+    lib().ocrf_oracle_gaussian_heads_backward(C.c_longlong(n), C.c_int(F), _ptr(feat), _ptr(rgb), keep[0][1], keep[1][1],
+                                              keep[2][1], keep[3][1], _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]),
+                                              _ptr(g_feat), gp[0], gp[1], gp[2], gp[3])
+    return g_feat, grads

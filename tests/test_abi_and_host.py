@@ -124,3 +124,35 @@ def test_camera_conventions():
                             torch.from_numpy(np.stack([c["projmatrix"] for c in ring])),
                             torch.from_numpy(np.stack([c["campos"] for c in ring])), 0.63, torch.full((6,), 0.23))
     assert packed.shape == (6, _lib.OCRF_CAM_STRIDE) and float(packed[3, 35]) == pytest.approx(0.63)
+
+
+def test_gaussian_heads_checkpoint_keys_and_packing_roundtrip():
+    """GaussianHeads keeps one packed parameter but reads/writes the reference's checkpoint keys
+    (view_transformer_ocrf.py:619-622: S_MLP/R_MLP/A_MLP/C_MLP, each fc1 + fc2)."""
+    from ocrfdet_b200.gaussian_heads import GaussianHeads, _views, packed_sizes
+    torch.manual_seed(0)
+    m = GaussianHeads(80)
+    sd = m.state_dict()
+    want = {"%s.%s.%s" % (h, fc, p) for h in ("S_MLP", "R_MLP", "A_MLP", "C_MLP") for fc in ("fc1", "fc2")
+            for p in ("weight", "bias")}
+    assert set(sd) == want
+    assert tuple(sd["C_MLP.fc1.weight"].shape) == (4, 83) and tuple(sd["S_MLP.fc1.weight"].shape) == (4, 80)
+    assert tuple(sd["R_MLP.fc2.weight"].shape) == (4, 4) and tuple(sd["A_MLP.fc2.bias"].shape) == (1,)
+    # the S/R/A heads have no rgb inputs: those packed rows are zero
+    v = _views(m.packed.data, 80)
+    assert float(v["w1t"][80:, :12].abs().max()) == 0.0 and float(v["w1t"][80:, 12:].abs().max()) > 0.0
+    assert m.packed.numel() == packed_sizes(80)[1] == 83 * 16 + 16 + 44 + 12
+    # load a "checkpoint" with the reference's keys into a fresh module (also under a prefix, as inside a detector)
+    sd2 = {k: torch.randn_like(t) for k, t in sd.items()}
+    m2 = GaussianHeads(80)
+    m2.load_state_dict(sd2)
+    for k, t in m2.state_dict().items():
+        assert torch.equal(t, sd2[k]), k
+    holder = torch.nn.Module()
+    holder.heads = GaussianHeads(80)
+    holder.load_state_dict({"heads." + k: t for k, t in sd2.items()})
+    assert torch.equal(holder.heads.packed.data, m2.packed.data)
+    with pytest.raises(RuntimeError):
+        GaussianHeads(80).load_state_dict({k: t for k, t in sd2.items() if k != "R_MLP.fc2.bias"})
+    with pytest.raises(Exception):   # no CPU path
+        m2(torch.zeros(4, 80), torch.zeros(4, 3))

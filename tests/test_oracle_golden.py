@@ -11,7 +11,9 @@ from oracle import oracle
 from tests import util
 from tests.golden.make_golden import scene
 
-GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
+                if not os.path.basename(p).startswith("heads_"))
+GOLDEN_HEADS = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "heads_*.npz")))
 
 
 def test_golden_files_present():
@@ -53,3 +55,29 @@ def test_oracle_matches_reference_cuda_golden(path):
     # per-Gaussian chain: ill-conditioned in float32 (see tests/test_gpu_reference.py) -> looser bound
     for name, key in (("means3D", "g_means3D"), ("scales", "g_scales"), ("rotations", "g_rotations")):
         assert util.rel_err(z[key], gw[name]) <= 5e-4, name
+
+
+def heads_params(z):
+    return {h: {k: z["%s.%s" % (h, k)] for k in ("fc1.weight", "fc1.bias", "fc2.weight", "fc2.bias")}
+            for h in oracle.HEAD_ORDER}
+
+
+@pytest.mark.parametrize("path", GOLDEN_HEADS, ids=[os.path.basename(p) for p in GOLDEN_HEADS])
+def test_heads_oracle_matches_reference_modules(path):
+    """tests/golden/heads_*.npz were produced by executing the reference's own four nn.Module classes
+    (tests/golden/make_golden_heads.py); float32, so 1e-5 forward / 1e-4 gradients."""
+    z = np.load(path)
+    params = heads_params(z)
+    op, sc, rot, col = oracle.gaussian_heads_forward(z["feat"], z["rgb"], params)
+    for got, key in ((op, "opacity"), (sc, "scaling"), (rot, "rotation"), (col, "color")):
+        assert np.abs(got - z[key]).max() <= 1e-5 * (1 + np.abs(z[key]).max()), key
+    g_feat, grads = oracle.gaussian_heads_backward(z["feat"], z["rgb"], params, z["g_opacity"], z["g_scaling"],
+                                                   z["g_rotation"], z["g_color"])
+    assert util.rel_err(g_feat, z["g_feat"]) <= 1e-4
+    for h in oracle.HEAD_ORDER:
+        for k, v in grads[h].items():
+            assert util.rel_err(v, z["g.%s.%s" % (h, k)]) <= 1e-4, (h, k)
+
+
+def test_heads_golden_present():
+    assert len(GOLDEN_HEADS) >= 2
