@@ -36,7 +36,8 @@ def build(force=False, verbose=False):
         s = os.path.join(CSRC, src)
         o = os.path.join(OBJ, src.replace(".cu", ".o"))
         if force or _stale(o, [s] + headers):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
+            extra = os.environ.get("OCRF_NVCC_EXTRA", "").split()  # experiments only, e.g. -DOCRF_PRE_MINB=6
+            jobs.append([nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

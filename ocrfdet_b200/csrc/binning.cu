@@ -207,10 +207,6 @@ __global__ void __launch_bounds__(256) ranges_cull_pack_kernel(OcrfShape sh, uin
 // passes instead of 6.  A stable sort by tile of a depth-ordered sequence is exactly the reference's
 // order, so keys, point list and ranges are bit-identical (tests run both algorithms).
 // ------------------------------------------------------------------------------------------------
-constexpr unsigned long long SS_FLAG_LOCAL = 1ull << 62;
-constexpr unsigned long long SS_FLAG_INCL = 2ull << 62;
-constexpr unsigned long long SS_VALUE_MASK = (1ull << 62) - 1;
-
 // inclusive scan of tiles_touched over the depth-sorted visible Gaussians (decoupled look-back)
 __global__ void __launch_bounds__(256) scan_sorted_tiles_kernel(const uint32_t* __restrict__ header,
                                                                 const uint32_t* __restrict__ vis_vals,
@@ -248,23 +244,9 @@ __global__ void __launch_bounds__(256) scan_sorted_tiles_kernel(const uint32_t* 
     if (w < warp) warp_off += y;
     total += y;
   }
-  if (tid == 0) {
-    unsigned long long excl = 0;
-    if (bid == 0) {
-      atomicExch(&status[0], SS_FLAG_INCL | total);
-    } else {
-      atomicExch(&status[bid], SS_FLAG_LOCAL | total);
-      int look = (int)bid - 1;
-      while (true) {
-        const unsigned long long st = *reinterpret_cast<volatile unsigned long long*>(&status[look]);
-        if ((st >> 62) == 0) continue;
-        excl += st & SS_VALUE_MASK;
-        if ((st >> 62) == 2) break;
-        look--;
-      }
-      atomicExch(&status[bid], SS_FLAG_INCL | (excl + total));
-    }
-    s_prefix = (uint32_t)excl;
+  if (warp == 0) {
+    const unsigned long long excl = lookback_warp(status, (int)bid, total);
+    if (lane == 0) s_prefix = (uint32_t)excl;
   }
   __syncthreads();
   uint32_t run = s_prefix + warp_off + incl - sum;

@@ -147,6 +147,45 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // make generic-proxy shared-memory writes visible to the async proxy (TMA unit)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// ---- decoupled look-back, resolved by one warp (32 predecessors per memory round trip) ----
+// status words: bits 63:62 = 0 not published, 1 = the CTA's own total, 2 = inclusive prefix; bits 61:0 = value.
+constexpr unsigned long long LBK_FLAG_LOCAL = 1ull << 62;
+constexpr unsigned long long LBK_FLAG_INCL = 2ull << 62;
+constexpr unsigned long long LBK_VALUE_MASK = (1ull << 62) - 1;
+
+// Called by all 32 lanes of ONE warp of CTA `bid` (chain order = bid).  Publishes `total`, returns the exclusive
+// prefix of the chain (same value in every lane) and publishes the inclusive one.
+__device__ __forceinline__ unsigned long long lookback_warp(unsigned long long* status, int bid,
+                                                            unsigned long long total) {
+  const int lane = threadIdx.x & 31;
+  if (bid == 0) {
+    if (lane == 0) atomicExch(&status[0], LBK_FLAG_INCL | total);
+    return 0ull;
+  }
+  if (lane == 0) atomicExch(&status[bid], LBK_FLAG_LOCAL | total);
+  unsigned long long excl = 0;
+  int look = bid - 1;
+  while (true) {
+    const int idx = look - lane;
+    unsigned long long st = 2ull << 62;  // virtual inclusive 0 before the start of the chain
+    if (idx >= 0) st = *reinterpret_cast<volatile unsigned long long*>(&status[idx]);
+    const unsigned flag = (unsigned)(st >> 62);
+    const unsigned incl_mask = __ballot_sync(0xffffffffu, flag == 2u);
+    const unsigned pending = __ballot_sync(0xffffffffu, flag == 0u);
+    const int first = incl_mask ? (__ffs(incl_mask) - 1) : 31;
+    const unsigned need = first == 31 ? 0xffffffffu : ((2u << first) - 1u);
+    if (pending & need) continue;  // a predecessor we need has not published yet
+    unsigned long long v = lane <= first ? (st & LBK_VALUE_MASK) : 0ull;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    excl += v;
+    if (incl_mask) break;
+    look -= 32;
+  }
+  if (lane == 0) atomicExch(&status[bid], LBK_FLAG_INCL | (excl + total));
+  return excl;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

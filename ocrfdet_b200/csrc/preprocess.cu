@@ -22,11 +22,11 @@
 
 namespace ocrf {
 
-constexpr unsigned long long SCAN_FLAG_LOCAL = 1ull << 62;
-constexpr unsigned long long SCAN_FLAG_INCL = 2ull << 62;
-constexpr unsigned long long SCAN_VALUE_MASK = (1ull << 62) - 1;
+#ifndef OCRF_PRE_MINB
+#define OCRF_PRE_MINB 5  // 48 registers: five CTAs per SM (the kernel is latency bound: ticket, staging, look-back)
+#endif
 
-__global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
+__global__ void __launch_bounds__(PRE_THREADS, OCRF_PRE_MINB) preprocess_forward_kernel(
     OcrfShape sh, int blocks_per_view, const float* __restrict__ means3D, const float* __restrict__ scales,
     const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp, const float* __restrict__ opacities,
     const float* __restrict__ shs, const Camera* __restrict__ cams, float scale_modifier, int prefiltered,
@@ -172,28 +172,16 @@ __global__ void __launch_bounds__(PRE_THREADS) preprocess_forward_kernel(
     if (w < warp) warp_off += t;
     cta_total += t;
   }
-  if (tid == 0) {
-    unsigned long long excl = 0;
-    if (bid == 0) {
-      atomicExch(&scan_status[0], SCAN_FLAG_INCL | cta_total);
-    } else {
-      atomicExch(&scan_status[bid], SCAN_FLAG_LOCAL | cta_total);
-      int look = bid - 1;
-      while (true) {
-        const unsigned long long st = *reinterpret_cast<volatile unsigned long long*>(&scan_status[look]);
-        if ((st >> 62) == 0) continue;  // predecessor not published yet
-        excl += st & SCAN_VALUE_MASK;
-        if ((st >> 62) == 2) break;
-        look--;
+  if (warp == 0) {
+    const unsigned long long excl = lookback_warp(scan_status, bid, cta_total);
+    if (lane == 0) {
+      s_prefix = excl;
+      if (i0 == 0) view_start[v] = (uint32_t)(excl >> 32);
+      if (bid == (int)gridDim.x - 1) {
+        header[HDR_NUM_PAIRS] = (uint32_t)(excl + cta_total);
+        header[HDR_NUM_VIS] = (uint32_t)((excl + cta_total) >> 32);
+        view_start[sh.V] = (uint32_t)((excl + cta_total) >> 32);
       }
-      atomicExch(&scan_status[bid], SCAN_FLAG_INCL | (excl + cta_total));
-    }
-    s_prefix = excl;
-    if (i0 == 0) view_start[v] = (uint32_t)(excl >> 32);
-    if (bid == (int)gridDim.x - 1) {
-      header[HDR_NUM_PAIRS] = (uint32_t)(excl + cta_total);
-      header[HDR_NUM_VIS] = (uint32_t)((excl + cta_total) >> 32);
-      view_start[sh.V] = (uint32_t)((excl + cta_total) >> 32);
     }
   }
   __syncthreads();

@@ -56,7 +56,9 @@ __device__ __forceinline__ void cov3d_f64(const float* sc, float mod, float4 q, 
     for (int j = i; j < 3; j++) out[e++] = s2[0] * A[0][i] * A[0][j] + s2[1] * A[1][i] * A[1][j] + s2[2] * A[2][i] * A[2][j];
 }
 
-__global__ void __launch_bounds__(256) preprocess_backward_kernel(
+constexpr int PB_THREADS = 128;  // ~160 registers (fp64 chain): 3 CTAs of 128 per SM instead of 1 of 256
+
+__global__ void __launch_bounds__(PB_THREADS) preprocess_backward_kernel(
     OcrfShape sh, const float* __restrict__ means3D, const float* __restrict__ scales,
     const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp, const float* __restrict__ shs,
     const Camera* __restrict__ cams, float scale_modifier, const int32_t* __restrict__ radii,
@@ -97,11 +99,17 @@ __global__ void __launch_bounds__(256) preprocess_backward_kernel(
   if (shs != nullptr)
     for (int k = 0; k < sh.sh_M * 3; k++) dL_dshs[gi * (size_t)sh.sh_M * 3 + k] = 0.;
 
+  // one round trip for the visibility of this Gaussian in every view of the sample, then only the visible ones
+  unsigned long long vis_mask = 0ull;
+#pragma unroll 8
+  for (int lv = 0; lv < vps; lv++)
+    vis_mask |= (unsigned long long)(__ldg(radii + (size_t)(s * vps + lv) * sh.P + i) > 0) << (lv & 63);
+
   for (int lv = 0; lv < vps; lv++) {
     const int v = s * vps + lv;
     const size_t o = (size_t)v * sh.P + i;
     double g2x = 0., g2y = 0.;
-    if (radii[o] > 0) {
+    if (vps <= 64 ? ((vis_mask >> lv) & 1ull) != 0ull : radii[o] > 0) {
       const Camera& cam = s_cams[lv];
       const float* vm = cam.view;
       const float* pm = cam.proj;
@@ -267,8 +275,8 @@ extern "C" int ocrf_preprocess_backward(void* stream, const OcrfShape* sh, const
   ocrf_geom_layout(sh, shs != nullptr, &G);
   const size_t smem = (size_t)sh->views_per_sample * sizeof(Camera);
   if (smem > 48 * 1024) return OCRF_ECAPACITY;
-  const dim3 grid(ceil_div(sh->P, 256), sh->S);
-  preprocess_backward_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+  const dim3 grid(ceil_div(sh->P, PB_THREADS), sh->S);
+  preprocess_backward_kernel<<<grid, PB_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
       *sh, means3D, scales, rotations, cov3D_precomp, shs, reinterpret_cast<const Camera*>(cams), scale_modifier,
       radii, at<uint8_t>(geom_ws, G.clamped), ggrad, dL_dcolors_view, dL_dmeans3D, dL_dmeans2D, dL_dopacities,
       dL_dscales, dL_drotations, dL_dcov3D, dL_dshs);
