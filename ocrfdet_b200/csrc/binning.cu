@@ -8,6 +8,8 @@
 // the tile boundaries AND gathers each pair's blend inputs (mean, conic, opacity, depth, colour)
 // into a contiguous 48-byte record, so that both blend kernels stream their tile's list with bulk
 // async copies instead of two dependent gathers per pair.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ocrf {
@@ -214,6 +216,7 @@ __global__ void __launch_bounds__(256) scan_sorted_tiles_kernel(const uint32_t* 
                                                                 uint32_t* __restrict__ sorted_offsets,
                                                                 unsigned long long* __restrict__ status,
                                                                 uint32_t* __restrict__ ticket) {
+  pdl_enter();
   __shared__ uint32_t s_warp[8];
   __shared__ uint32_t s_bid, s_prefix;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -413,6 +416,10 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
     uint32_t* vb = at<uint32_t>(geom_ws, (vpasses & 1) ? G.vis_vals : G.vis_vals_tmp);
     rc = sort_pairs_device(st, header + HDR_NUM_VIS, n, 0, vbit, ka, va, kb, vb, at<char>(geom_ws, G.vis_sort_ws));
     if (rc) return rc;
+#ifdef OCRF_DIAG  // timing experiment: the sort a second time (same result up to exact ties)
+    if (getenv("OCRF_DUP") && (atoi(getenv("OCRF_DUP")) & 8))
+      sort_pairs_device(st, header + HDR_NUM_VIS, n, 0, vbit, ka, va, kb, vb, at<char>(geom_ws, G.vis_sort_ws));
+#endif
     // (2) inclusive scan of tiles_touched in depth order: where every Gaussian's pairs sit in the pair stream
     const uint32_t* vvals = at<uint32_t>(geom_ws, G.vis_vals);
     uint32_t* sorted_offsets = at<uint32_t>(bin_ws, B.split_counts);
@@ -420,7 +427,7 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
     const size_t sblocks = (n + 1023) / 1024;
     uint32_t* sticket = reinterpret_cast<uint32_t*>(sstat + sblocks + 1);
     cudaMemsetAsync(sstat, 0, (sblocks + 1) * 8 + 64, st);
-    scan_sorted_tiles_kernel<<<(unsigned)sblocks, 256, 0, st>>>(header, vvals, at<uint32_t>(geom_ws, G.tiles_touched),
+    launch_chain(scan_sorted_tiles_kernel, dim3((unsigned)sblocks), dim3(256), 0, st, header, vvals, at<uint32_t>(geom_ws, G.tiles_touched),
                                                                 sorted_offsets, sstat, sticket);
     if (multisplit) {
       // (3) one stable multi-split of the pair stream by tile, culled records written directly

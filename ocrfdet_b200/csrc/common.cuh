@@ -3,6 +3,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+#include <utility>
+
 #include "ocrf_raster.h"
 
 namespace ocrf {
@@ -57,9 +60,16 @@ __host__ __device__ inline const T* at(const void* base, size_t off) {
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // keys per CTA per pass
+// Small inputs (the (view | depth) sort of the visible Gaussians) are latency bound, not bandwidth bound: a
+// quarter-size tile spreads them over 4x as many CTAs and shortens every CTA's serial load-rank-scatter chain.
+constexpr int SORT_ITEMS_SMALL = 4;
+constexpr uint64_t SORT_SMALL_MAX = 1ull << 20;  // capacity at or below which the small tile is used
+inline uint64_t sort_tile_size(uint64_t n_cap) {
+  return (uint64_t)SORT_THREADS * (n_cap <= SORT_SMALL_MAX ? SORT_ITEMS_SMALL : SORT_ITEMS);
+}
 constexpr int SORT_MAX_PASSES = 8;
 
-inline uint64_t sort_tiles(uint64_t n) { return (n + SORT_TILE - 1) / SORT_TILE; }
+inline uint64_t sort_tiles(uint64_t n) { return (n + sort_tile_size(n) - 1) / sort_tile_size(n); }
 
 struct SortWs {
   size_t hist;    // uint32 [SORT_MAX_PASSES][256]
@@ -146,6 +156,41 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 // make generic-proxy shared-memory writes visible to the async proxy (TMA unit)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- programmatic dependent launch (PDL) for the kernels of the render chain ----
+// The path is a chain of ~15 small dependent kernels; with plain stream order every link pays the full launch
+// latency (~3-4 us) after its predecessor has drained.  Chain kernels are launched with the programmatic stream
+// serialization attribute and begin with pdl_enter(): griddepcontrol.wait (the predecessor grid has completed and
+// its writes are visible) followed by griddepcontrol.launch_dependents (the successor may be scheduled as soon as
+// every CTA of this grid has started).  Nothing touches global memory before pdl_enter(), so the semantics are
+// exactly those of stream order; only the launch latency and the CTA ramp overlap with the predecessor's tail.
+// OCRF_PDL=0 in the environment falls back to plain launches.  A kernel launched without the attribute treats
+// both instructions as no-ops.
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+inline bool pdl_enabled() {
+  static const bool on = !(getenv("OCRF_PDL") != nullptr && atoi(getenv("OCRF_PDL")) == 0);
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr = {};
+  attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr.val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = &attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(std::forward<Args>(args))...);
+}
 
 // ---- decoupled look-back, resolved by one warp (32 predecessors per memory round trip) ----
 // status words: bits 63:62 = 0 not published, 1 = the CTA's own total, 2 = inclusive prefix; bits 61:0 = value.

@@ -17,6 +17,8 @@
 // are bit-identical to what the pair-sort and depth-first paths produce from the same geometry state
 // (tests/test_gpu_parity.py compares them), and `last_state(reference_lists=True)` materialises the
 // reference lists on demand.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace ocrf {
@@ -74,6 +76,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_count_kernel(
     const uint32_t* __restrict__ vis_vals, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
     const float4* __restrict__ conic_opacity, uint32_t* __restrict__ cnt_full, uint32_t* __restrict__ cnt_kept,
     uint2* __restrict__ items) {
+  pdl_enter();
   extern __shared__ uint32_t s_dyn[];  // [2][tiles] counters, then [MS_ROUND/2] packed u16 Gaussian offsets
   __shared__ uint32_t s_jf, s_jl;
   __shared__ uint32_t s_wtot[MS_WARPS];
@@ -182,6 +185,7 @@ __global__ void __launch_bounds__(256) ms_scan_chunks_kernel(OcrfShape sh, int c
                                                              uint32_t* __restrict__ cnt_kept,
                                                              uint32_t* __restrict__ tot_full,
                                                              uint32_t* __restrict__ tot_kept) {
+  pdl_enter();
   const int v = blockIdx.y;
   const int tiles = ceil_div(sh.W, TILE) * ceil_div(sh.H, TILE);
   const int lane = threadIdx.x & 31;
@@ -193,22 +197,32 @@ __global__ void __launch_bounds__(256) ms_scan_chunks_kernel(OcrfShape sh, int c
   uint32_t* cf = cnt_full + (size_t)v * chunks_max * tiles + t;
   uint32_t* ck = cnt_kept + (size_t)v * chunks_max * tiles + t;
   uint32_t rf = 0, rk = 0;
-  for (int c0 = 0; c0 < nchunks; c0 += 32) {
-    const int c = c0 + lane;
-    const uint32_t xf = c < nchunks ? cf[(size_t)c * tiles] : 0u;
-    const uint32_t xk = c < nchunks ? ck[(size_t)c * tiles] : 0u;
-    uint32_t inf = xf, ink = xk;
+  constexpr int BATCH = 8;  // rounds of 32 chunks whose loads are all issued before the first in-place store
+  for (int cb = 0; cb < nchunks; cb += 32 * BATCH) {
+    uint32_t xf[BATCH], xk[BATCH];
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t yf = __shfl_up_sync(0xffffffffu, inf, d), yk = __shfl_up_sync(0xffffffffu, ink, d);
-      if (lane >= d) { inf += yf; ink += yk; }
+    for (int r = 0; r < BATCH; r++) {
+      const int c = cb + r * 32 + lane;
+      xf[r] = c < nchunks ? cf[(size_t)c * tiles] : 0u;
+      xk[r] = c < nchunks ? ck[(size_t)c * tiles] : 0u;
     }
-    if (c < nchunks) {
-      cf[(size_t)c * tiles] = rf + inf - xf;
-      ck[(size_t)c * tiles] = rk + ink - xk;
+#pragma unroll
+    for (int r = 0; r < BATCH; r++) {
+      const int c = cb + r * 32 + lane;
+      if (cb + r * 32 >= nchunks) break;  // warp-uniform
+      uint32_t inf = xf[r], ink = xk[r];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t yf = __shfl_up_sync(0xffffffffu, inf, d), yk = __shfl_up_sync(0xffffffffu, ink, d);
+        if (lane >= d) { inf += yf; ink += yk; }
+      }
+      if (c < nchunks) {
+        cf[(size_t)c * tiles] = rf + inf - xf[r];
+        ck[(size_t)c * tiles] = rk + ink - xk[r];
+      }
+      rf += __shfl_sync(0xffffffffu, inf, 31);
+      rk += __shfl_sync(0xffffffffu, ink, 31);
     }
-    rf += __shfl_sync(0xffffffffu, inf, 31);
-    rk += __shfl_sync(0xffffffffu, ink, 31);
   }
   if (lane == 0) {
     tot_full[(size_t)v * tiles + t] = rf;
@@ -223,8 +237,9 @@ __global__ void __launch_bounds__(1024) ms_scan_tiles_kernel(int n_tiles, const 
                                                              uint32_t* __restrict__ tile_offset,
                                                              uint2* __restrict__ ranges,
                                                              uint2* __restrict__ ranges_render) {
+  pdl_enter();
   __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry;
+  __shared__ uint32_t s_carry, s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if ((uint64_t)header[HDR_NUM_PAIRS] > n_cap) {  // capacity overflow: nothing was binned, render background only
     for (int i = tid; i < n_tiles; i += 1024) {
@@ -235,10 +250,17 @@ __global__ void __launch_bounds__(1024) ms_scan_tiles_kernel(int n_tiles, const 
   }
   if (tid == 0) s_carry = 0;
   __syncthreads();
-  for (int base = 0; base < n_tiles; base += 1024) {
-    const int i = base + tid;
-    const uint32_t x = i < n_tiles ? tot_full[i] : 0u;
-    uint32_t incl = x;
+  constexpr int PER = 8;  // consecutive tiles per thread: one load round trip and one CTA scan per 8192 tiles
+  for (int base = 0; base < n_tiles; base += 1024 * PER) {
+    const int i0 = base + tid * PER;
+    uint32_t x[PER], kept[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      x[k] = i0 + k < n_tiles ? tot_full[i0 + k] : 0u;
+      kept[k] = i0 + k < n_tiles ? tot_kept[i0 + k] : 0u;
+      sum += x[k];
+    }
+    uint32_t incl = sum;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
@@ -246,19 +268,34 @@ __global__ void __launch_bounds__(1024) ms_scan_tiles_kernel(int n_tiles, const 
     }
     if (lane == 31) s_warp[warp] = incl;
     __syncthreads();
-    uint32_t off = s_carry;
-    for (int w = 0; w < warp; w++) off += s_warp[w];
-    if (i < n_tiles) {
-      const uint32_t first = off + incl - x;
-      tile_offset[i] = first;
-      ranges[i] = x ? make_uint2(first, first + x) : make_uint2(0u, 0u);  // empty tiles read (0,0) like the reference
-      ranges_render[i] = make_uint2(first, first + tot_kept[i]);
+    if (warp == 0) {  // scan of the 32 warp totals
+      const uint32_t w = s_warp[lane];
+      uint32_t wi = w;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, wi, d);
+        if (lane >= d) wi += y;
+      }
+      s_warp[lane] = wi - w;
+      if (lane == 31) s_total = wi;
     }
     __syncthreads();
-    if (tid == 1023) s_carry = off + incl;
+    uint32_t run = s_carry + s_warp[warp] + incl - sum;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+      if (i0 + k < n_tiles) {
+        tile_offset[i0 + k] = run;
+        ranges[i0 + k] = x[k] ? make_uint2(run, run + x[k]) : make_uint2(0u, 0u);  // empty tiles read (0,0) like the reference
+        ranges_render[i0 + k] = make_uint2(run, run + kept[k]);
+      }
+      run += x[k];
+    }
+    __syncthreads();
+    if (tid == 0) s_carry += s_total;
     __syncthreads();
   }
 }
+
 
 // (C) stable ranks per tile + direct record writes.  grid (chunks_max, V).
 __global__ void __launch_bounds__(MS_THREADS) ms_scatter_kernel(
@@ -268,6 +305,7 @@ __global__ void __launch_bounds__(MS_THREADS) ms_scatter_kernel(
     const float4* __restrict__ conic_opacity, const float* __restrict__ depths, const float* __restrict__ rgb,
     const float* __restrict__ colors, const uint32_t* __restrict__ cnt_full, const uint32_t* __restrict__ cnt_kept,
     const uint32_t* __restrict__ tile_offset, Record* __restrict__ records) {
+  pdl_enter();
   extern __shared__ uint32_t s_dyn[];  // [2][tiles] running bases (full: relative to the tile list, kept: record slot)
                                        // then [MS_WARPS][2][tiles] u16 per-warp counts / prefixes of the round, [2][tiles] u16 round totals
   const int v = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -407,14 +445,23 @@ int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity,
   }
   if (smem_a > 100 * 1024 || smem_c > 200 * 1024) return OCRF_ECAPACITY;
   const dim3 grid(chunks_max, sh->V);
-  ms_count_kernel<<<grid, MS_THREADS, smem_a, st>>>(*sh, chunks_max, Q, pair_capacity, header, view_start, sorted_offsets,
+#ifdef OCRF_DIAG  // timing experiments only: repeat an idempotent kernel, the stage-time delta is its in-stream cost
+  static const int diag_dup = getenv("OCRF_DUP") ? atoi(getenv("OCRF_DUP")) : 0;
+#define OCRF_DIAG_REP(bit) (((diag_dup >> (bit)) & 1) ? 2 : 1)
+#else
+#define OCRF_DIAG_REP(bit) 1
+#endif
+  for (int rep = 0; rep < OCRF_DIAG_REP(0); rep++)
+  launch_chain(ms_count_kernel, dim3(grid), dim3(MS_THREADS), smem_a, st, *sh, chunks_max, Q, pair_capacity, header, view_start, sorted_offsets,
                                                     vis_vals, radii, xy, conic_opacity, cnt_full, cnt_kept, items);
-  ms_scan_chunks_kernel<<<dim3(ceil_div(tiles_v, 8), sh->V), 256, 0, st>>>(*sh, chunks_max, Q, view_start,
+  launch_chain(ms_scan_chunks_kernel, dim3(ceil_div(tiles_v, 8), sh->V), dim3(256), 0, st, *sh, chunks_max, Q, view_start,
                                                                              sorted_offsets, cnt_full, cnt_kept, tot_full,
                                                                              tot_kept);
-  ms_scan_tiles_kernel<<<1, 1024, 0, st>>>(sh->V * tiles_v, header, pair_capacity, tot_full, tot_kept, tile_offset, ranges,
+  for (int rep = 0; rep < OCRF_DIAG_REP(1); rep++)
+  launch_chain(ms_scan_tiles_kernel, dim3(1), dim3(1024), 0, st, sh->V * tiles_v, header, pair_capacity, tot_full, tot_kept, tile_offset, ranges,
                                            ranges_render);
-  ms_scatter_kernel<<<grid, MS_THREADS, smem_c, st>>>(*sh, chunks_max, Q, pair_capacity, use_sh, sh->C == 3, header,
+  for (int rep = 0; rep < OCRF_DIAG_REP(2); rep++)
+  launch_chain(ms_scatter_kernel, dim3(grid), dim3(MS_THREADS), smem_c, st, *sh, chunks_max, Q, pair_capacity, use_sh, sh->C == 3, header,
                                                       view_start, sorted_offsets, items, xy, conic_opacity, depths, rgb,
                                                       colors, cnt_full, cnt_kept, tile_offset, records);
   cudaError_t e = cudaGetLastError();

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(PRE_THREADS, OCRF_PRE_MINB) preprocess_forward
     float4* __restrict__ conic_opacity, uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ offsets,
     float* __restrict__ rgb, uint8_t* __restrict__ clamped, unsigned long long* __restrict__ scan_status,
     uint64_t* __restrict__ vis_keys, uint32_t* __restrict__ vis_vals, uint32_t* __restrict__ view_start) {
+  pdl_enter();
   __shared__ __align__(16) float s_pos[PRE_THREADS * 3];
   __shared__ __align__(16) float s_scl[PRE_THREADS * 3];
   __shared__ Camera s_cam;
@@ -250,7 +251,7 @@ extern "C" int ocrf_preprocess_forward(void* stream, const OcrfShape* sh, const 
   const int blocks = bpv * sh->V;
   // header and look-back state are adjacent: one memset resets both
   cudaMemsetAsync(at<char>(geom_ws, L.header), 0, L.depths - L.header, st);
-  preprocess_forward_kernel<<<blocks, PRE_THREADS, 0, st>>>(
+  launch_chain(preprocess_forward_kernel, dim3(blocks), dim3(PRE_THREADS), 0, st, 
       *sh, bpv, means3D, scales, rotations, cov3D_precomp, opacities, shs, reinterpret_cast<const Camera*>(cams),
       scale_modifier, prefiltered, radii, at<uint32_t>(geom_ws, L.header), at<float>(geom_ws, L.depths),
       at<float2>(geom_ws, L.xy), at<float4>(geom_ws, L.conic_opacity), at<uint32_t>(geom_ws, L.tiles_touched),

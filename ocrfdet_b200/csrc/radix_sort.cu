@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(SORT_THREADS) sort_histogram_kernel(const uint
                                                                       const uint32_t* __restrict__ n_dev,
                                                                       uint64_t n_cap, int passes, int begin_bit,
                                                                       int end_bit, uint32_t* __restrict__ hist) {
+  pdl_enter();
   __shared__ uint32_t s_hist[SORT_MAX_PASSES * 256];
   const uint32_t n = effective_n(n_dev, n_cap);
   for (int i = threadIdx.x; i < passes * 256; i += SORT_THREADS) s_hist[i] = 0;
@@ -72,15 +73,18 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan_256(uint32_t v, uint32_t*
   return off + incl - v;
 }
 
-__global__ void __launch_bounds__(SORT_THREADS, 3) sort_onesweep_kernel(
+template <int ITEMS>
+__global__ void __launch_bounds__(SORT_THREADS, ITEMS >= 16 ? 3 : 4) sort_onesweep_kernel(
     const uint64_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint64_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ n_dev, uint64_t n_cap, int shift, int bits,
     const uint32_t* __restrict__ hist /*[256] this pass*/, uint32_t* __restrict__ status /*[tiles][256] this pass*/,
     uint32_t* __restrict__ ticket) {
+  pdl_enter();
+  constexpr int TILE_N = SORT_THREADS * ITEMS;  // keys per CTA
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);                                // [SORT_TILE]
-  uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw + SORT_TILE * 8);                // [SORT_TILE]
-  uint32_t* s_warp_hist = reinterpret_cast<uint32_t*>(smem_raw + SORT_TILE * 12);          // [SORT_WARPS][256]
+  uint64_t* s_keys = reinterpret_cast<uint64_t*>(smem_raw);                                // [TILE_N]
+  uint32_t* s_vals = reinterpret_cast<uint32_t*>(smem_raw + TILE_N * 8);                // [TILE_N]
+  uint32_t* s_warp_hist = reinterpret_cast<uint32_t*>(smem_raw + TILE_N * 12);          // [SORT_WARPS][256]
   uint32_t* s_tile_excl = s_warp_hist + SORT_WARPS * 256;                                   // [256]
   uint32_t* s_digit_base = s_tile_excl + 256;                                               // [256]
   uint32_t* s_scan = s_digit_base + 256;                                                    // [8]
@@ -92,16 +96,16 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) sort_onesweep_kernel(
   for (int i = tid; i < SORT_WARPS * 256; i += SORT_THREADS) s_warp_hist[i] = 0;
   __syncthreads();
   const uint32_t tile = s_tile_id;
-  const uint64_t base = (uint64_t)tile * SORT_TILE;
+  const uint64_t base = (uint64_t)tile * TILE_N;
   if (base >= n) return;
-  const uint32_t n_valid = (uint32_t)min((uint64_t)SORT_TILE, (uint64_t)n - base);
+  const uint32_t n_valid = (uint32_t)min((uint64_t)TILE_N, (uint64_t)n - base);
   const uint32_t digit_mask = (1u << bits) - 1;
 
   // ---- load (warp-striped: item i of lane l sits at warp_base + i*32 + l, i.e. index order) ----
-  uint64_t key[SORT_ITEMS];
-  const uint32_t warp_base = warp * (32 * SORT_ITEMS);
+  uint64_t key[ITEMS];
+  const uint32_t warp_base = warp * (32 * ITEMS);
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++) {
+  for (int i = 0; i < ITEMS; i++) {
     const uint32_t loc = warp_base + i * 32 + lane;
     key[i] = loc < n_valid ? keys_in[base + loc] : ~0ull;  // padding ranks behind every valid key of the (last) tile
   }
@@ -111,18 +115,18 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) sort_onesweep_kernel(
   s_tile_excl[tid] = 0;  // reused as the counting histogram until the scan below
   __syncthreads();
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++) atomicAdd(&s_tile_excl[(uint32_t)(key[i] >> shift) & digit_mask], 1u);
+  for (int i = 0; i < ITEMS; i++) atomicAdd(&s_tile_excl[(uint32_t)(key[i] >> shift) & digit_mask], 1u);
   __syncthreads();
   const uint32_t tile_count = s_tile_excl[tid];
   uint32_t* my_status = status + (size_t)tile * 256 + tid;
   atomicExch(my_status, (tile == 0 ? LB_FLAG_INCL : LB_FLAG_LOCAL) | tile_count);
 
   // ---- rank inside the warp: match_any multi-split, one item row at a time (stable) ----
-  uint32_t rank[SORT_ITEMS];
+  uint32_t rank[ITEMS];
   uint32_t* my_hist = s_warp_hist + warp * 256;
   const uint32_t lt_mask = (1u << lane) - 1;
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++) {
+  for (int i = 0; i < ITEMS; i++) {
     const uint32_t d = (uint32_t)(key[i] >> shift) & digit_mask;
     const uint32_t peers = __match_any_sync(0xffffffffu, d);
     const uint32_t before = my_hist[d];
@@ -163,7 +167,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) sort_onesweep_kernel(
 
   // ---- reorder through shared memory, then write runs ----
 #pragma unroll
-  for (int i = 0; i < SORT_ITEMS; i++) {
+  for (int i = 0; i < ITEMS; i++) {
     const uint32_t d = (uint32_t)(key[i] >> shift) & digit_mask;
     const uint32_t pos = s_tile_excl[d] + s_warp_hist[warp * 256 + d] + rank[i];
     s_keys[pos] = key[i];
@@ -180,7 +184,24 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) sort_onesweep_kernel(
   }
 }
 
-constexpr size_t SORT_SMEM_BYTES = SORT_TILE * 12 + (SORT_WARPS * 256 + 256 + 256 + 8) * 4;
+template <int ITEMS>
+constexpr size_t sort_smem_bytes() { return (size_t)SORT_THREADS * ITEMS * 12 + (SORT_WARPS * 256 + 256 + 256 + 8) * 4; }
+
+template <int ITEMS>
+static int launch_onesweep(cudaStream_t st, unsigned tiles, const uint64_t* kin, const uint32_t* vin, uint64_t* kout,
+                           uint32_t* vout, const uint32_t* n_dev, uint64_t n_cap, int shift, int bits,
+                           const uint32_t* hist, uint32_t* status, uint32_t* ticket) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(sort_onesweep_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)sort_smem_bytes<ITEMS>());
+    if (e != cudaSuccess) return (int)e;
+    attr_set = true;
+  }
+  launch_chain(sort_onesweep_kernel<ITEMS>, dim3(tiles), dim3(SORT_THREADS), sort_smem_bytes<ITEMS>(), st, kin, vin, kout, vout, n_dev, n_cap, shift,
+                                                                                    bits, hist, status, ticket);
+  return 0;
+}
 
 // Sorts n_cap-bounded pairs; data starts in (keys_a, vals_a) and the result lands in (keys_b, vals_b)
 // when `passes` is odd, in (keys_a, vals_a) when it is even -- callers pick a/b accordingly.
@@ -189,19 +210,13 @@ int sort_pairs_device(cudaStream_t st, const uint32_t* n_dev, uint64_t n_cap, in
   if (begin_bit < 0 || end_bit <= begin_bit || end_bit > 64) return OCRF_EINVAL;
   const int passes = (end_bit - begin_bit + 7) / 8;
   if (n_cap == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sort_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)SORT_SMEM_BYTES);
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
+  const bool small = n_cap <= SORT_SMALL_MAX;
   const SortWs L = sort_ws_layout(n_cap);
   const uint64_t tiles = sort_tiles(n_cap);
   cudaMemsetAsync(ws, 0, L.status + (size_t)passes * (tiles + 1) * 256 * 4, st);
   uint32_t* hist = at<uint32_t>(ws, L.hist);
   const int hgrid = (int)min((uint64_t)NUM_SMS * 8, (n_cap + SORT_THREADS * 4 - 1) / (SORT_THREADS * 4));
-  sort_histogram_kernel<<<hgrid, SORT_THREADS, 0, st>>>(keys_a, n_dev, n_cap, passes, begin_bit, end_bit, hist);
+  launch_chain(sort_histogram_kernel, dim3(hgrid), dim3(SORT_THREADS), 0, st, keys_a, n_dev, n_cap, passes, begin_bit, end_bit, hist);
   uint64_t* kin = keys_a;
   uint32_t* vin = vals_a;
   uint64_t* kout = keys_b;
@@ -209,9 +224,12 @@ int sort_pairs_device(cudaStream_t st, const uint32_t* n_dev, uint64_t n_cap, in
   for (int p = 0; p < passes; p++) {
     const int shift = begin_bit + p * 8;
     const int bits = end_bit - shift < 8 ? end_bit - shift : 8;
-    sort_onesweep_kernel<<<(unsigned)tiles, SORT_THREADS, SORT_SMEM_BYTES, st>>>(
-        kin, vin, kout, vout, n_dev, n_cap, shift, bits, hist + p * 256,
-        at<uint32_t>(ws, L.status) + (size_t)p * (tiles + 1) * 256, at<uint32_t>(ws, L.ticket) + p);
+    uint32_t* status = at<uint32_t>(ws, L.status) + (size_t)p * (tiles + 1) * 256;
+    const int rc = small ? launch_onesweep<SORT_ITEMS_SMALL>(st, (unsigned)tiles, kin, vin, kout, vout, n_dev, n_cap, shift,
+                                                             bits, hist + p * 256, status, at<uint32_t>(ws, L.ticket) + p)
+                         : launch_onesweep<SORT_ITEMS>(st, (unsigned)tiles, kin, vin, kout, vout, n_dev, n_cap, shift, bits,
+                                                       hist + p * 256, status, at<uint32_t>(ws, L.ticket) + p);
+    if (rc != 0) return rc;
     uint64_t* tk = kin; kin = kout; kout = tk;
     uint32_t* tv = vin; vin = vout; vout = tv;
   }

@@ -59,6 +59,7 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
     const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ max_contrib,
     const float* __restrict__ dL_dpix, const float* __restrict__ dL_dopa, double* __restrict__ ggrad,
     float* __restrict__ dL_dcolors) {
+  pdl_enter();
   constexpr int NT = TILE_PIX / PPT;
   constexpr int NW = NT / 32;
   constexpr int BWD_BATCH = BwdBatch<PPT>::value;
@@ -464,15 +465,15 @@ extern "C" int ocrf_render_backward(void* stream, const OcrfShape* sh, uint64_t 
     static const int ppt = env_int_b("OCRF_BWD_PPT", 4);
     const Record* rec = at<Record>(bin_ws, B.records);
     if (ppt == 4)
-      render_backward_c3_kernel<4><<<grid, TILE_PIX / 4, 0, st>>>(sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
+      launch_chain(render_backward_c3_kernel<4>, dim3(grid), dim3(TILE_PIX / 4), 0, st, sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
                                                                   ranges, rec, bg, fT, nc, mc, dL_dcolor,
                                                                   dL_dopacity_map, ggrad, dL_dcolors);
     else if (ppt == 2)
-      render_backward_c3_kernel<2><<<grid, TILE_PIX / 2, 0, st>>>(sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
+      launch_chain(render_backward_c3_kernel<2>, dim3(grid), dim3(TILE_PIX / 2), 0, st, sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
                                                                   ranges, rec, bg, fT, nc, mc, dL_dcolor,
                                                                   dL_dopacity_map, ggrad, dL_dcolors);
     else
-      render_backward_c3_kernel<1><<<grid, TILE_PIX, 0, st>>>(sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
+      launch_chain(render_backward_c3_kernel<1>, dim3(grid), dim3(TILE_PIX), 0, st, sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
                                                               ranges, rec, bg, fT, nc, mc, dL_dcolor, dL_dopacity_map,
                                                               ggrad, dL_dcolors);
   } else {

@@ -34,6 +34,7 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_forward_c3_kernel(
     const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
     uint32_t* __restrict__ max_contrib, float* __restrict__ out_color, float* __restrict__ out_depth,
     float* __restrict__ out_opacity) {
+  pdl_enter();
   constexpr int NT = TILE_PIX / PPT;
   __shared__ __align__(128) Record s_rec[2][FWD_BATCH];
   __shared__ __align__(8) uint64_t s_bar[2];
@@ -306,13 +307,13 @@ extern "C" int ocrf_render_forward(void* stream, const OcrfShape* sh, uint64_t p
     static const int ppt = env_int("OCRF_FWD_PPT", 2);
     const Record* rec = at<Record>(bin_ws, B.records);
     if (ppt == 4)
-      render_forward_c3_kernel<4><<<grid, TILE_PIX / 4, 0, st>>>(sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
+      launch_chain(render_forward_c3_kernel<4>, dim3(grid), dim3(TILE_PIX / 4), 0, st, sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
                                                                  out_depth, out_opacity);
     else if (ppt == 2)
-      render_forward_c3_kernel<2><<<grid, TILE_PIX / 2, 0, st>>>(sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
+      launch_chain(render_forward_c3_kernel<2>, dim3(grid), dim3(TILE_PIX / 2), 0, st, sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
                                                                  out_depth, out_opacity);
     else
-      render_forward_c3_kernel<1><<<grid, TILE_PIX, 0, st>>>(sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
+      launch_chain(render_forward_c3_kernel<1>, dim3(grid), dim3(TILE_PIX), 0, st, sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
                                                              out_depth, out_opacity);
   } else {
     (void)use_sh;

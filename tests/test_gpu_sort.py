@@ -29,7 +29,7 @@ def _expect(keys, vals, end_bit):
     return keys[order], vals[order]
 
 
-@pytest.mark.parametrize("n", [1, 2, 31, 4095, 4096, 4097, 50_000, 1_000_003])
+@pytest.mark.parametrize("n", [1, 2, 31, 1023, 1025, 4095, 4096, 4097, 50_000, 1_000_003, 1_048_576, 1_048_577, 2_100_000])
 @pytest.mark.parametrize("end_bit", [42, 44, 48, 64, 13])
 def test_sort_pairs_matches_stable_numpy(n, end_bit):
     rng = np.random.default_rng(n * 131 + end_bit)
