@@ -162,17 +162,18 @@ def run_ours(args, rank, world, device):
     binning = os.environ.get("OCRF_BINNING", "split")
     vis_passes = (32 + max(VIEWS - 1, 0).bit_length() + 7) // 8
     if binning == "pairsort":
-        # preprocess, duplicate, histogram, `passes` onesweep passes, cull/pack, blend fwd, blend bwd, preprocess bwd
-        launches_per_step = 7 + passes
+        # preprocess, duplicate, histogram, `passes` onesweep passes, cull/pack, blend fwd, clear grads, blend bwd,
+        # preprocess bwd
+        launches_per_step = 8 + passes
     elif binning == "depthfirst":
         # preprocess | histogram + passes over (view|depth) of the visible Gaussians | scan + duplicate in depth
-        # order | histogram + passes over the tile bits | cull/pack | fwd | bwd | preprocess bwd
+        # order | histogram + passes over the tile bits | cull/pack | fwd | clear grads | bwd | preprocess bwd
         tile_passes = (end_bit - 32 + 7) // 8
-        launches_per_step = 1 + (1 + vis_passes) + 2 + (1 + tile_passes) + 1 + 3
+        launches_per_step = 1 + (1 + vis_passes) + 2 + (1 + tile_passes) + 1 + 4
     else:
         # default multi-split: preprocess | histogram + passes over (view|depth) | scan | count, scan chunks,
-        # scan tiles, scatter | fwd | bwd | preprocess bwd
-        launches_per_step = 1 + (1 + vis_passes) + 1 + 4 + 3
+        # scan tiles, scatter | fwd | clear grads | bwd | preprocess bwd
+        launches_per_step = 1 + (1 + vis_passes) + 1 + 4 + 4
 
     # ---- device-resident throughput ----
     if world > 1:

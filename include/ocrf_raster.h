@@ -148,11 +148,19 @@ int ocrf_render_forward(void* stream, const OcrfShape* shape, uint64_t pair_capa
 
 /* Stage 4 (backward.cu:399-557).  dL_dcolor [V,C,H,W]; dL_dopacity_map [V,1,H,W] or NULL.
  * Accumulates into ggrad [V,P,OCRF_GGRAD_STRIDE] and dL_dcolors [S,P,C] (or [V,P,3] when use_sh);
- * both must be zeroed by the caller (as torch::zeros in rasterize_points.cu:151-159). */
+ * both must be zeroed by the caller (as torch::zeros in rasterize_points.cu:151-159), or prepared with
+ * ocrf_clear_gradients. */
 int ocrf_render_backward(void* stream, const OcrfShape* shape, uint64_t pair_capacity, const float* colors,
                          int use_sh, const float* bg, const void* geom_ws, const void* bin_ws,
                          const void* image_ws, const float* dL_dcolor, const float* dL_dopacity_map,
                          double* ggrad, float* dL_dcolors);
+
+/* Clears the accumulators of ocrf_render_backward in one launch: the ggrad rows of visible (radii > 0) pairs --
+ * rows of invisible pairs are neither read nor written by the two backward stages -- and all of dL_dcolors
+ * ([S,P,C], or [V,P,3] when use_sh).  Equivalent to zero-filling both buffers (rasterize_points.cu:151-159).
+ * Both pointers 16-byte aligned. */
+int ocrf_clear_gradients(void* stream, const OcrfShape* shape, int use_sh, const int32_t* radii, double* ggrad,
+                         float* dL_dcolors);
 
 /* backward.cu:144-396: screen-space gradients -> dL_dmeans3D [S,P,3], dL_dmeans2D [V,P,3],
  * dL_dopacities [S,P], dL_dscales [S,P,3] + dL_drotations [S,P,4] (or dL_dcov3D [S,P,6] when

@@ -23,7 +23,7 @@ EXPORTS = [
     "ocrf_sort_end_bit", "ocrf_preprocess_forward", "ocrf_bin_forward", "ocrf_render_forward",
     "ocrf_render_backward", "ocrf_preprocess_backward", "ocrf_mark_visible", "ocrf_sort_workspace_bytes",
     "ocrf_sort_pairs", "ocrf_opacity_mask_forward", "ocrf_opacity_mask_backward",
-    "ocrf_gaussian_heads_forward", "ocrf_gaussian_heads_backward",
+    "ocrf_gaussian_heads_forward", "ocrf_gaussian_heads_backward", "ocrf_clear_gradients",
 ]
 
 
@@ -86,6 +86,7 @@ def lib():
     L.ocrf_sort_pairs.argtypes = [vp, u64, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.ocrf_opacity_mask_forward.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.ocrf_opacity_mask_backward.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ocrf_clear_gradients.argtypes = [vp, shp, C.c_int, vp, vp, vp]
     L.ocrf_gaussian_heads_forward.argtypes = [vp, C.c_int64, i32] + [vp] * 11
     L.ocrf_gaussian_heads_backward.argtypes = [vp, C.c_int64, i32] + [vp] * 15
     if L.ocrf_abi_version() != ABI_VERSION:

@@ -414,19 +414,17 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
     uint32_t* va = at<uint32_t>(geom_ws, (vpasses & 1) ? G.vis_vals_tmp : G.vis_vals);
     uint64_t* kb = at<uint64_t>(geom_ws, (vpasses & 1) ? G.vis_keys : G.vis_keys_tmp);
     uint32_t* vb = at<uint32_t>(geom_ws, (vpasses & 1) ? G.vis_vals : G.vis_vals_tmp);
-    rc = sort_pairs_device(st, header + HDR_NUM_VIS, n, 0, vbit, ka, va, kb, vb, at<char>(geom_ws, G.vis_sort_ws));
-    if (rc) return rc;
-#ifdef OCRF_DIAG  // timing experiment: the sort a second time (same result up to exact ties)
-    if (getenv("OCRF_DUP") && (atoi(getenv("OCRF_DUP")) & 8))
-      sort_pairs_device(st, header + HDR_NUM_VIS, n, 0, vbit, ka, va, kb, vb, at<char>(geom_ws, G.vis_sort_ws));
-#endif
-    // (2) inclusive scan of tiles_touched in depth order: where every Gaussian's pairs sit in the pair stream
-    const uint32_t* vvals = at<uint32_t>(geom_ws, G.vis_vals);
-    uint32_t* sorted_offsets = at<uint32_t>(bin_ws, B.split_counts);
+    // The sort workspace was zeroed together with the geom header (ocrf_preprocess_forward); the look-back state of
+    // the scan below is cleared by the sort's histogram kernel: no memset node between preprocess and the blend.
     unsigned long long* sstat = at<unsigned long long>(bin_ws, B.split_tiles);
     const size_t sblocks = (n + 1023) / 1024;
     uint32_t* sticket = reinterpret_cast<uint32_t*>(sstat + sblocks + 1);
-    cudaMemsetAsync(sstat, 0, (sblocks + 1) * 8 + 64, st);
+    rc = sort_pairs_device(st, header + HDR_NUM_VIS, n, 0, vbit, ka, va, kb, vb, at<char>(geom_ws, G.vis_sort_ws), true,
+                           reinterpret_cast<uint32_t*>(sstat), (uint32_t)(((sblocks + 1) * 8 + 64) / 4));
+    if (rc) return rc;
+    // (2) inclusive scan of tiles_touched in depth order: where every Gaussian's pairs sit in the pair stream
+    const uint32_t* vvals = at<uint32_t>(geom_ws, G.vis_vals);
+    uint32_t* sorted_offsets = at<uint32_t>(bin_ws, B.split_counts);
     launch_chain(scan_sorted_tiles_kernel, dim3((unsigned)sblocks), dim3(256), 0, st, header, vvals, at<uint32_t>(geom_ws, G.tiles_touched),
                                                                 sorted_offsets, sstat, sticket);
     if (multisplit) {

@@ -60,10 +60,10 @@ __host__ __device__ inline const T* at(const void* base, size_t off) {
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_ITEMS = 16;
 constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS;  // keys per CTA per pass
-// Small inputs (the (view | depth) sort of the visible Gaussians) are latency bound, not bandwidth bound: a
-// quarter-size tile spreads them over 4x as many CTAs and shortens every CTA's serial load-rank-scatter chain.
+// Optional quarter-size tile for small inputs.  Measured on the (view | depth) sort of ~114k visible Gaussians:
+// no gain, a pass is bound by its fixed chain of L2 round trips (ticket, keys, look-back), not by per-CTA work.
 constexpr int SORT_ITEMS_SMALL = 4;
-constexpr uint64_t SORT_SMALL_MAX = 1ull << 20;  // capacity at or below which the small tile is used
+constexpr uint64_t SORT_SMALL_MAX = 0;  // capacity at or below which the small tile is used (measured: no gain -> off)
 inline uint64_t sort_tile_size(uint64_t n_cap) {
   return (uint64_t)SORT_THREADS * (n_cap <= SORT_SMALL_MAX ? SORT_ITEMS_SMALL : SORT_ITEMS);
 }
@@ -89,8 +89,12 @@ inline SortWs sort_ws_layout(uint64_t n) {
 // radix_sort.cu: stable sort on key bits [begin_bit, end_bit).  Data starts in (keys_a, vals_a); result in
 // (keys_b, vals_b) when the pass count ceil((end_bit-begin_bit)/8) is odd, back in (keys_a, vals_a) when even.
 // n is read from *n_dev (<= n_cap).
+// ws_zeroed: the caller has already zeroed the workspace (it sits inside a larger memset);
+// zero_extra/zero_words: a small region the histogram kernel clears on the side (saves a memset node between
+// two chain kernels).
 int sort_pairs_device(cudaStream_t st, const uint32_t* n_dev, uint64_t n_cap, int begin_bit, int end_bit,
-                      uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, void* ws);
+                      uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, void* ws,
+                      bool ws_zeroed = false, uint32_t* zero_extra = nullptr, uint32_t zero_words = 0);
 
 // ---- preprocess geometry ----
 constexpr int PRE_THREADS = 256;

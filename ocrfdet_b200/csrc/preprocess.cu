@@ -216,6 +216,7 @@ extern "C" int ocrf_geom_layout(const OcrfShape* sh, int use_sh, OcrfGeomLayout*
   size_t off = 0;
   out->header = off;        off = align128(off + 32 * 4);
   out->scan_status = off;   off = align128(off + blocks * 8);
+  out->vis_sort_ws = off;   off = align128(off + sort_ws_layout(n ? n : 1).total + 128);  // zeroed with the two above
   out->depths = off;        off = align128(off + n * 4);
   out->xy = off;            off = align128(off + n * 8);
   out->conic_opacity = off; off = align128(off + n * 16);
@@ -228,7 +229,6 @@ extern "C" int ocrf_geom_layout(const OcrfShape* sh, int use_sh, OcrfGeomLayout*
   out->vis_vals = off;      off = align128(off + n * 4);
   out->vis_vals_tmp = off;  off = align128(off + n * 4);
   out->view_start = off;    off = align128(off + ((size_t)sh->V + 1) * 4);
-  out->vis_sort_ws = off;   off = align128(off + sort_ws_layout(n ? n : 1).total + 128);
   out->total = off + 128;
   return 0;
 }

@@ -33,10 +33,13 @@ __device__ __forceinline__ uint32_t effective_n(const uint32_t* n_dev, uint64_t 
 __global__ void __launch_bounds__(SORT_THREADS) sort_histogram_kernel(const uint64_t* __restrict__ keys,
                                                                       const uint32_t* __restrict__ n_dev,
                                                                       uint64_t n_cap, int passes, int begin_bit,
-                                                                      int end_bit, uint32_t* __restrict__ hist) {
+                                                                      int end_bit, uint32_t* __restrict__ hist,
+                                                                      uint32_t* __restrict__ zero_extra,
+                                                                      uint32_t zero_words) {
   pdl_enter();
   __shared__ uint32_t s_hist[SORT_MAX_PASSES * 256];
   const uint32_t n = effective_n(n_dev, n_cap);
+  for (uint32_t i = blockIdx.x * SORT_THREADS + threadIdx.x; i < zero_words; i += gridDim.x * SORT_THREADS) zero_extra[i] = 0u;
   for (int i = threadIdx.x; i < passes * 256; i += SORT_THREADS) s_hist[i] = 0;
   __syncthreads();
   for (uint64_t i = (uint64_t)blockIdx.x * SORT_THREADS + threadIdx.x; i < n; i += (uint64_t)gridDim.x * SORT_THREADS) {
@@ -206,17 +209,19 @@ static int launch_onesweep(cudaStream_t st, unsigned tiles, const uint64_t* kin,
 // Sorts n_cap-bounded pairs; data starts in (keys_a, vals_a) and the result lands in (keys_b, vals_b)
 // when `passes` is odd, in (keys_a, vals_a) when it is even -- callers pick a/b accordingly.
 int sort_pairs_device(cudaStream_t st, const uint32_t* n_dev, uint64_t n_cap, int begin_bit, int end_bit,
-                      uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, void* ws) {
+                      uint64_t* keys_a, uint32_t* vals_a, uint64_t* keys_b, uint32_t* vals_b, void* ws, bool ws_zeroed,
+                      uint32_t* zero_extra, uint32_t zero_words) {
   if (begin_bit < 0 || end_bit <= begin_bit || end_bit > 64) return OCRF_EINVAL;
   const int passes = (end_bit - begin_bit + 7) / 8;
   if (n_cap == 0) return 0;
   const bool small = n_cap <= SORT_SMALL_MAX;
   const SortWs L = sort_ws_layout(n_cap);
   const uint64_t tiles = sort_tiles(n_cap);
-  cudaMemsetAsync(ws, 0, L.status + (size_t)passes * (tiles + 1) * 256 * 4, st);
+  if (!ws_zeroed) cudaMemsetAsync(ws, 0, L.status + (size_t)passes * (tiles + 1) * 256 * 4, st);
   uint32_t* hist = at<uint32_t>(ws, L.hist);
   const int hgrid = (int)min((uint64_t)NUM_SMS * 8, (n_cap + SORT_THREADS * 4 - 1) / (SORT_THREADS * 4));
-  launch_chain(sort_histogram_kernel, dim3(hgrid), dim3(SORT_THREADS), 0, st, keys_a, n_dev, n_cap, passes, begin_bit, end_bit, hist);
+  launch_chain(sort_histogram_kernel, dim3(hgrid), dim3(SORT_THREADS), 0, st, keys_a, n_dev, n_cap, passes, begin_bit, end_bit, hist,
+               zero_extra, zero_words);
   uint64_t* kin = keys_a;
   uint32_t* vin = vals_a;
   uint64_t* kout = keys_b;

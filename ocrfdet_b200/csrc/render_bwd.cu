@@ -435,6 +435,28 @@ static int launch_backward_generic(cudaStream_t st, dim3 grid, const OcrfShape* 
   return 0;
 }
 
+// Zeroes what ocrf_render_backward accumulates into: every ggrad row of a visible (view, Gaussian) pair -- rows of
+// invisible pairs are never read or written downstream, so the 48-byte rows of ~80 % of the pairs are skipped --
+// and the whole colour-gradient buffer.  Replaces the two torch::zeros of rasterize_points.cu:151-159 on this path.
+__global__ void __launch_bounds__(256) clear_gradients_kernel(size_t n_pairs, const int32_t* __restrict__ radii,
+                                                              double* __restrict__ ggrad, size_t n_color_vec4,
+                                                              size_t n_color, float* __restrict__ dL_dcolors) {
+  pdl_enter();
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t o = t0; o < n_pairs; o += stride) {
+    if (__ldg(radii + o) > 0) {
+      double2* row = reinterpret_cast<double2*>(ggrad + o * OCRF_GGRAD_STRIDE);
+      row[0] = make_double2(0., 0.);
+      row[1] = make_double2(0., 0.);
+      row[2] = make_double2(0., 0.);
+    }
+  }
+  float4* c4 = reinterpret_cast<float4*>(dL_dcolors);
+  for (size_t i = t0; i < n_color_vec4; i += stride) c4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (size_t i = n_color_vec4 * 4 + t0; i < n_color; i += stride) dL_dcolors[i] = 0.f;
+}
+
 }  // namespace ocrf
 
 using namespace ocrf;
@@ -493,6 +515,21 @@ extern "C" int ocrf_render_backward(void* stream, const OcrfShape* sh, uint64_t 
 #undef OCRF_BWDG
     if (rc2) return rc2;
   }
+  OCRF_CHECK_LAST();
+  return 0;
+}
+
+extern "C" int ocrf_clear_gradients(void* stream, const OcrfShape* sh, int use_sh, const int32_t* radii, double* ggrad,
+                                    float* dL_dcolors) {
+  if (!sh || !radii || !ggrad || !dL_dcolors) return OCRF_EINVAL;
+  if ((reinterpret_cast<uintptr_t>(ggrad) & 15) || (reinterpret_cast<uintptr_t>(dL_dcolors) & 15)) return OCRF_EINVAL;
+  const size_t n_pairs = (size_t)sh->V * sh->P;
+  const size_t n_color = use_sh ? n_pairs * 3 : (size_t)sh->S * sh->P * sh->C;
+  if (n_pairs == 0) return 0;
+  const size_t want = (n_pairs + 255) / 256;
+  const unsigned grid = (unsigned)(want < (size_t)NUM_SMS * 8 ? want : (size_t)NUM_SMS * 8);
+  launch_chain(clear_gradients_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), n_pairs, radii, ggrad,
+               n_color / 4, n_color, dL_dcolors);
   OCRF_CHECK_LAST();
   return 0;
 }

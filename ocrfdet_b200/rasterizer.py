@@ -176,8 +176,10 @@ class _RasterizeBatch(torch.autograd.Function):
             g_color = torch.zeros((V, Cc, shape.H, shape.W), dtype=torch.float32, device=dev)
         g_color = g_color.contiguous()
         g_opac = g_opac.contiguous() if g_opac is not None else None
-        ggrad = torch.zeros((V, P, _lib.OCRF_GGRAD_STRIDE), dtype=torch.float64, device=dev)
-        g_feat = torch.zeros((V, P, 3) if use_sh else (S, P, Cc), dtype=torch.float32, device=dev)
+        ggrad = torch.empty((V, P, _lib.OCRF_GGRAD_STRIDE), dtype=torch.float64, device=dev)
+        g_feat = torch.empty((V, P, 3) if use_sh else (S, P, Cc), dtype=torch.float32, device=dev)
+        check(L.ocrf_clear_gradients(stream, C.byref(shape), int(use_sh), ptr(radii), ptr(ggrad), ptr(g_feat)),
+              "ocrf_clear_gradients")
         check(L.ocrf_render_backward(stream, C.byref(shape), C.c_uint64(ctx.capacity), ptr(colors), int(use_sh),
                                      ptr(bg), ptr(geom), ptr(binning), ptr(image), ptr(g_color), ptr(g_opac),
                                      ptr(ggrad), ptr(g_feat)), "ocrf_render_backward")
