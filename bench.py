@@ -23,7 +23,6 @@ Contract (see DESIGN.md "Measurement"):
 import argparse
 import json
 import os
-import subprocess
 import sys
 import threading
 import time
@@ -52,44 +51,71 @@ def parse():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    """SM clock and clock-event (throttle) reasons sampled DURING the timed region, in-process through NVML
+    (every 2 ms from a helper thread; a `nvidia-smi -lms` child takes longer to start than the timed region lasts)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown", "nvmlClocksThrottleReasonHwSlowdown"),
+               ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown", "nvmlClocksThrottleReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown", "nvmlClocksThrottleReasonSwThermalSlowdown"),
+               ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap", "nvmlClocksThrottleReasonSwPowerCap"))
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.sm, self.bits, self.err = index, [], 0, None
+        self.run, self.thread, self.nv, self.h, self.max_mhz = False, None, None, None, None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            try:  # the CUDA ordinal is not the NVML index under CUDA_VISIBLE_DEVICES: match by UUID
+                uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+                self.h = nv.nvmlDeviceGetHandleByUUID(uuid)
+            except Exception:  # noqa: BLE001
+                vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                ids = [v.strip() for v in vis.split(",")] if vis else []
+                phys = int(ids[self.index]) if self.index < len(ids) and ids[self.index].isdigit() else self.index
+                self.h = nv.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self._sample()
+            self.run = True
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception as e:  # noqa: BLE001
+            self.err = "nvml unavailable: %s" % e
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        self.bits |= int(get(self.h))
 
     def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+        while self.run:
+            try:
+                self._sample()
+            except Exception as e:  # noqa: BLE001
+                self.err = str(e)
+                return
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
-        reasons = set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for n, val in zip(names, r[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(n)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        if self.nv is None or self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "nvml unavailable"], "samples": 0}
+        self.run = False
+        if self.thread is not None:
+            self.thread.join(timeout=1.0)
+        try:
+            self._sample()
+        except Exception:  # noqa: BLE001
+            pass
+        reasons = []
+        for name, new_attr, old_attr in self.REASONS:
+            mask = getattr(self.nv, new_attr, None) or getattr(self.nv, old_attr, 0)
+            if self.bits & int(mask):
+                reasons.append(name)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.max_mhz,
+                "reasons": reasons, "samples": len(self.sm)}
 
 
 def make_inputs(rank, device):

@@ -183,6 +183,156 @@ __global__ void __launch_bounds__(GH_THREADS) gaussian_heads_forward_kernel(
   }
 }
 
+// ---- forward, fast path (F % 4 == 0, 16-byte aligned features): k-sliced cp.async ring ----------------------
+// A 128-row tile is consumed in slices of 16 feature columns.  One slice of a tile is 128 x 64 B = 8 KB (10 KB with the
+// conflict-free 20-float row pitch), so a 3-deep ring costs 30 KB instead of the 43 KB a whole tile needs: six CTAs
+// (12 warps) fit per SM, every CTA prefetches two slices ahead, and HBM latency is hidden inside the CTA instead of
+// by neighbours that all stall at the same moment.  Each thread copies eight 16-byte chunks per slice (LDGSTS,
+// fully coalesced: a slice row is two 32-byte sectors) and keeps two rows' 16 hidden units in registers across the
+// slices of a tile.
+constexpr int GH_KS = 16;                 // feature columns per slice
+constexpr int GH_SS = GH_KS + 4;          // slice row pitch in floats (5 float4: odd -> LDS.128 conflict-free)
+constexpr int GH_STAGES = 3;
+constexpr int GH_STAGE_FLOATS = GH_ROWS * GH_SS;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__global__ void __launch_bounds__(GH_THREADS) gaussian_heads_forward_sliced_kernel(
+    long long n, int F, const float* __restrict__ feat, const float* __restrict__ rgb, const float* __restrict__ w1t,
+    const float* __restrict__ b1, const float* __restrict__ w2, const float* __restrict__ b2,
+    float* __restrict__ opacity, float* __restrict__ scales, float* __restrict__ rotations, float* __restrict__ colors,
+    float* __restrict__ hidden) {
+  extern __shared__ __align__(128) float s_mem[];
+  const int K = F + 3;
+  const int NS = (F + GH_KS - 1) / GH_KS;   // slices per tile
+  float* s_stage = s_mem;                                   // [GH_STAGES][GH_ROWS][GH_SS]
+  float* s_w1 = s_stage + GH_STAGES * GH_STAGE_FLOATS;      // [max(K, NS*16)][16], rows >= K zero
+  const int w_rows = max(K, NS * GH_KS);
+  float* s_b1 = s_w1 + w_rows * GH_HID;                     // [16]
+  float* s_w2 = s_b1 + GH_HID;                              // [11][4]
+  float* s_b2 = s_w2 + GH_OUT * 4;                          // [11]
+  const int tid = threadIdx.x;
+  for (int i = tid; i < w_rows * GH_HID; i += GH_THREADS) s_w1[i] = i < K * GH_HID ? w1t[i] : 0.f;
+  if (tid < GH_HID) s_b1[tid] = b1[tid];
+  if (tid < GH_OUT * 4) s_w2[tid] = w2[tid];
+  if (tid < GH_OUT) s_b2[tid] = b2[tid];
+
+  const long long tiles = (n + GH_ROWS - 1) / GH_ROWS;
+  const long long my_tiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long G = my_tiles * NS;  // stages this CTA consumes
+
+  // producer state: the next stage to issue
+  long long pf_g = 0, pf_tile = blockIdx.x;
+  int pf_slice = 0;
+  auto issue = [&]() {
+    if (pf_g < G) {
+      const long long base = pf_tile * GH_ROWS;
+      const int rows = (int)min((long long)GH_ROWS, n - base);
+      float* dst = s_stage + (int)(pf_g % GH_STAGES) * GH_STAGE_FLOATS;
+      const int kcol = pf_slice * GH_KS + (tid & 3) * 4;
+#pragma unroll
+      for (int q = 0; q < GH_ROWS * 4 / GH_THREADS; q++) {
+        const int row = (tid >> 2) + q * (GH_THREADS / 4);
+        const bool ok = row < rows && kcol < F;
+        const float* src = ok ? feat + (base + row) * F + kcol : feat;
+        cp_async16(dst + row * GH_SS + (tid & 3) * 4, src, ok ? 16u : 0u);  // src-size 0: zero fill
+      }
+      pf_g++;
+      if (++pf_slice == NS) {
+        pf_slice = 0;
+        pf_tile += gridDim.x;
+      }
+    }
+    cp_async_commit();  // (an empty group keeps the wait arithmetic uniform at the end)
+  };
+#pragma unroll
+  for (int st = 0; st < GH_STAGES - 1; st++) issue();
+
+  float h0[GH_HID], h1[GH_HID];
+  float c0[3] = {0.f, 0.f, 0.f}, c1[3] = {0.f, 0.f, 0.f};
+  long long tile = blockIdx.x;
+  int slice = 0;
+  for (long long g = 0; g < G; g++) {
+    cp_async_wait<GH_STAGES - 2>();
+    __syncthreads();  // stage g has landed for every thread; stage g-1's buffer is free for the next issue
+    issue();
+    const long long base = tile * GH_ROWS;
+    const int rows = (int)min((long long)GH_ROWS, n - base);
+    if (slice == 0) {
+#pragma unroll
+      for (int j = 0; j < GH_HID; j++) h0[j] = h1[j] = s_b1[j];
+#pragma unroll
+      for (int c = 0; c < 3; c++) {  // the colour head's rgb inputs: in flight until the last slice
+        c0[c] = tid < rows ? __ldg(rgb + (base + tid) * 3 + c) : 0.f;
+        c1[c] = tid + GH_THREADS < rows ? __ldg(rgb + (base + tid + GH_THREADS) * 3 + c) : 0.f;
+      }
+    }
+    const float* st = s_stage + (int)(g % GH_STAGES) * GH_STAGE_FLOATS;
+    const float* x0p = st + tid * GH_SS;
+    const float* x1p = st + (tid + GH_THREADS) * GH_SS;
+    const float* wp = s_w1 + slice * GH_KS * GH_HID;
+#pragma unroll
+    for (int k4 = 0; k4 < GH_KS / 4; k4++) {
+      const float4 xa = *reinterpret_cast<const float4*>(x0p + 4 * k4);
+      const float4 xb = *reinterpret_cast<const float4*>(x1p + 4 * k4);
+      const float xav[4] = {xa.x, xa.y, xa.z, xa.w};
+      const float xbv[4] = {xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const float4* w = reinterpret_cast<const float4*>(wp + (4 * k4 + q) * GH_HID);
+        const float4 wa = w[0], wb = w[1], wc = w[2], wd = w[3];
+        GH_FMA16(h0, xav[q], wa, wb, wc, wd)
+        GH_FMA16(h1, xbv[q], wa, wb, wc, wd)
+      }
+    }
+    if (++slice == NS) {
+      // ---- the tile is complete: rgb columns, second layers, activations, stores ----
+#pragma unroll
+      for (int c = 0; c < 3; c++) {
+        const float4* w = reinterpret_cast<const float4*>(s_w1 + (F + c) * GH_HID);
+        const float4 wa = w[0], wb = w[1], wc = w[2], wd = w[3];
+        GH_FMA16(h0, c0[c], wa, wb, wc, wd)
+        GH_FMA16(h1, c1[c], wa, wb, wc, wd)
+      }
+#pragma unroll
+      for (int half = 0; half < 2; half++) {
+        float* h = half ? h1 : h0;
+        const int r = tid + half * GH_THREADS;
+        if (r < rows) {
+          const long long gi = base + r;
+#pragma unroll
+          for (int j = 0; j < GH_HID; j++) h[j] = fmaxf(h[j], 0.f);
+          float z[GH_OUT];
+          gh_second_layer(h, s_w2, s_b2, z);
+          scales[gi * 3 + 0] = gh_softplus(z[0]);
+          scales[gi * 3 + 1] = gh_softplus(z[1]);
+          scales[gi * 3 + 2] = gh_softplus(z[2]);
+          const float nrm = fmaxf(sqrtf(z[3] * z[3] + z[4] * z[4] + z[5] * z[5] + z[6] * z[6]), 1e-12f);  // F.normalize eps
+          reinterpret_cast<float4*>(rotations)[gi] = make_float4(z[3] / nrm, z[4] / nrm, z[5] / nrm, z[6] / nrm);
+          opacity[gi] = gh_sigmoid(z[7]);
+          colors[gi * 3 + 0] = gh_sigmoid(z[8]);
+          colors[gi * 3 + 1] = gh_sigmoid(z[9]);
+          colors[gi * 3 + 2] = gh_sigmoid(z[10]);
+          float4* hp = reinterpret_cast<float4*>(hidden + gi * GH_HID);
+          hp[0] = make_float4(h[0], h[1], h[2], h[3]);
+          hp[1] = make_float4(h[4], h[5], h[6], h[7]);
+          hp[2] = make_float4(h[8], h[9], h[10], h[11]);
+          hp[3] = make_float4(h[12], h[13], h[14], h[15]);
+        }
+      }
+      slice = 0;
+      tile += gridDim.x;
+    }
+  }
+  cp_async_wait<0>();
+}
+
 // Backward.  Persistent CTAs: each keeps its share of the weight gradients in registers across all its tiles and
 // adds them to the global sums once at the end.  Per tile:
 //   (1) per row: z2 from the saved hidden, activation derivatives -> dL/dz2 [11] -> dL/dhidden [16] (ReLU-masked);
@@ -454,12 +604,22 @@ extern "C" int ocrf_gaussian_heads_forward(void* stream, int64_t n, int32_t F, c
   if (n == 0) return 0;
   if (!feat || !rgb || !w1t || !b1 || !w2 || !b2 || !opacity || !scales || !rotations || !colors || !hidden) return OCRF_EINVAL;
   if (!gh_aligned16(rotations) || !gh_aligned16(hidden)) return OCRF_EINVAL;
-  const size_t smem = gh_fwd_smem(F);
-  cudaError_t e = cudaFuncSetAttribute(gaussian_heads_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  const int fast = (F % 4 == 0) && gh_aligned16(feat);
-  gaussian_heads_forward_kernel<<<gh_grid(n, smem), GH_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      n, F, fast, feat, rgb, w1t, b1, w2, b2, opacity, scales, rotations, colors, hidden);
+  if ((F % 4 == 0) && gh_aligned16(feat)) {
+    const int ns = (F + GH_KS - 1) / GH_KS;
+    const int w_rows = (F + 3) > ns * GH_KS ? (F + 3) : ns * GH_KS;
+    const size_t smem = ((size_t)GH_STAGES * GH_STAGE_FLOATS + (size_t)w_rows * GH_HID + GH_HID + GH_OUT * 4 + 12) * 4;
+    cudaError_t e = cudaFuncSetAttribute(gaussian_heads_forward_sliced_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    gaussian_heads_forward_sliced_kernel<<<gh_grid(n, smem), GH_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+        n, F, feat, rgb, w1t, b1, w2, b2, opacity, scales, rotations, colors, hidden);
+  } else {  // odd channel counts / unaligned views: whole-row tiles filled with plain loads
+    const size_t smem = gh_fwd_smem(F);
+    cudaError_t e = cudaFuncSetAttribute(gaussian_heads_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    gaussian_heads_forward_kernel<<<gh_grid(n, smem), GH_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+        n, F, 0, feat, rgb, w1t, b1, w2, b2, opacity, scales, rotations, colors, hidden);
+  }
   OCRF_CHECK_LAST();
   return 0;
 }

@@ -161,6 +161,7 @@ class _RasterizeBatch(torch.autograd.Function):
         ctx.save_for_backward(means3D, shs, colors, scales, rotations, cov3D_precomp, cams, bg, radii, geom, binning,
                               image)
         ctx.mark_non_differentiable(radii, depth)  # no depth backward in the fork (its README:13)
+        ctx.set_materialize_grads(False)  # no zero-filled gradient tensors for radii / depth / unused outputs
         return color, radii, depth, opac
 
     @staticmethod
@@ -185,7 +186,8 @@ class _RasterizeBatch(torch.autograd.Function):
                                      ptr(ggrad), ptr(g_feat)), "ocrf_render_backward")
         _stage("render_backward")
         g_means3D = torch.empty_like(means3D)
-        g_means2D = torch.empty((V, P, 3), dtype=torch.float32, device=dev)
+        # dL/dmean2D is only materialised when the caller holds a means2D leaf (the reference's screenspace_points)
+        g_means2D = torch.empty((V, P, 3), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
         g_opacities = torch.empty((S, P, 1), dtype=torch.float32, device=dev)
         has_cov = cov3D_precomp is not None
         g_scales = None if has_cov else torch.empty_like(scales)
@@ -299,8 +301,8 @@ def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors
             ((scales is not None or rotations is not None) and cov3D_precomp is not None):
         raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
     f = lambda t: None if t is None else t.float().contiguous()  # noqa: E731
-    if means2D is None:
-        means2D = torch.zeros((V, P, 3), dtype=torch.float32, device=means3D.device)
+    if means2D is None:  # gradient holder only, never read: no fill, and no dL/dmean2D output in backward
+        means2D = torch.empty((V, P, 3), dtype=torch.float32, device=means3D.device)
     cfg = dict(W=int(image_width), H=int(image_height), scale_modifier=float(scale_modifier), sh_degree=int(sh_degree),
                prefiltered=bool(prefiltered), pair_capacity=pair_capacity,
                binning=binning if binning is not None else os.environ.get("OCRF_BINNING", "split"))
