@@ -213,6 +213,24 @@ int ocrf_gaussian_heads_backward(void* stream, int64_t n, int32_t F, const float
                                  const float* g_colors, float* g_feat, float* g_w1t, float* g_b1, float* g_w2,
                                  float* g_b2);
 
+/* "Next" row f-3: BEV pooling v2 (mmdet3d/ops/bev_pool_v2/src/bev_pool_cuda.cu:21-121, bound at
+ * bev_pool_v2/src/bev_pool.cpp and called from bev_pool_v2/bev_pool.py:18-79).
+ * depth: flat floats indexed by ranks_depth; feat [n_feat, c]; out [n_bev, c] zero-filled by the caller (as
+ * feat.new_zeros in bev_pool.py:29); the rank / interval arrays are the reference's int32 tensors, points sorted by
+ * ranks_bev.  out[ranks_bev[start], :] = sum over the interval of depth * feat row (same summation order as the
+ * reference kernel). */
+int ocrf_bev_pool_forward(void* stream, int32_t c, int32_t n_intervals, const float* depth, const float* feat,
+                          const int32_t* ranks_depth, const int32_t* ranks_feat, const int32_t* ranks_bev,
+                          const int32_t* interval_starts, const int32_t* interval_lengths, float* out);
+/* Backward, INCLUDING the regrouping of the points by feature pixel that the reference does in Python before its kernel
+ * (bev_pool.py:47-60): pass the forward's rank arrays as they are (n_points entries, any order).  c <= 128.
+ * depth_grad (same extent as depth) must be zero-filled by the caller; feat_grad [n_feat, c] is written completely.
+ * ws holds ocrf_bev_pool_backward_workspace_bytes(n_points). */
+size_t ocrf_bev_pool_backward_workspace_bytes(uint64_t n_points);
+int ocrf_bev_pool_backward(void* stream, int32_t c, uint64_t n_points, int32_t n_feat, const float* out_grad,
+                           const float* depth, const float* feat, const int32_t* ranks_depth, const int32_t* ranks_feat,
+                           const int32_t* ranks_bev, float* depth_grad, float* feat_grad, void* ws);
+
 #ifdef __cplusplus
 }
 #endif

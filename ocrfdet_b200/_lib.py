@@ -24,6 +24,7 @@ EXPORTS = [
     "ocrf_render_backward", "ocrf_preprocess_backward", "ocrf_mark_visible", "ocrf_sort_workspace_bytes",
     "ocrf_sort_pairs", "ocrf_opacity_mask_forward", "ocrf_opacity_mask_backward",
     "ocrf_gaussian_heads_forward", "ocrf_gaussian_heads_backward", "ocrf_clear_gradients",
+    "ocrf_bev_pool_forward", "ocrf_bev_pool_backward_workspace_bytes", "ocrf_bev_pool_backward",
 ]
 
 
@@ -86,6 +87,10 @@ def lib():
     L.ocrf_sort_pairs.argtypes = [vp, u64, C.c_int, vp, vp, vp, vp, vp, vp, vp]
     L.ocrf_opacity_mask_forward.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp]
     L.ocrf_opacity_mask_backward.argtypes = [vp, i32, i32, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.ocrf_bev_pool_forward.argtypes = [vp, i32, i32] + [vp] * 8
+    L.ocrf_bev_pool_backward_workspace_bytes.restype = C.c_size_t
+    L.ocrf_bev_pool_backward_workspace_bytes.argtypes = [u64]
+    L.ocrf_bev_pool_backward.argtypes = [vp, i32, u64, i32] + [vp] * 9
     L.ocrf_clear_gradients.argtypes = [vp, shp, C.c_int, vp, vp, vp]
     L.ocrf_gaussian_heads_forward.argtypes = [vp, C.c_int64, i32] + [vp] * 11
     L.ocrf_gaussian_heads_backward.argtypes = [vp, C.c_int64, i32] + [vp] * 15

@@ -58,3 +58,46 @@ def ring_scene(P=100000, seed=0, width=704, height=256, channels=3, n_views=6, b
     g = gaussians_on_grid(P, seed, channels=channels, bev=bev)
     cams = ego_ring_cameras(width, height)[:n_views]
     return g, cams
+
+
+def bev_pool_case(B=1, N=6, D=88, H=16, W=44, C=80, bev=128, seed=0, pc=51.2, depth_range=(1.0, 45.0)):
+    """Rank / interval tensors of an LSS lift as `voxel_pooling_prepare_v2` builds them
+    (view_transformer_ocrf.py:697-748): every (camera, depth bin, pixel) frustum point is dropped into a
+    bev x bev grid over +-pc metres (Z collapsed), points outside are filtered, the rest are sorted by BEV cell.
+    Six ring cameras with a 70 degree horizontal field of view.  Returns numpy arrays:
+    depth [B,N,D,H,W], feat [B,N,H,W,C], ranks_depth, ranks_feat, ranks_bev (int32, sorted by ranks_bev),
+    interval_starts, interval_lengths, n_bev = B*bev*bev."""
+    rng = np.random.default_rng(seed)
+    d = depth_range[0] + (depth_range[1] - depth_range[0]) * (np.arange(D) + 0.5) / D
+    half = np.tan(np.deg2rad(35.0))
+    u = ((np.arange(W) + 0.5) / W * 2 - 1) * half
+    v = ((np.arange(H) + 0.5) / H * 2 - 1) * half * H / W
+    yaw = np.deg2rad(np.array([0, 55, 110, 180, -110, -55])[np.arange(N) % 6] + 360.0 * (np.arange(N) // 6) / max(N, 1))
+    dd, vv, uu = np.meshgrid(d, v, u, indexing="ij")          # [D,H,W]
+    xc, zc = uu * dd, dd                                          # camera frame: x right, z forward
+    ranks_depth, ranks_feat, ranks_bev = [], [], []
+    for b in range(B):
+        shift = rng.uniform(-2, 2, size=2)                        # per-sample ego jitter (augmentation)
+        for n in range(N):
+            ex = np.cos(yaw[n]) * zc + np.sin(yaw[n]) * xc + shift[0]
+            ey = np.sin(yaw[n]) * zc - np.cos(yaw[n]) * xc + shift[1]
+            ix = np.floor((ex + pc) / (2 * pc) * bev).astype(np.int64)
+            iy = np.floor((ey + pc) / (2 * pc) * bev).astype(np.int64)
+            kept = (ix >= 0) & (ix < bev) & (iy >= 0) & (iy < bev)
+            di, hi, wi = np.nonzero(kept)
+            bn = b * N + n
+            ranks_depth.append(((bn * D + di) * H + hi) * W + wi)
+            ranks_feat.append((bn * H + hi) * W + wi)
+            ranks_bev.append((b * bev + iy[kept]) * bev + ix[kept])
+    rd, rf, rb = (np.concatenate(a) for a in (ranks_depth, ranks_feat, ranks_bev))
+    order = np.argsort(rb, kind="stable")
+    rd, rf, rb = rd[order].astype(np.int32), rf[order].astype(np.int32), rb[order].astype(np.int32)
+    kept = np.ones(len(rb), bool)
+    kept[1:] = rb[1:] != rb[:-1]
+    starts = np.nonzero(kept)[0].astype(np.int32)
+    lengths = np.diff(np.append(starts, len(rb))).astype(np.int32)
+    depth = rng.random((B, N, D, H, W), dtype=np.float32)
+    depth /= depth.sum(2, keepdims=True)                          # a softmax-like depth distribution
+    feat = rng.normal(size=(B, N, H, W, C)).astype(np.float32)
+    return dict(depth=depth, feat=feat, ranks_depth=rd, ranks_feat=rf, ranks_bev=rb, interval_starts=starts,
+                interval_lengths=lengths, n_bev=B * bev * bev, bev_feat_shape=(B, 1, bev, bev, C))

@@ -718,3 +718,46 @@ void ocrf_oracle_gaussian_heads_backward(long long n, int F, const float* feat, 
     free(a1w[hd]);
   }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * BEV pooling v2 (mmdet3d/ops/bev_pool_v2/src/bev_pool_cuda.cu).  Same loops, same summation order; the products
+ * are accumulated with fmaf because nvcc contracts `psum += a * b` of the reference kernels (this file is compiled
+ * with -ffp-contract=off, so the contraction is spelled out).
+ * ------------------------------------------------------------------------------------------ */
+/* bev_pool_cuda.cu:21-49 */
+void ocrf_oracle_bev_pool_forward(int c, int n_intervals, const float* depth, const float* feat, const int* ranks_depth,
+                                  const int* ranks_feat, const int* ranks_bev, const int* interval_starts,
+                                  const int* interval_lengths, float* out) {
+  for (int index = 0; index < n_intervals; index++) {
+    const int start = interval_starts[index], len = interval_lengths[index];
+    for (int cur_c = 0; cur_c < c; cur_c++) {
+      float psum = 0.f;
+      for (int i = 0; i < len; i++)
+        psum = fmaf(feat[(size_t)ranks_feat[start + i] * c + cur_c], depth[ranks_depth[start + i]], psum);
+      out[(size_t)ranks_bev[start] * c + cur_c] = psum;
+    }
+  }
+}
+
+/* bev_pool_cuda.cu:69-121; the rank arrays and intervals are the feature-sorted ones of bev_pool.py:47-60 */
+void ocrf_oracle_bev_pool_backward(int c, int n_intervals, const float* out_grad, const float* depth, const float* feat,
+                                   const int* ranks_depth, const int* ranks_feat, const int* ranks_bev,
+                                   const int* interval_starts, const int* interval_lengths, float* depth_grad,
+                                   float* feat_grad) {
+  for (int idx = 0; idx < n_intervals; idx++) {
+    const int start = interval_starts[idx], len = interval_lengths[idx];
+    for (int i = 0; i < len; i++) {
+      const float* g = out_grad + (size_t)ranks_bev[start + i] * c;
+      const float* f = feat + (size_t)ranks_feat[start + i] * c;
+      float grad_sum = 0.f;
+      for (int cur_c = 0; cur_c < c; cur_c++) grad_sum = fmaf(g[cur_c], f[cur_c], grad_sum);
+      depth_grad[ranks_depth[start + i]] = grad_sum;
+    }
+    for (int cur_c = 0; cur_c < c; cur_c++) {
+      float grad_sum = 0.f;
+      for (int i = 0; i < len; i++)
+        grad_sum = fmaf(out_grad[(size_t)ranks_bev[start + i] * c + cur_c], depth[ranks_depth[start + i]], grad_sum);
+      feat_grad[(size_t)ranks_feat[start] * c + cur_c] = grad_sum;
+    }
+  }
+}

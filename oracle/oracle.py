@@ -271,3 +271,46 @@ def gaussian_heads_backward(feat, rgb, params, g_opacity, g_scales, g_rotations,
                                               keep[2][1], keep[3][1], _ptr(gs[0]), _ptr(gs[1]), _ptr(gs[2]), _ptr(gs[3]),
                                               _ptr(g_feat), gp[0], gp[1], gp[2], gp[3])
     return g_feat, grads
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def bev_pool_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, n_bev, interval_starts, interval_lengths):
+    """out [n_bev, c] (channels-last, before the permute of bev_pool.py:86)."""
+    depth, feat = _f32(depth).reshape(-1), _f32(feat)
+    c = feat.shape[-1]
+    feat = feat.reshape(-1, c)
+    rd, rf, rb, st, ln = (_i32(a) for a in (ranks_depth, ranks_feat, ranks_bev, interval_starts, interval_lengths))
+    out = np.zeros((n_bev, c), np.float32)
+    lib().ocrf_oracle_bev_pool_forward(C.c_int(c), C.c_int(len(st)), _ptr(depth), _ptr(feat), _ptr(rd), _ptr(rf), _ptr(rb),
+                                       _ptr(st), _ptr(ln), _ptr(out))
+    return out
+
+
+def bev_pool_regroup(ranks_depth, ranks_feat, ranks_bev):
+    """bev_pool.py:47-60 with a STABLE argsort (torch's default argsort leaves the order of equal keys open)."""
+    rf = _i32(ranks_feat)
+    order = np.argsort(rf, kind="stable")
+    rf, rd, rb = rf[order], _i32(ranks_depth)[order], _i32(ranks_bev)[order]
+    kept = np.ones(len(rf), bool)
+    kept[1:] = rf[1:] != rf[:-1]
+    starts = np.nonzero(kept)[0].astype(np.int32)
+    lengths = np.diff(np.append(starts, len(rf))).astype(np.int32)
+    return rd, rf, rb, starts, lengths
+
+
+def bev_pool_backward(out_grad, depth, feat, ranks_depth, ranks_feat, ranks_bev):
+    """out_grad [n_bev, c] -> (depth_grad like depth, feat_grad like feat)."""
+    depth_shape, feat_shape = np.shape(depth), np.shape(feat)
+    depth, feat = _f32(depth).reshape(-1), _f32(feat)
+    c = feat.shape[-1]
+    feat = feat.reshape(-1, c)
+    og = _f32(out_grad).reshape(-1, c)
+    depth_grad, feat_grad = np.zeros_like(depth), np.zeros_like(feat)
+    if len(ranks_feat):
+        rd, rf, rb, st, ln = bev_pool_regroup(ranks_depth, ranks_feat, ranks_bev)
+        lib().ocrf_oracle_bev_pool_backward(C.c_int(c), C.c_int(len(st)), _ptr(og), _ptr(depth), _ptr(feat), _ptr(rd),
+                                            _ptr(rf), _ptr(rb), _ptr(st), _ptr(ln), _ptr(depth_grad), _ptr(feat_grad))
+    return depth_grad.reshape(depth_shape), feat_grad.reshape(feat_shape)

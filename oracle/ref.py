@@ -118,3 +118,55 @@ def mark_visible(means3D, viewmatrix, projmatrix):
     present = torch.zeros(P, dtype=torch.bool, device=means3D.device)
     lib().ref_mark_visible(P, _p(means3D), _p(viewmatrix), _p(projmatrix), _p(present))
     return present
+
+
+# ---- the reference's bev_pool_v2 kernels (oracle/_ref/libbevpool_ref.so, `make -C oracle refbev`) ----
+SO_BEV = os.path.join(_HERE, "_ref", "libbevpool_ref.so")
+_lib_bev = None
+
+
+def bev_available():
+    return os.path.exists(SO_BEV)
+
+
+def _bev():
+    global _lib_bev
+    if _lib_bev is None:
+        L = C.CDLL(SO_BEV)
+        L.ref_bev_pool_forward.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 8
+        L.ref_bev_pool_backward.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 10
+        _lib_bev = L
+    return _lib_bev
+
+
+def bev_pool_forward(depth, feat, ranks_depth, ranks_feat, ranks_bev, n_bev, interval_starts, interval_lengths):
+    """CUDA tensors in, out [n_bev, c] (bev_pool.py:18-44 without the permute).  Legacy default stream."""
+    c = feat.shape[-1]
+    out = feat.new_zeros((n_bev, c))
+    torch.cuda.synchronize()
+    rc = _bev().ref_bev_pool_forward(c, interval_starts.numel(), _p(depth), _p(feat), _p(ranks_depth), _p(ranks_feat),
+                                     _p(ranks_bev), _p(interval_starts), _p(interval_lengths), _p(out))
+    torch.cuda.synchronize()
+    assert rc == 0, rc
+    return out
+
+
+def bev_pool_backward(out_grad, depth, feat, ranks_depth, ranks_feat, ranks_bev, stable=True):
+    """bev_pool.py:46-79: regroup by ranks_feat (stable order here, see oracle.bev_pool_regroup), then the kernel."""
+    order = torch.sort(ranks_feat.long(), stable=stable)[1]
+    rf, rd, rb = ranks_feat[order].contiguous(), ranks_depth[order].contiguous(), ranks_bev[order].contiguous()
+    kept = torch.ones(rb.shape[0], device=rb.device, dtype=torch.bool)
+    kept[1:] = rf[1:] != rf[:-1]
+    starts = torch.where(kept)[0].int()
+    lengths = torch.zeros_like(starts)
+    lengths[:-1] = starts[1:] - starts[:-1]
+    lengths[-1] = rb.shape[0] - starts[-1]
+    depth_grad, feat_grad = torch.zeros_like(depth), torch.zeros_like(feat)
+    c = feat.shape[-1]
+    torch.cuda.synchronize()
+    rc = _bev().ref_bev_pool_backward(c, starts.numel(), _p(out_grad.contiguous()), _p(depth), _p(feat), _p(rd), _p(rf),
+                                      _p(rb), _p(starts.contiguous()), _p(lengths.contiguous()), _p(depth_grad),
+                                      _p(feat_grad))
+    torch.cuda.synchronize()
+    assert rc == 0, rc
+    return depth_grad, feat_grad

@@ -87,3 +87,28 @@ def test_opacity_mask_oracle_matches_torch(B, C, H, W, K):
     assert util.rel_err(gx, xt.grad.numpy()) <= 1e-5
     assert util.rel_err(gw, wt.grad.numpy().reshape(2, K, K)) <= 1e-5
     assert util.rel_err(gop, ot.grad.numpy()) <= 1e-5
+
+
+@pytest.mark.parametrize("case", [dict(B=1, N=2, D=10, H=4, W=7, C=12, bev=16, seed=1),
+                                  dict(B=2, N=3, D=16, H=6, W=10, C=19, bev=32, seed=2)])
+def test_bev_pool_oracle_matches_dense_numpy(case):
+    """ocrf_oracle_bev_pool_* (restating bev_pool_cuda.cu:21-121) against an order-free float64 formulation."""
+    from ocrfdet_b200.scenes import bev_pool_case
+    c = bev_pool_case(**case)
+    C_ = case["C"]
+    d, f = c["depth"].reshape(-1).astype(np.float64), c["feat"].reshape(-1, C_).astype(np.float64)
+    out = oracle.bev_pool_forward(c["depth"], c["feat"], c["ranks_depth"], c["ranks_feat"], c["ranks_bev"], c["n_bev"],
+                                  c["interval_starts"], c["interval_lengths"])
+    want = np.zeros((c["n_bev"], C_))
+    np.add.at(want, c["ranks_bev"], d[c["ranks_depth"]][:, None] * f[c["ranks_feat"]])
+    assert np.abs(out - want).max() <= 1e-5 * (1 + np.abs(want).max())
+    og = np.random.default_rng(5).normal(size=out.shape).astype(np.float32)
+    dg, fg = oracle.bev_pool_backward(og, c["depth"], c["feat"], c["ranks_depth"], c["ranks_feat"], c["ranks_bev"])
+    wdg = np.zeros(d.shape)
+    wdg[c["ranks_depth"]] = (og[c["ranks_bev"]].astype(np.float64) * f[c["ranks_feat"]]).sum(1)
+    wfg = np.zeros(f.shape)
+    np.add.at(wfg, c["ranks_feat"], og[c["ranks_bev"]].astype(np.float64) * d[c["ranks_depth"]][:, None])
+    assert np.abs(dg.reshape(-1) - wdg).max() <= 1e-5 * (1 + np.abs(wdg).max())
+    assert np.abs(fg.reshape(-1, C_) - wfg).max() <= 1e-5 * (1 + np.abs(wfg).max())
+    # intervals cover the point list exactly once, sorted by BEV cell (voxel_pooling_prepare_v2's contract)
+    assert int(c["interval_lengths"].sum()) == len(c["ranks_bev"]) and np.all(np.diff(c["ranks_bev"]) >= 0)

@@ -12,7 +12,7 @@ from tests import util
 from tests.golden.make_golden import scene
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not os.path.basename(p).startswith("heads_"))
+                if not os.path.basename(p).startswith(("heads_", "bevpool_")))
 GOLDEN_HEADS = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "heads_*.npz")))
 
 
@@ -81,3 +81,26 @@ def test_heads_oracle_matches_reference_modules(path):
 
 def test_heads_golden_present():
     assert len(GOLDEN_HEADS) >= 2
+
+
+GOLDEN_BEV = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "bevpool_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN_BEV, ids=[os.path.basename(p) for p in GOLDEN_BEV])
+def test_bev_pool_oracle_matches_reference_cuda_golden(path):
+    """tests/golden/bevpool_*.npz hold the outputs of the reference's own bev_pool_v2 CUDA kernels on a B200
+    (tests/golden/make_golden_bev.py).  The oracle keeps their loops and fma contraction: bit-exact."""
+    from tests.golden.make_golden_bev import case_inputs
+    z = np.load(path)
+    c = case_inputs(ast.literal_eval(str(z["case"])))
+    out = oracle.bev_pool_forward(c["depth"], c["feat"], c["ranks_depth"], c["ranks_feat"], c["ranks_bev"], c["n_bev"],
+                                  c["interval_starts"], c["interval_lengths"])
+    assert np.array_equal(out, z["out"])
+    dg, fg = oracle.bev_pool_backward(c["out_grad"], c["depth"], c["feat"], c["ranks_depth"], c["ranks_feat"],
+                                      c["ranks_bev"])
+    assert np.array_equal(fg, z["feat_grad"])
+    assert np.array_equal(dg, z["depth_grad"])
+
+
+def test_bev_pool_golden_present():
+    assert len(GOLDEN_BEV) >= 2
