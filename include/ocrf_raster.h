@@ -231,6 +231,20 @@ int ocrf_bev_pool_backward(void* stream, int32_t c, uint64_t n_points, int32_t n
                            const float* depth, const float* feat, const int32_t* ranks_depth, const int32_t* ranks_feat,
                            const int32_t* ranks_bev, float* depth_grad, float* feat_grad, void* ws);
 
+/* "Next" row f-4 (callers upstream of the Gaussian heads).
+ * ocrf_color_voxels = lidar_points_to_image_values + color_voxels (view_transformer_ocrf.py:924-971): avg [B,M,C] =
+ * mean over the cameras n with mask[b,n,m] != 0 of the bilinear sample (grid_sample, align_corners=True, zero padding)
+ * of imgs [B,N,C,H,W] at pixel coordinates coords [B,N,M,2] (x,y); 0 where no camera sees the voxel; the mean is
+ * divided by `divisor` when it is not 1 (the caller's / 255.0 at :1071).  valid [B,M] (may be NULL) = any(mask).
+ * C <= 4; coords 8-byte aligned. */
+int ocrf_color_voxels(void* stream, int32_t B, int32_t N, int64_t M, int32_t C, int32_t H, int32_t W, const float* coords,
+                      const uint8_t* mask, const float* imgs, float divisor, float* avg, uint8_t* valid);
+/* ocrf_retain_valid_pixels = retain_valid_pixels (view_transformer_ocrf.py:1004-1022): out [V,C,H,W] = `fill` except
+ * at the pixels (trunc(x), trunc(y)), clamped to [0, max(W,H)-1], of the points with mask != 0 and x != -1, which
+ * keep img's value.  coords [V,M,2], mask [V,M]; out 16-byte aligned. */
+int ocrf_retain_valid_pixels(void* stream, int32_t V, int64_t M, int32_t C, int32_t H, int32_t W, const float* coords,
+                             const uint8_t* mask, const float* img, float fill, float* out);
+
 #ifdef __cplusplus
 }
 #endif

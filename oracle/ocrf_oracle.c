@@ -761,3 +761,65 @@ void ocrf_oracle_bev_pool_backward(int c, int n_intervals, const float* out_grad
     }
   }
 }
+
+/* ------------------------------------------------------------------------------------------
+ * Voxel colouring and the sparse supervision image (view_transformer_ocrf.py:924-971, 1004-1022).
+ * ------------------------------------------------------------------------------------------ */
+/* F.grid_sample(bilinear, zeros, align_corners=True) of one point after the caller's normalisation (:929-930);
+ * ATen grid_sampler_2d: ix = (xn + 1) / 2 * (W - 1), corners nw/ne/sw/se accumulated in that order. */
+static void vc_bilinear(const float* img, int C, int H, int W, float x, float y, float* out) {
+  const float xn = x / (float)(W - 1) * 2.f - 1.f, yn = y / (float)(H - 1) * 2.f - 1.f;
+  const float ix = (xn + 1.f) / 2.f * (float)(W - 1), iy = (yn + 1.f) / 2.f * (float)(H - 1);
+  const float fx0 = floorf(ix), fy0 = floorf(iy), fx1 = fx0 + 1.f, fy1 = fy0 + 1.f;
+  const float w[4] = {(fx1 - ix) * (fy1 - iy), (ix - fx0) * (fy1 - iy), (fx1 - ix) * (iy - fy0), (ix - fx0) * (iy - fy0)};
+  const float cx[4] = {fx0, fx1, fx0, fx1}, cy[4] = {fy0, fy0, fy1, fy1};
+  for (int c = 0; c < C; c++) {
+    float v = 0.f;
+    for (int k = 0; k < 4; k++)
+      if (cx[k] >= 0.f && cx[k] <= (float)(W - 1) && cy[k] >= 0.f && cy[k] <= (float)(H - 1))
+        v += img[((size_t)c * H + (int)cy[k]) * W + (int)cx[k]] * w[k];
+    out[c] = v;
+  }
+}
+
+/* lidar_points_to_image_values (:924-942) + color_voxels (:945-962): avg [B,M,C], valid [B,M] */
+void ocrf_oracle_color_voxels(int B, int N, long long M, int C, int H, int W, const float* coords, const uint8_t* mask,
+                              const float* imgs, float divisor, float* avg, uint8_t* valid) {
+  for (int b = 0; b < B; b++)
+    for (long long m = 0; m < M; m++) {
+      float sum[8] = {0};
+      int count = 0;
+      for (int n = 0; n < N; n++) {
+        const size_t o = ((size_t)b * N + n) * M + m;
+        if (!mask[o]) continue;
+        float s[8];
+        vc_bilinear(imgs + ((size_t)b * N + n) * C * H * W, C, H, W, coords[2 * o], coords[2 * o + 1], s);
+        for (int c = 0; c < C; c++) sum[c] += s[c];
+        count++;
+      }
+      for (int c = 0; c < C; c++) {
+        float v = sum[c] / (float)(count > 0 ? count : 1);
+        if (divisor != 1.f) v = v / divisor;
+        avg[((size_t)b * M + m) * C + c] = v;
+      }
+      valid[(size_t)b * M + m] = count > 0;
+    }
+}
+
+/* retain_valid_pixels (:1004-1022) */
+void ocrf_oracle_retain_valid_pixels(int V, long long M, int C, int H, int W, const float* coords, const uint8_t* mask,
+                                     const float* img, float fill, float* out) {
+  const size_t HW = (size_t)H * W;
+  for (size_t i = 0; i < (size_t)V * C * HW; i++) out[i] = fill;
+  const long long lim = (W > H ? W : H) - 1;
+  for (int v = 0; v < V; v++)
+    for (long long m = 0; m < M; m++) {
+      const size_t o = (size_t)v * M + m;
+      if (!mask[o] || coords[2 * o] == -1.f) continue;
+      long long xi = (long long)coords[2 * o], yi = (long long)coords[2 * o + 1];
+      xi = xi < 0 ? 0 : (xi > lim ? lim : xi);
+      yi = yi < 0 ? 0 : (yi > lim ? lim : yi);
+      if (xi >= W || yi >= H) continue;
+      for (int c = 0; c < C; c++) out[((size_t)v * C + c) * HW + yi * W + xi] = img[((size_t)v * C + c) * HW + yi * W + xi];
+    }
+}

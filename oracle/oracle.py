@@ -314,3 +314,26 @@ def bev_pool_backward(out_grad, depth, feat, ranks_depth, ranks_feat, ranks_bev)
         lib().ocrf_oracle_bev_pool_backward(C.c_int(c), C.c_int(len(st)), _ptr(og), _ptr(depth), _ptr(feat), _ptr(rd),
                                             _ptr(rf), _ptr(rb), _ptr(st), _ptr(ln), _ptr(depth_grad), _ptr(feat_grad))
     return depth_grad.reshape(depth_shape), feat_grad.reshape(feat_shape)
+
+
+def color_voxels(pillars, imgs, mask, divisor=1.0):
+    """pillars [B,N,P,Q,2], imgs [B,N,C,H,W], mask [B,N,P,Q,1] -> avg [B,P,Q,C], valid [B,P,Q] (bool)."""
+    pillars, imgs = _f32(pillars), _f32(imgs)
+    B, N, P, Q, _ = pillars.shape
+    _, _, Cc, H, W = imgs.shape
+    m8 = np.ascontiguousarray(np.asarray(mask).reshape(B, N, P * Q) != 0, dtype=np.uint8)
+    avg, valid = np.zeros((B, P, Q, Cc), np.float32), np.zeros((B, P, Q), np.uint8)
+    lib().ocrf_oracle_color_voxels(C.c_int(B), C.c_int(N), C.c_longlong(P * Q), C.c_int(Cc), C.c_int(H), C.c_int(W),
+                                   _ptr(pillars), _ptr(m8), _ptr(imgs), C.c_float(divisor), _ptr(avg), _ptr(valid))
+    return avg, valid.astype(bool)
+
+
+def retain_valid_pixels(image_matrix, cloud, mask, fill=255.0):
+    img, cloud = _f32(image_matrix), _f32(cloud)
+    B, N, Cc, H, W = img.shape
+    M = int(np.prod(cloud.shape[2:-1]))
+    m8 = np.ascontiguousarray(np.asarray(mask).reshape(B * N, M) != 0, dtype=np.uint8)
+    out = np.zeros_like(img)
+    lib().ocrf_oracle_retain_valid_pixels(C.c_int(B * N), C.c_longlong(M), C.c_int(Cc), C.c_int(H), C.c_int(W),
+                                          _ptr(cloud), _ptr(m8), _ptr(img), C.c_float(fill), _ptr(out))
+    return out

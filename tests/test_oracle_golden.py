@@ -12,7 +12,7 @@ from tests import util
 from tests.golden.make_golden import scene
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not os.path.basename(p).startswith(("heads_", "bevpool_")))
+                if not os.path.basename(p).startswith(("heads_", "bevpool_", "voxelcolor_")))
 GOLDEN_HEADS = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "heads_*.npz")))
 
 
@@ -104,3 +104,26 @@ def test_bev_pool_oracle_matches_reference_cuda_golden(path):
 
 def test_bev_pool_golden_present():
     assert len(GOLDEN_BEV) >= 2
+
+
+GOLDEN_VC = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "voxelcolor_*.npz")))
+
+
+@pytest.mark.parametrize("path", GOLDEN_VC, ids=[os.path.basename(p) for p in GOLDEN_VC])
+def test_voxel_color_oracle_matches_reference_methods(path):
+    """tests/golden/voxelcolor_*.npz were produced by executing the reference's own lidar_points_to_image_values,
+    color_voxels and retain_valid_pixels (tests/golden/make_golden_voxel_color.py).  Colours live on a 0..255 scale:
+    1e-5 relative to that scale; the sparse image and the validity mask are exact."""
+    from tests.golden.make_golden_voxel_color import voxel_color_case
+    z = np.load(path)
+    pillars, imgs, mask = voxel_color_case(**ast.literal_eval(str(z["case"])))
+    avg, valid = oracle.color_voxels(pillars, imgs, mask)
+    assert np.array_equal(valid, z["valid"])
+    assert np.abs(avg - z["avg"]).max() <= 1e-5 * 255
+    assert np.array_equal(avg[~valid], np.zeros_like(avg[~valid]))
+    sparse = oracle.retain_valid_pixels(imgs, pillars, mask)
+    assert np.array_equal(sparse, z["sparse"])
+
+
+def test_voxel_color_golden_present():
+    assert len(GOLDEN_VC) >= 2
