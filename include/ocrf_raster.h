@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define OCRF_ABI_VERSION 1
+#define OCRF_ABI_VERSION 2
 
 #define OCRF_EINVAL (-1)    /* bad argument (null pointer, non-positive size, unsupported channel count) */
 #define OCRF_ECAPACITY (-2) /* workspace too small for the request */
@@ -206,12 +206,15 @@ int ocrf_opacity_mask_backward(void* stream, int32_t B, int32_t C, int32_t H, in
 int ocrf_gaussian_heads_forward(void* stream, int64_t n, int32_t F, const float* feat, const float* rgb,
                                 const float* w1t, const float* b1, const float* w2, const float* b2, float* opacity,
                                 float* scales, float* rotations, float* colors, float* hidden);
-/* g_feat [n,F] is written; g_w1t [F+3,16], g_b1 [16], g_w2 [11,4], g_b2 [11] are ACCUMULATED (zero them first). */
+/* g_feat [n,F] is written; g_w1t [F+3,16], g_b1 [16], g_w2 [11,4], g_b2 [11] are ACCUMULATED (zero them first).
+ * ws: ocrf_gaussian_heads_backward_workspace_bytes(n) bytes of scratch (dL/dhidden between the two kernels of the
+ * fast path); may be NULL, then (as for F % 4 != 0 or unaligned feat) a single slower kernel runs. */
+size_t ocrf_gaussian_heads_backward_workspace_bytes(int64_t n);
 int ocrf_gaussian_heads_backward(void* stream, int64_t n, int32_t F, const float* feat, const float* rgb,
                                  const float* w1t, const float* w2, const float* b2, const float* hidden,
                                  const float* g_opacity, const float* g_scales, const float* g_rotations,
                                  const float* g_colors, float* g_feat, float* g_w1t, float* g_b1, float* g_w2,
-                                 float* g_b2);
+                                 float* g_b2, void* ws);
 
 /* "Next" row f-3: BEV pooling v2 (mmdet3d/ops/bev_pool_v2/src/bev_pool_cuda.cu:21-121, bound at
  * bev_pool_v2/src/bev_pool.cpp and called from bev_pool_v2/bev_pool.py:18-79).

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libocrf_raster.so")
 OCRF_CAM_STRIDE = 40
 OCRF_RECORD_BYTES = 48
 OCRF_GGRAD_STRIDE = 6
-ABI_VERSION = 1
+ABI_VERSION = 2
 OCRF_EINVAL = -1
 OCRF_ECAPACITY = -2
 OCRF_BIN_PAIR_SORT = 1
@@ -23,7 +23,7 @@ EXPORTS = [
     "ocrf_sort_end_bit", "ocrf_preprocess_forward", "ocrf_bin_forward", "ocrf_render_forward",
     "ocrf_render_backward", "ocrf_preprocess_backward", "ocrf_mark_visible", "ocrf_sort_workspace_bytes",
     "ocrf_sort_pairs", "ocrf_opacity_mask_forward", "ocrf_opacity_mask_backward",
-    "ocrf_gaussian_heads_forward", "ocrf_gaussian_heads_backward", "ocrf_clear_gradients",
+    "ocrf_gaussian_heads_forward", "ocrf_gaussian_heads_backward", "ocrf_gaussian_heads_backward_workspace_bytes", "ocrf_clear_gradients",
     "ocrf_color_voxels", "ocrf_retain_valid_pixels", "ocrf_bev_pool_forward", "ocrf_bev_pool_backward_workspace_bytes", "ocrf_bev_pool_backward",
 ]
 
@@ -95,7 +95,9 @@ def lib():
     L.ocrf_bev_pool_backward.argtypes = [vp, i32, u64, i32] + [vp] * 9
     L.ocrf_clear_gradients.argtypes = [vp, shp, C.c_int, vp, vp, vp]
     L.ocrf_gaussian_heads_forward.argtypes = [vp, C.c_int64, i32] + [vp] * 11
-    L.ocrf_gaussian_heads_backward.argtypes = [vp, C.c_int64, i32] + [vp] * 15
+    L.ocrf_gaussian_heads_backward.argtypes = [vp, C.c_int64, i32] + [vp] * 16
+    L.ocrf_gaussian_heads_backward_workspace_bytes.restype = C.c_size_t
+    L.ocrf_gaussian_heads_backward_workspace_bytes.argtypes = [C.c_int64]
     if L.ocrf_abi_version() != ABI_VERSION:
         raise OcrfError("libocrf_raster.so ABI %d != expected %d: rebuild" % (L.ocrf_abi_version(), ABI_VERSION))
     _lib = L

@@ -577,6 +577,278 @@ __global__ void __launch_bounds__(GH_THREADS) gaussian_heads_backward_kernel(
   }
 }
 
+
+// ---- backward, fast path (F % 4 == 0, aligned): two kernels --------------------------------------------------
+// (1) rows:    per Gaussian, hidden + upstream gradients -> dL/dz2 -> dL/dhidden (kept in registers, also written to
+//              a [n,16] scratch for kernel 2) -> dL/dfeat = w1t . dL/dhidden, produced in 16-column slices that leave
+//              through a double-buffered shared-memory slice as coalesced 16-byte stores.  The features themselves are
+//              not needed here, so there is no 43 KB tile and 8 CTAs (16 warps) fit per SM.  The 71 small parameter
+//              sums (w2, b2, b1) are reduce-scattered over the warp once per tile and kept in two registers per lane.
+// (2) weights: dL/dw1t[k][j] = sum_n x[n][k] * dL/dhidden[n][j], a [F+3, n] x [n, 16] product streamed through a 3-deep
+//              cp.async ring of 64-row tiles; thread (k-block, j-quad) owns a 4 x 4 block of the result in registers for
+//              the whole kernel (two LDS.128 feed 16 FFMAs), one atomicAdd per parameter per CTA at the end.
+constexpr int GHB_PITCH = 57;  // 44 (w2) + 11 (b2) per thread, odd pitch: conflict-free rows and columns
+
+__global__ void __launch_bounds__(GH_THREADS) gaussian_heads_backward_rows_kernel(
+    long long n, int F, const float* __restrict__ w1t, const float* __restrict__ w2, const float* __restrict__ b2,
+    const float* __restrict__ hidden, const float* __restrict__ g_opacity, const float* __restrict__ g_scales,
+    const float* __restrict__ g_rotations, const float* __restrict__ g_colors, float* __restrict__ g_hidden /*[n,16]*/,
+    float* __restrict__ g_feat, float* __restrict__ g_w2, float* __restrict__ g_b2) {
+  extern __shared__ __align__(128) float s_mem[];
+  const int NS = (F + GH_KS - 1) / GH_KS;
+  float* s_slice = s_mem;                              // [2][GH_ROWS][GH_SS]
+  float* s_w1 = s_slice + 2 * GH_STAGE_FLOATS;         // [NS*16][16], rows >= F zero
+  float* s_w2 = s_w1 + NS * GH_KS * GH_HID;            // [11][4]
+  float* s_b2 = s_w2 + GH_OUT * 4;                     // [11] (+1 pad)
+  float* s_small = s_slice;                            // [GH_THREADS][GHB_PITCH]: per-thread dL/dw2 (44), dL/db2 (11);
+                                                       // aliases the slice buffers (used before them, barrier between)
+  const int tid = threadIdx.x;
+  for (int i = tid; i < NS * GH_KS * GH_HID; i += GH_THREADS) s_w1[i] = i < F * GH_HID ? w1t[i] : 0.f;
+  if (tid < GH_OUT * 4) s_w2[tid] = w2[tid];
+  if (tid < GH_OUT) s_b2[tid] = b2[tid];
+  __syncthreads();
+
+  float small = 0.f;  // thread t < 55 keeps parameter sum t (44 dL/dw2, then 11 dL/db2) across all its tiles
+  const long long tiles = (n + GH_ROWS - 1) / GH_ROWS;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const long long base = tile * GH_ROWS;
+    const int rows = (int)min((long long)GH_ROWS, n - base);
+    float gh[2][GH_HID];
+    float* my_small = s_small + tid * GHB_PITCH;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const int r = tid + half * GH_THREADS;
+      float h[GH_HID], gz[GH_OUT];
+#pragma unroll
+      for (int j = 0; j < GH_HID; j++) gh[half][j] = h[j] = 0.f;
+#pragma unroll
+      for (int i = 0; i < GH_OUT; i++) gz[i] = 0.f;
+      if (r < rows) {
+        const long long g = base + r;
+        const float4* hp = reinterpret_cast<const float4*>(hidden + g * GH_HID);
+        const float4 h0 = __ldg(hp), h1 = __ldg(hp + 1), h2 = __ldg(hp + 2), h3 = __ldg(hp + 3);
+        h[0] = h0.x; h[1] = h0.y; h[2] = h0.z; h[3] = h0.w; h[4] = h1.x; h[5] = h1.y; h[6] = h1.z; h[7] = h1.w;
+        h[8] = h2.x; h[9] = h2.y; h[10] = h2.z; h[11] = h2.w; h[12] = h3.x; h[13] = h3.y; h[14] = h3.z; h[15] = h3.w;
+        float z[GH_OUT];
+        gh_second_layer(h, s_w2, s_b2, z);
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float sg = z[c] > 20.f ? 1.f : gh_sigmoid(z[c]);  // d softplus
+          gz[c] = __ldg(g_scales + g * 3 + c) * sg;
+        }
+        {
+          const float4 gr = __ldg(reinterpret_cast<const float4*>(g_rotations) + g);
+          const float n2 = z[3] * z[3] + z[4] * z[4] + z[5] * z[5] + z[6] * z[6];
+          const float nrm = sqrtf(n2);
+          if (nrm > 1e-12f) {
+            const float inv = 1.f / nrm;
+            const float dotv = (gr.x * z[3] + gr.y * z[4] + gr.z * z[5] + gr.w * z[6]) * inv * inv;
+            gz[3] = (gr.x - z[3] * dotv) * inv;
+            gz[4] = (gr.y - z[4] * dotv) * inv;
+            gz[5] = (gr.z - z[5] * dotv) * inv;
+            gz[6] = (gr.w - z[6] * dotv) * inv;
+          } else {  // clamped norm: y = z / eps
+            gz[3] = gr.x * 1e12f; gz[4] = gr.y * 1e12f; gz[5] = gr.z * 1e12f; gz[6] = gr.w * 1e12f;
+          }
+        }
+        {
+          const float y = gh_sigmoid(z[7]);
+          gz[7] = __ldg(g_opacity + g) * y * (1.f - y);
+        }
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          const float y = gh_sigmoid(z[8 + c]);
+          gz[8 + c] = __ldg(g_colors + g * 3 + c) * y * (1.f - y);
+        }
+#pragma unroll
+        for (int i = 0; i < GH_OUT; i++) {
+          const int hb = gh_hidden_base(i);
+#pragma unroll
+          for (int j = 0; j < 4; j++) gh[half][hb + j] = fmaf(s_w2[i * 4 + j], gz[i], gh[half][hb + j]);
+        }
+#pragma unroll
+        for (int j = 0; j < GH_HID; j++) gh[half][j] = h[j] > 0.f ? gh[half][j] : 0.f;
+        float4* gp = reinterpret_cast<float4*>(g_hidden + g * GH_HID);
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+          gp[q] = make_float4(gh[half][4 * q], gh[half][4 * q + 1], gh[half][4 * q + 2], gh[half][4 * q + 3]);
+      }
+      // this thread's share of dL/dw2, dL/db2 goes to its own shared-memory row (h = gz = 0 for rows past the end)
+#pragma unroll
+      for (int i = 0; i < GH_OUT; i++) {
+        const int hb = gh_hidden_base(i);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const float v = gz[i] * h[hb + j];
+          my_small[i * 4 + j] = half ? my_small[i * 4 + j] + v : v;
+        }
+        my_small[44 + i] = half ? my_small[44 + i] + gz[i] : gz[i];
+      }
+    }
+    __syncthreads();
+    if (tid < 55) {
+      float acc = 0.f;
+#pragma unroll 8
+      for (int t = 0; t < GH_THREADS; t++) acc += s_small[t * GHB_PITCH + tid];
+      small += acc;
+    }
+    __syncthreads();  // s_small is dead: its storage becomes the first dL/dfeat slice
+    // dL/dfeat in slices of 16 columns through the double-buffered slice
+    for (int s = 0; s < NS; s++) {
+      float* buf = s_slice + (s & 1) * GH_STAGE_FLOATS;
+      const float* wp = s_w1 + s * GH_KS * GH_HID;
+#pragma unroll
+      for (int k4 = 0; k4 < GH_KS / 4; k4++) {
+        float o0[4], o1[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          const float4* w = reinterpret_cast<const float4*>(wp + (4 * k4 + q) * GH_HID);
+          const float4 wa = w[0], wb = w[1], wc = w[2], wd = w[3];
+          const float wv[16] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w, wd.x, wd.y, wd.z, wd.w};
+          float a0 = 0.f, a1 = 0.f, c0 = 0.f, c1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 8; j++) {
+            a0 = fmaf(wv[j], gh[0][j], a0);
+            c0 = fmaf(wv[8 + j], gh[0][8 + j], c0);
+            a1 = fmaf(wv[j], gh[1][j], a1);
+            c1 = fmaf(wv[8 + j], gh[1][8 + j], c1);
+          }
+          o0[q] = a0 + c0;
+          o1[q] = a1 + c1;
+        }
+        *reinterpret_cast<float4*>(buf + tid * GH_SS + 4 * k4) = make_float4(o0[0], o0[1], o0[2], o0[3]);
+        *reinterpret_cast<float4*>(buf + (tid + GH_THREADS) * GH_SS + 4 * k4) = make_float4(o1[0], o1[1], o1[2], o1[3]);
+      }
+      __syncthreads();  // slice complete; the other buffer's readers finished before the previous barrier
+      const int kcol = s * GH_KS + (tid & 3) * 4;
+#pragma unroll
+      for (int q = 0; q < GH_ROWS * 4 / GH_THREADS; q++) {
+        const int row = (tid >> 2) + q * (GH_THREADS / 4);
+        if (row < rows && kcol < F)
+          *reinterpret_cast<float4*>(g_feat + (base + row) * F + kcol) =
+              *reinterpret_cast<const float4*>(buf + row * GH_SS + (tid & 3) * 4);
+      }
+    }
+    __syncthreads();
+  }
+  if (tid < 44) atomicAdd(g_w2 + tid, small);
+  else if (tid < 55) atomicAdd(g_b2 + (tid - 44), small);
+}
+
+constexpr int GHW_MAX_THREADS = 160;  // owner warps for the 4 * ceil((F+3)/4) (k-block, j-quad) pairs + one warp for dL/db1
+constexpr int GHW_ROWS = 64;
+constexpr int GHW_STAGES = 3;
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(GHW_MAX_THREADS) gaussian_heads_backward_weights_kernel(
+    long long n, int F, const float* __restrict__ feat, const float* __restrict__ rgb,
+    const float* __restrict__ g_hidden /*[n,16]*/, float* __restrict__ g_w1t, float* __restrict__ g_b1) {
+  extern __shared__ __align__(128) float s_mem[];
+  const int XP = F + 4;                                   // row pitch: [feat F | rgb 3 | 0]
+  const int stage_floats = GHW_ROWS * (XP + GH_HID);
+  const int tid = threadIdx.x;
+  const int kb = tid >> 2, jq = tid & 3;
+  const int kblocks = (F + 3 + 3) / 4;
+  const bool owner = kb < kblocks;
+  // the pad column F+3 of every x row is never written by the copies: zero it once
+  for (int i = tid; i < GHW_STAGES * GHW_ROWS; i += (int)blockDim.x)
+    s_mem[(i / GHW_ROWS) * stage_floats + (i % GHW_ROWS) * XP + F + 3] = 0.f;
+
+  const long long tiles = (n + GHW_ROWS - 1) / GHW_ROWS;
+  const long long my_tiles = tiles > blockIdx.x ? (tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  long long pf = 0;
+  const int f4 = F / 4;
+  auto issue = [&]() {
+    if (pf < my_tiles) {
+      const long long base = (blockIdx.x + pf * gridDim.x) * GHW_ROWS;
+      const int rows = (int)min((long long)GHW_ROWS, n - base);
+      float* sx = s_mem + (int)(pf % GHW_STAGES) * stage_floats;
+      float* sg = sx + GHW_ROWS * XP;
+      // features: lane = 16-byte column chunk, one row per warp per iteration (no integer division in the loop)
+      for (int c0 = 0; c0 < f4; c0 += 32) {
+        const int col = c0 + (tid & 31);
+        if (col < f4) {
+#pragma unroll 4
+          for (int row = tid >> 5; row < GHW_ROWS; row += (int)(blockDim.x >> 5)) {
+            const bool ok = row < rows;
+            cp_async16(sx + row * XP + 4 * col, ok ? feat + (base + row) * F + 4 * col : feat, ok ? 16u : 0u);
+          }
+        }
+      }
+#pragma unroll
+      for (int c = tid; c < GHW_ROWS * 4; c += (int)blockDim.x) {           // dL/dhidden: 4 chunks per row
+        const int row = c >> 2, col = c & 3;
+        const bool ok = row < rows;
+        cp_async16(sg + row * GH_HID + 4 * col, ok ? g_hidden + (base + row) * GH_HID + 4 * col : g_hidden, ok ? 16u : 0u);
+        if (col < 3)                                                     // rgb: 4-byte copies into columns F..F+2
+          cp_async4(sx + row * XP + F + col, ok ? rgb + (base + row) * 3 + col : rgb, ok ? 4u : 0u);
+      }
+      pf++;
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int st = 0; st < GHW_STAGES - 1; st++) issue();
+
+  float acc[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; a++)
+#pragma unroll
+    for (int b = 0; b < 4; b++) acc[a][b] = 0.f;
+  float bsum = 0.f;  // dL/db1[lane], kept by the last warp of the CTA (the host adds it after the owner warps)
+
+  for (long long t = 0; t < my_tiles; t++) {
+    cp_async_wait<GHW_STAGES - 2>();
+    __syncthreads();
+    issue();
+    const float* sx = s_mem + (int)(t % GHW_STAGES) * stage_floats;
+    const float* sg = sx + GHW_ROWS * XP;
+    if (owner) {
+      const float* xp = sx + 4 * kb;
+      const float* gp = sg + 4 * jq;
+#pragma unroll 4
+      for (int r = 0; r < GHW_ROWS; r++) {   // rows past the end of the last tile are zero-filled
+        const float4 x = *reinterpret_cast<const float4*>(xp + r * XP);
+        const float4 g = *reinterpret_cast<const float4*>(gp + r * GH_HID);
+        acc[0][0] = fmaf(x.x, g.x, acc[0][0]); acc[0][1] = fmaf(x.x, g.y, acc[0][1]);
+        acc[0][2] = fmaf(x.x, g.z, acc[0][2]); acc[0][3] = fmaf(x.x, g.w, acc[0][3]);
+        acc[1][0] = fmaf(x.y, g.x, acc[1][0]); acc[1][1] = fmaf(x.y, g.y, acc[1][1]);
+        acc[1][2] = fmaf(x.y, g.z, acc[1][2]); acc[1][3] = fmaf(x.y, g.w, acc[1][3]);
+        acc[2][0] = fmaf(x.z, g.x, acc[2][0]); acc[2][1] = fmaf(x.z, g.y, acc[2][1]);
+        acc[2][2] = fmaf(x.z, g.z, acc[2][2]); acc[2][3] = fmaf(x.z, g.w, acc[2][3]);
+        acc[3][0] = fmaf(x.w, g.x, acc[3][0]); acc[3][1] = fmaf(x.w, g.y, acc[3][1]);
+        acc[3][2] = fmaf(x.w, g.z, acc[3][2]); acc[3][3] = fmaf(x.w, g.w, acc[3][3]);
+      }
+    } else if (tid >= (int)blockDim.x - 32 && (tid & 31) < GH_HID) {  // dL/db1: one hidden unit per lane of the last warp
+      const float* gp = sg + (tid & 31);
+      float b = 0.f;
+#pragma unroll 8
+      for (int r = 0; r < GHW_ROWS; r++) b += gp[r * GH_HID];
+      bsum += b;
+    }
+  }
+  cp_async_wait<0>();
+  if (owner) {
+#pragma unroll
+    for (int a = 0; a < 4; a++) {
+      const int k = 4 * kb + a;
+      if (k >= F + 3) continue;
+#pragma unroll
+      for (int b = 0; b < 4; b++) {
+        const int j = 4 * jq + b;
+        const bool structural_zero = k >= F && j < 12;  // the S/R/A heads do not see rgb
+        if (!structural_zero && acc[a][b] != 0.f) atomicAdd(g_w1t + k * GH_HID + j, acc[a][b]);
+      }
+    }
+  } else if (tid >= (int)blockDim.x - 32 && (tid & 31) < GH_HID) {
+    atomicAdd(g_b1 + (tid & 31), bsum);
+  }
+}
+
 }  // namespace ocrf
 
 using namespace ocrf;
@@ -624,24 +896,52 @@ extern "C" int ocrf_gaussian_heads_forward(void* stream, int64_t n, int32_t F, c
   return 0;
 }
 
+extern "C" size_t ocrf_gaussian_heads_backward_workspace_bytes(int64_t n) {
+  return (size_t)(n > 0 ? n : 1) * GH_HID * sizeof(float) + 128;
+}
+
 extern "C" int ocrf_gaussian_heads_backward(void* stream, int64_t n, int32_t F, const float* feat, const float* rgb,
                                             const float* w1t, const float* w2, const float* b2, const float* hidden,
                                             const float* g_opacity, const float* g_scales, const float* g_rotations,
                                             const float* g_colors, float* g_feat, float* g_w1t, float* g_b1,
-                                            float* g_w2, float* g_b2) {
+                                            float* g_w2, float* g_b2, void* ws) {
   if (n < 0 || F <= 0 || F + 3 > GH_MAXK) return OCRF_EINVAL;
   if (n == 0) return 0;
   if (!feat || !rgb || !w1t || !w2 || !b2 || !hidden || !g_opacity || !g_scales || !g_rotations || !g_colors || !g_feat ||
       !g_w1t || !g_b1 || !g_w2 || !g_b2)
     return OCRF_EINVAL;
   if (!gh_aligned16(g_rotations) || !gh_aligned16(hidden)) return OCRF_EINVAL;
-  const size_t smem = gh_bwd_smem(F);
-  cudaError_t e = cudaFuncSetAttribute(gaussian_heads_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return (int)e;
-  const int fast = (F % 4 == 0) && gh_aligned16(feat) && gh_aligned16(g_feat);
-  gaussian_heads_backward_kernel<<<gh_grid(n, smem), GH_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-      n, F, fast, feat, rgb, w1t, w2, b2, hidden, g_opacity, g_scales, g_rotations, g_colors, g_feat, g_w1t, g_b1,
-      g_w2, g_b2);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if ((F % 4 == 0) && gh_aligned16(feat) && gh_aligned16(g_feat) && ws != nullptr && gh_aligned16(ws)) {
+    float* g_hidden = static_cast<float*>(ws);
+    const int ns = (F + GH_KS - 1) / GH_KS;
+    const size_t smem1 = ((size_t)2 * GH_STAGE_FLOATS + (size_t)ns * GH_KS * GH_HID + GH_OUT * 4 + 12) * 4;
+    cudaError_t e = cudaFuncSetAttribute(gaussian_heads_backward_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)smem1);
+    if (e != cudaSuccess) return (int)e;
+    const long long tiles1 = (n + GH_ROWS - 1) / GH_ROWS;
+    const long long cap1 = (long long)NUM_SMS * 8;  // residency of the rows kernel: 128 registers x 64 threads, 26 KB
+    gaussian_heads_backward_rows_kernel<<<(unsigned)(tiles1 < cap1 ? tiles1 : cap1), GH_THREADS, smem1, st>>>(
+        n, F, w1t, w2, b2, hidden, g_opacity, g_scales, g_rotations, g_colors, g_hidden, g_feat, g_w2, g_b2);
+    const size_t smem2 = (size_t)GHW_STAGES * GHW_ROWS * (F + 4 + GH_HID) * 4;
+    e = cudaFuncSetAttribute(gaussian_heads_backward_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2);
+    if (e != cudaSuccess) return (int)e;
+    const long long tiles2 = (n + GHW_ROWS - 1) / GHW_ROWS;
+    const int per_sm = (int)((220 * 1024) / (smem2 + 1024));
+    const long long cap = (long long)NUM_SMS * (per_sm < 1 ? 1 : per_sm);
+    const int owner_threads = 4 * ((F + 3 + 3) / 4);
+    const int threads2 = ((owner_threads + 31) / 32) * 32 + 32;  // + the dL/db1 warp
+    gaussian_heads_backward_weights_kernel<<<(unsigned)(tiles2 < cap ? tiles2 : cap), threads2, smem2, st>>>(
+        n, F, feat, rgb, g_hidden, g_w1t, g_b1);
+  } else {  // odd channel counts / unaligned views / no workspace: the single fused kernel with whole-row tiles
+    const size_t smem = gh_bwd_smem(F);
+    cudaError_t e = cudaFuncSetAttribute(gaussian_heads_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    const int fast = (F % 4 == 0) && gh_aligned16(feat) && gh_aligned16(g_feat);
+    gaussian_heads_backward_kernel<<<gh_grid(n, smem), GH_THREADS, smem, st>>>(
+        n, F, fast, feat, rgb, w1t, w2, b2, hidden, g_opacity, g_scales, g_rotations, g_colors, g_feat, g_w1t, g_b1,
+        g_w2, g_b2);
+  }
   OCRF_CHECK_LAST();
   return 0;
 }

@@ -89,12 +89,13 @@ class _GaussianHeadsFn(torch.autograd.Function):
         g_feat = torch.empty_like(feat)
         g_packed = torch.zeros_like(packed)
         gv = _views(g_packed, Fd)
+        ws = torch.empty(L.ocrf_gaussian_heads_backward_workspace_bytes(n), dtype=torch.uint8, device=feat.device)
         _lib.check(L.ocrf_gaussian_heads_backward(_lib.current_stream(), n, Fd, _lib.ptr(feat), _lib.ptr(rgb),
                                                   _lib.ptr(v["w1t"]), _lib.ptr(v["w2"]), _lib.ptr(v["b2"]),
                                                   _lib.ptr(hidden), _lib.ptr(g_opacity), _lib.ptr(g_scales),
                                                   _lib.ptr(g_rotations), _lib.ptr(g_colors), _lib.ptr(g_feat),
                                                   _lib.ptr(gv["w1t"]), _lib.ptr(gv["b1"]), _lib.ptr(gv["w2"]),
-                                                  _lib.ptr(gv["b2"])), "ocrf_gaussian_heads_backward")
+                                                  _lib.ptr(gv["b2"]), _lib.ptr(ws)), "ocrf_gaussian_heads_backward")
         return g_feat, None, g_packed
 
 

@@ -99,8 +99,9 @@ def main():
     def k_bwd():
         _lib.check(L.ocrf_gaussian_heads_backward(_lib.current_stream(), n4, Fd, P(f4), P(r4), P(v["w1t"]), P(v["w2"]),
                                                   P(v["b2"]), P(outs[4]), P(g4[0]), P(g4[1]), P(g4[2]), P(g4[3]), P(gf),
-                                                  P(gv["w1t"]), P(gv["b1"]), P(gv["w2"]), P(gv["b2"])), "bwd")
+                                                  P(gv["w1t"]), P(gv["b1"]), P(gv["w2"]), P(gv["b2"]), P(ws4)), "bwd")
 
+    ws4 = torch.empty(L.ocrf_gaussian_heads_backward_workspace_bytes(n4), dtype=torch.uint8, device=dev)
     tiny = torch.empty(1, device=dev)
     res["kernel_fwd_ms_4samples"] = timeit(k_fwd, tiny)
     res["kernel_bwd_ms_4samples"] = timeit(k_bwd, tiny)
