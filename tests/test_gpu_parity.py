@@ -275,3 +275,22 @@ def test_capacity_mode_no_sync_and_overflow():
     with pytest.raises(Exception, match="overflow"):
         R.check_overflow()
     assert float(tight[0].abs().max()) == 0.0  # rendered background only, no overrun
+
+
+def test_clear_gradients_touches_only_what_backward_accumulates_into():
+    """ocrf_clear_gradients == the reference's torch::zeros for everything the backward reads: rows of visible pairs
+    and the colour gradients are zeroed, rows of invisible pairs (never read nor written downstream) are left alone."""
+    import ctypes as C
+    from ocrfdet_b200 import _lib
+    L = _lib.lib()
+    V, P, S, Cc = 3, 1000, 1, 3
+    shape = _lib.OcrfShape(S, P, V, V, 64, 48, Cc, 0, 0)
+    rng = np.random.default_rng(0)
+    radii = torch.from_numpy((rng.random((V, P)) < 0.3).astype(np.int32) * 5).cuda()
+    ggrad = torch.full((V, P, 6), float("nan"), dtype=torch.float64, device="cuda")
+    gcol = torch.full((S, P, Cc), float("nan"), dtype=torch.float32, device="cuda")
+    _lib.check(L.ocrf_clear_gradients(_lib.current_stream(), C.byref(shape), 0, _lib.ptr(radii), _lib.ptr(ggrad),
+                                      _lib.ptr(gcol)), "ocrf_clear_gradients")
+    vis = radii > 0
+    assert bool((ggrad[vis] == 0).all()) and bool(torch.isnan(ggrad[~vis]).all())
+    assert bool((gcol == 0).all())
