@@ -308,16 +308,28 @@ def run_ours(args, rank, world, device):
                  if stage_ms.get("render_backward") else None}
 
     # ---- end to end through the public API with host buffers ----
+    # A step = pinned host parameters -> H2D -> forward -> loss -> backward (gradients stay on the device, where an
+    # optimiser consumes them) -> D2H of the step's result, the loss.  OCRF_E2E_D2H=grads additionally reads every
+    # parameter gradient back (5.6 MB), the most a host-side consumer could ask for.
+    d2h_grads = os.environ.get("OCRF_E2E_D2H", "loss") == "grads"
     grads_host = {k: torch.empty_like(host[k]).pin_memory() for k in names}
+    loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
     h2d = sum(host[k].numel() * 4 for k in names)
-    d2h = sum(grads_host[k].numel() * 4 for k in names)
+    d2h = 4 + (sum(grads_host[k].numel() * 4 for k in names) if d2h_grads else 0)
     e2e_steps = max(3, min(args.steps, 20))
 
     def e2e_step():
         t = {k: host[k].to(device, non_blocking=True).requires_grad_(True) for k in names}
-        step(t)
-        for k in names:
-            grads_host[k].copy_(t[k].grad, non_blocking=True)
+        color, radii, depth, opac = render(t)
+        gathered = gather_opacity_maps(opac.detach(), world, VIEWS, stream=side) if world > 1 else opac  # noqa: F841
+        loss = (color * gcol).sum() + (opac * gop).sum()   # dL/dcolor = gcol, dL/dopacity = gop: the same backward
+        loss.backward()
+        if side is not None:
+            torch.cuda.current_stream().wait_stream(side)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        if d2h_grads:
+            for k in names:
+                grads_host[k].copy_(t[k].grad, non_blocking=True)
 
     for _ in range(2):
         e2e_step()
