@@ -584,7 +584,7 @@ __global__ void __launch_bounds__(GH_THREADS) gaussian_heads_backward_kernel(
 //              through a double-buffered shared-memory slice as coalesced 16-byte stores.  The features themselves are
 //              not needed here, so there is no 43 KB tile and 8 CTAs (16 warps) fit per SM.  The 71 small parameter
 //              sums (w2, b2, b1) are reduce-scattered over the warp once per tile and kept in two registers per lane.
-// (2) weights: dL/dw1t[k][j] = sum_n x[n][k] * dL/dhidden[n][j], a [F+3, n] x [n, 16] product streamed through a 3-deep
+// (2) weights: dL/dw1t[k][j] = sum_n x[n][k] * dL/dhidden[n][j], a [F+3, n] x [n, 16] product streamed through a 2-deep
 //              cp.async ring of 64-row tiles; thread (k-block, j-quad) owns a 4 x 4 block of the result in registers for
 //              the whole kernel (two LDS.128 feed 16 FFMAs), one atomicAdd per parameter per CTA at the end.
 constexpr int GHB_PITCH = 57;  // 44 (w2) + 11 (b2) per thread, odd pitch: conflict-free rows and columns
@@ -736,8 +736,14 @@ __global__ void __launch_bounds__(GH_THREADS) gaussian_heads_backward_rows_kerne
 }
 
 constexpr int GHW_MAX_THREADS = 160;  // owner warps for the 4 * ceil((F+3)/4) (k-block, j-quad) pairs + one warp for dL/db1
-constexpr int GHW_ROWS = 64;
-constexpr int GHW_STAGES = 3;
+#ifndef OCRF_GHW_ROWS
+#define OCRF_GHW_ROWS 64
+#endif
+#ifndef OCRF_GHW_STAGES
+#define OCRF_GHW_STAGES 2
+#endif
+constexpr int GHW_ROWS = OCRF_GHW_ROWS;
+constexpr int GHW_STAGES = OCRF_GHW_STAGES;
 
 __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src, uint32_t src_bytes) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(src_bytes)

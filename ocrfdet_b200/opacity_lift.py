@@ -65,3 +65,17 @@ class OpacityMask(nn.Module):
 
     def forward(self, x, opacity_bev):
         return opacity_mask(x, self.conv.weight, opacity_bev)[0]
+
+
+class GeomAttentionGate(nn.Module):
+    """`BEVGeomAttention` (view_transformer_ocrf.py:215-228) followed by its gating multiply (:1190,
+    `geom_feat = self.geom_att(channel_feat, bev_mask_logit) * channel_feat`): the same arithmetic as the opacity
+    mask with the BEV-mask logit in place of the opacity logit, so it is the same fused op.  The parameter keeps the
+    reference's name (`conv1.weight` [1,2,7,7], no bias): `geom_att.*` checkpoint entries load unchanged."""
+
+    def __init__(self, kernel_size=7):
+        super().__init__()
+        self.conv1 = nn.Conv2d(2, 1, kernel_size, padding=kernel_size // 2, bias=False)  # parameters only
+
+    def forward(self, x, bev_prob):
+        return opacity_mask(x, self.conv1.weight, bev_prob)[0]

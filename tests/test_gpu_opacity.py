@@ -36,6 +36,28 @@ def test_opacity_mask_forward_backward(B, C, H, W, K):
     assert float((ref_out - out).abs().max()) <= 1e-5 * (1 + float(ref_out.abs().max()))
 
 
+def test_geom_attention_gate_is_the_same_fused_op():
+    """BEVGeomAttention + its multiply (view_transformer_ocrf.py:215-228, 1190) through GeomAttentionGate."""
+    from ocrfdet_b200.opacity_lift import GeomAttentionGate
+    torch.manual_seed(3)
+    B, C, H, W = 2, 80, 128, 128
+    gate = GeomAttentionGate().cuda()
+    assert list(gate.state_dict()) == ["conv1.weight"]
+    x = torch.randn(B, C, H, W, device="cuda", requires_grad=True)
+    logit = torch.randn(B, 1, H, W, device="cuda", requires_grad=True)
+    out = gate(x, logit)
+    # float64 torch formulation (cuDNN's float32 convolutions run in TF32 on this GPU)
+    x2, l2 = x.detach().double().requires_grad_(True), logit.detach().double().requires_grad_(True)
+    s = torch.cat([x2.mean(1, keepdim=True), x2.max(1, keepdim=True)[0]], 1)
+    ref = torch.sigmoid(torch.nn.functional.conv2d(s, gate.conv1.weight.detach().double(), padding=3) + l2) * x2
+    assert float((out.detach() - ref.detach()).abs().max()) <= 1e-5 * (1 + float(ref.abs().max()))
+    g = torch.randn_like(out)
+    out.backward(g)
+    ref.backward(g.double())
+    assert util.rel_err(x.grad.cpu().numpy(), x2.grad.cpu().numpy()) <= 1e-4
+    assert util.rel_err(logit.grad.cpu().numpy(), l2.grad.cpu().numpy()) <= 1e-4
+
+
 def test_dropin_render_wrapper_call_sequence():
     """Exactly what gaussian_renderer/__init__.py:17-75 does, against the import name it uses."""
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
