@@ -202,6 +202,11 @@ def run_ours(args, rank, world, device):
         launches_per_step = 1 + (1 + vis_passes) + 1 + 4 + 4
 
     # ---- device-resident throughput ----
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()  # NVML initialisation takes milliseconds and differs per rank: keep it out of the timed region
+    import gc
+    gc.collect()
+    gc.disable()  # no collector pauses on the launching thread inside the timed region (N ranks wait for the slowest)
     if world > 1:
         # settle: a few flushed steps with the collective, so that lazy NCCL channel setup and rank skew are not
         # inside the timed region (untimed, in addition to the --warmup steps above)
@@ -211,8 +216,7 @@ def run_ours(args, rank, world, device):
         torch.cuda.synchronize()
         dist.barrier()
     torch.cuda.synchronize()
-    sampler = ClockSampler(torch.cuda.current_device())
-    sampler.start()
+    sampler.sm, sampler.bits = [], 0  # keep only the samples of the timed region
     evs = []
     for _ in range(args.steps):
         flush.fill_(1)  # evict L2 (126 MB) before every timed step; not timed
@@ -222,10 +226,12 @@ def run_ours(args, rank, world, device):
         e1.record()
         evs.append((e0, e1))
     torch.cuda.synchronize()
+    gc.enable()
     clocks = sampler.stop()
     if world > 1:
         dist.barrier()
-    per_step = sorted(a.elapsed_time(b) for a, b in evs)
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    per_step = sorted(step_ms)
     total_ms = sum(per_step)
     median_ms = per_step[len(per_step) // 2]
     if world > 1:
@@ -359,6 +365,7 @@ def run_ours(args, rank, world, device):
 
     out = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_per_step_median_rank0": median_ms,
+           "ms_per_step_max_rank0": per_step[-1], "ms_steps_rank0": [round(x, 3) for x in step_ms],
            "ms_per_render": ms_per_step / VIEWS,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "BASELINE config 2: 1 sample x 6 views 256x704, 100k voxel-grid Gaussians, "
@@ -437,6 +444,9 @@ def run_reference(args, rank, world, device):
     torch.cuda.synchronize()
     sampler = ClockSampler(torch.cuda.current_device())
     sampler.start()
+    import gc
+    gc.collect()
+    gc.disable()  # no collector pauses on the launching thread inside the timed region (N ranks wait for the slowest)
     evs = []
     for _ in range(args.steps):
         flush.fill_(1)
@@ -446,6 +456,7 @@ def run_reference(args, rank, world, device):
         e1.record()
         evs.append((e0, e1))
     torch.cuda.synchronize()
+    gc.enable()
     clocks = sampler.stop()
     ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
     value = VIEWS / (ms / 1e3)
