@@ -324,11 +324,14 @@ def run_ours(args, rank, world, device):
     d2h = 4 + (sum(grads_host[k].numel() * 4 for k in names) if d2h_grads else 0)
     e2e_steps = max(3, min(args.steps, 20))
 
+    gcol_flat, gop_flat = gcol.reshape(-1), gop.reshape(-1)
+
     def e2e_step():
         t = {k: host[k].to(device, non_blocking=True).requires_grad_(True) for k in names}
         color, radii, depth, opac = render(t)
         gathered = gather_opacity_maps(opac.detach(), world, VIEWS, stream=side) if world > 1 else opac  # noqa: F841
-        loss = (color * gcol).sum() + (opac * gop).sum()   # dL/dcolor = gcol, dL/dopacity = gop: the same backward
+        # dL/dcolor = gcol, dL/dopacity = gop: the same backward as the device-resident step
+        loss = torch.dot(color.reshape(-1), gcol_flat) + torch.dot(opac.reshape(-1), gop_flat)
         loss.backward()
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
