@@ -47,7 +47,11 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="run a few untimed steps and exit (for ncu)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if not args.profile_only:
+        args.warmup = max(3, args.warmup)  # timing rule: at least three warm-up steps (the JSON line reports the value used)
+        args.steps = max(1, args.steps)
+    return args
 
 
 class ClockSampler:
