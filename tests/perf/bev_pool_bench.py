@@ -1,6 +1,6 @@
 """BEV pooling v2 at the OcRFDet training shape (8 samples x 6 cameras, D=88, 16x44 features, C=80, 128x128 BEV):
 ours (C ABI through ocrfdet_b200.bev_pool) against the reference's own CUDA kernels (oracle/_ref/libbevpool_ref.so,
-with the reference's Python regrouping before its backward).  python tools/bev_pool_bench.py"""
+with the reference's Python regrouping before its backward).  python tests/perf/bev_pool_bench.py"""
 import json
 import os
 import sys
@@ -8,7 +8,7 @@ import sys
 import numpy as np
 import torch
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from ocrfdet_b200.bev_pool import QuickCumsumCuda  # noqa: E402
 from ocrfdet_b200.scenes import bev_pool_case  # noqa: E402
 from oracle import ref  # noqa: E402
