@@ -346,10 +346,13 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
 class GaussianRasterizer(nn.Module):
     """PKG:171-220."""
 
-    def __init__(self, raster_settings, return_opacity=False):
+    def __init__(self, raster_settings, return_opacity=False, return_depth=True):
+        """`return_depth=False` gives the vendored package's 2-tuple `(color, radii)` (PKG:98, used by
+        MVSGaussian's `gaussian_renderer_ft`); the default is the live w-depth fork's `(color, radii, depth)`."""
         super().__init__()
         self.raster_settings = raster_settings
         self.return_opacity = return_opacity
+        self.return_depth = return_depth
 
     def markVisible(self, positions):
         # PKG:176-185 -> rasterizer_impl.cu:141-152
@@ -372,8 +375,9 @@ class GaussianRasterizer(nn.Module):
         if ((scales is None or rotations is None) and cov3D_precomp is None) or \
                 ((scales is not None or rotations is not None) and cov3D_precomp is not None):
             raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
-        return rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
-                                   self.raster_settings, return_opacity=self.return_opacity)
+        out = rasterize_gaussians(means3D, means2D, shs, colors_precomp, opacities, scales, rotations, cov3D_precomp,
+                                  self.raster_settings, return_opacity=self.return_opacity)
+        return out if self.return_depth else out[:2] + out[3:]
 
 
 def check_overflow():

@@ -58,6 +58,22 @@ def test_geom_attention_gate_is_the_same_fused_op():
     assert util.rel_err(logit.grad.cpu().numpy(), l2.grad.cpu().numpy()) <= 1e-4
 
 
+def test_two_tuple_flavour_of_the_vendored_package():
+    """`rendered_image, radii = rasterizer(...)` as MVSGaussian's gaussian_renderer_ft unpacks it (PKG:98)."""
+    from diff_gaussian_rasterization import GaussianRasterizer
+    W, H = 96, 48
+    g, cams = util.small_scene("frustum", P=500, seed=3, W=W, H=H)
+    gc = util.to_cuda(g)
+    st = util.settings_for(cams[0], [0.0, 0.0, 0.0])
+    kw = dict(means3D=gc["means3D"], means2D=torch.zeros_like(gc["means3D"]), opacities=gc["opacities"],
+              colors_precomp=gc["colors"], scales=gc["scales"], rotations=gc["rotations"])
+    image, radii = GaussianRasterizer(st, return_depth=False)(**kw)
+    image3, radii3, depth3 = GaussianRasterizer(st)(**kw)
+    assert torch.equal(image, image3) and torch.equal(radii, radii3) and tuple(depth3.shape) == (1, H, W)
+    image4, radii4, opacity4 = GaussianRasterizer(st, return_depth=False, return_opacity=True)(**kw)
+    assert torch.equal(image4, image3) and tuple(opacity4.shape) == (1, H, W)
+
+
 def test_dropin_render_wrapper_call_sequence():
     """Exactly what gaussian_renderer/__init__.py:17-75 does, against the import name it uses."""
     from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer

@@ -1,3 +1,2 @@
 set -x
-python -c "import __graft_entry__ as g; g.build(); g.smoke(); print('smoke ok')" 2>&1 | tail -2
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 900 python -m pytest tests/test_gpu_opacity.py -x -q 2>&1 | tail -3
