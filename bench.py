@@ -147,9 +147,10 @@ def run_ours(args, rank, world, device):
 
     cap = {"n": None}  # None: exact sizing (one 8-byte read-back per batch); int: sync-free capacity mode
 
-    def render(t):
+    def render(t, colors_ready=None):
         return R.render_batch(t["means3D"], t["opacities"], cam_t, H, W, bg, colors_precomp=t["colors"],
-                              scales=t["scales"], rotations=t["rotations"], pair_capacity=cap["n"])
+                              scales=t["scales"], rotations=t["rotations"], pair_capacity=cap["n"],
+                              colors_ready=colors_ready)
 
     def step(t=dev):
         for k in names:
@@ -330,9 +331,19 @@ def run_ours(args, rank, world, device):
 
     gcol_flat, gop_flat = gcol.reshape(-1), gop.reshape(-1)
 
+    copy_stream = torch.cuda.Stream()
+
     def e2e_step():
-        t = {k: host[k].to(device, non_blocking=True).requires_grad_(True) for k in names}
-        color, radii, depth, opac = render(t)
+        # geometry first on the launching stream; the colours -- first read by the binning stage -- follow on a second
+        # stream, so their copy runs under the preprocess and the depth sort (render_batch(colors_ready=...))
+        t = {k: host[k].to(device, non_blocking=True).requires_grad_(True) for k in names if k != "colors"}
+        with torch.cuda.stream(copy_stream):
+            col = host["colors"].to(device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(copy_stream)
+        col.record_stream(torch.cuda.current_stream())
+        t["colors"] = col.requires_grad_(True)
+        color, radii, depth, opac = render(t, colors_ready=ready)
         gathered = gather_opacity_maps(opac.detach(), world, VIEWS, stream=side) if world > 1 else opac  # noqa: F841
         # dL/dcolor = gcol, dL/dopacity = gop: the same backward as the device-resident step
         loss = torch.dot(color.reshape(-1), gcol_flat) + torch.dot(opac.reshape(-1), gop_flat)

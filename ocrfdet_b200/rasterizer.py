@@ -112,6 +112,8 @@ class _RasterizeBatch(torch.autograd.Function):
         shape = OcrfShape(S, P, V, V // S, W, H, Cc, cfg["sh_degree"], shs.shape[2] if use_sh else 0)
         dev = means3D.device
         stream = current_stream()
+        if use_sh and cfg.get("colors_ready") is not None:
+            torch.cuda.current_stream().wait_event(cfg["colors_ready"])
         ws = _Workspaces(shape, use_sh)
         radii = torch.empty((V, P), dtype=torch.int32, device=dev)
         geom = torch.empty(ws.geom.total, dtype=torch.uint8, device=dev)
@@ -125,6 +127,8 @@ class _RasterizeBatch(torch.autograd.Function):
                                         C.c_float(cfg["scale_modifier"]), int(cfg["prefiltered"]), ptr(radii),
                                         ptr(geom)), "ocrf_preprocess_forward")
         _stage("preprocess")
+        if cfg.get("colors_ready") is not None and not use_sh:   # SH coefficients are read by the preprocess itself
+            torch.cuda.current_stream().wait_event(cfg["colors_ready"])
         capacity = cfg.get("pair_capacity")
         if capacity is None:
             # exact sizing: one 8-byte read-back per BATCH (the reference syncs once per view,
@@ -273,7 +277,7 @@ def last_state(reference_lists=False):
 
 def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors_precomp=None, shs=None, scales=None,
                  rotations=None, cov3D_precomp=None, means2D=None, scale_modifier=1.0, sh_degree=0, prefiltered=False,
-                 pair_capacity: Optional[int] = None, binning: Optional[str] = None):
+                 pair_capacity: Optional[int] = None, binning: Optional[str] = None, colors_ready=None):
     """Render V = cams.shape[0] views of S = means3D.shape[0] samples in one launch sequence.
 
     means3D [S,P,3]; opacities [S,P,1]; colors_precomp [S,P,C] or shs [S,P,M,3]; scales [S,P,3] and
@@ -284,6 +288,9 @@ def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors
     tile writing the culled records directly (default; the pair lists are not materialised); "depthfirst" = same
     depth sort, pairs emitted in depth order, tile bits sorted (2 passes); "pairsort" = the reference's algorithm
     (sort every (tile | depth) pair).  All three give bit-identical records, range tables and images.
+    `colors_ready`: optional `torch.cuda.Event`; colours / SH coefficients are first read by the binning stage, so a
+    caller that uploads them on another stream can let that copy run under the preprocess and the depth sort: the
+    launching stream waits for the event only after the preprocess has been queued.
     `pair_capacity`: if given, the binning workspace is sized for that many (tile, Gaussian) pairs
     and NO host synchronisation happens (CUDA-graph friendly); an overflow renders background and
     raises on the next `check_overflow`.
@@ -304,7 +311,7 @@ def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors
     if means2D is None:  # gradient holder only, never read: no fill, and no dL/dmean2D output in backward
         means2D = torch.empty((V, P, 3), dtype=torch.float32, device=means3D.device)
     cfg = dict(W=int(image_width), H=int(image_height), scale_modifier=float(scale_modifier), sh_degree=int(sh_degree),
-               prefiltered=bool(prefiltered), pair_capacity=pair_capacity,
+               prefiltered=bool(prefiltered), pair_capacity=pair_capacity, colors_ready=colors_ready,
                binning=binning if binning is not None else os.environ.get("OCRF_BINNING", "split"))
     if P == 0:
         Cc = 3 if shs is not None else colors_precomp.shape[-1]

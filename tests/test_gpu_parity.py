@@ -294,3 +294,28 @@ def test_clear_gradients_touches_only_what_backward_accumulates_into():
     vis = radii > 0
     assert bool((ggrad[vis] == 0).all()) and bool(torch.isnan(ggrad[~vis]).all())
     assert bool((gcol == 0).all())
+
+
+def test_colors_ready_event_late_binds_the_colour_upload():
+    """render_batch(colors_ready=event): colours uploaded on a second stream while the preprocess runs."""
+    W, H, P = 176, 64, 5000
+    g, cams = util.small_scene("ring", P=P, seed=61, W=W, H=H, n_views=3)
+    cam_t = util.cams_tensor(cams)
+    gc = util.to_cuda(g)
+    bg = torch.zeros(3, device="cuda")
+    kw = dict(scales=gc["scales"].unsqueeze(0), rotations=gc["rotations"].unsqueeze(0))
+    want = R.render_batch(gc["means3D"].unsqueeze(0), gc["opacities"].unsqueeze(0), cam_t, H, W, bg,
+                          colors_precomp=gc["colors"].unsqueeze(0), **kw)
+    host_col = torch.from_numpy(g["colors"]).unsqueeze(0).pin_memory()
+    side = torch.cuda.Stream()
+    torch.cuda.synchronize()
+    with torch.cuda.stream(side):
+        torch.cuda._sleep(20_000_000)          # the upload is still in flight when render_batch is called
+        col = host_col.to("cuda", non_blocking=True)
+        ready = torch.cuda.Event()
+        ready.record(side)
+    col.record_stream(torch.cuda.current_stream())
+    got = R.render_batch(gc["means3D"].unsqueeze(0), gc["opacities"].unsqueeze(0), cam_t, H, W, bg, colors_precomp=col,
+                         colors_ready=ready, **kw)
+    for a, b in zip(want, got):
+        assert torch.equal(a, b)
