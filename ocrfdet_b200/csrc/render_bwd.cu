@@ -248,6 +248,7 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
 // the CP colour gradients 16 at a time (16 shuffles per 16 channels instead of 80) and issues one
 // 64-byte-contiguous global reduction per 16 channels; geometry gradients follow the C = 3 scheme.
 constexpr int BWDG_BATCH = 64;
+constexpr int BWDG_FB = 16;  // records per cross-warp reduction of the feature gradients
 
 // reduce-scatter of 16 values: afterwards lane L holds the warp total of value (L >> 1) & 15 (both lanes of a pair)
 __device__ __forceinline__ float butterfly16(const float* v, int lane) {
@@ -275,7 +276,7 @@ __device__ __forceinline__ float butterfly16(const float* v, int lane) {
 }
 
 template <int CP>
-__global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
+__global__ void __launch_bounds__(TILE_PIX, CP <= 80 ? 2 : 1) render_backward_generic_kernel(
     int W, int H, int C, int P, int views_per_sample, const uint2* __restrict__ ranges /* culled lists */,
     const Record* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
     const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
@@ -286,6 +287,7 @@ __global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
   Record* s_rec = reinterpret_cast<Record*>(smem_g);                                   // [BATCH]
   float* s_feat = reinterpret_cast<float*>(smem_g + BWDG_BATCH * sizeof(Record));      // [BATCH][CP]
   float* s_acc = s_feat + BWDG_BATCH * CP;                                             // [NW][BATCH][8]
+  float* s_facc = s_acc + NW * BWDG_BATCH * 8;                                         // [NW][BWDG_FB][CP] feature-gradient rows
   __shared__ uint32_t s_touched[NW][BWDG_BATCH / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -307,14 +309,17 @@ __global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
   const float fx = (float)px, fy = (float)py;
   const float Tf = inside ? final_T[view * HW + pix] : 0.f;
   const int nc = inside ? (int)n_contrib[view * HW + pix] : 0;
-  float g[CP], A[CP];
+  float g[CP];
   float bgdot = 0.f;
 #pragma unroll
   for (int k = 0; k < CP; k++) {
     g[k] = (inside && k < C) ? dL_dpix[((size_t)view * C + k) * HW + pix] : 0.f;
-    A[k] = 0.f;
     bgdot += (k < C ? bg[k] : 0.f) * g[k];
   }
+  // g . (colour accumulated behind this pixel): the reference keeps the accumulated colour per channel
+  // (backward.cu:480-490) and dots it with dL/dpixel; the dot product obeys the same linear recurrence, so one scalar
+  // replaces C registers and C multiply-adds per (pixel, Gaussian)
+  float S = 0.f;
   const float gop = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
   const float gob = Tf * (gop - bgdot);
   float T = Tf;
@@ -359,7 +364,8 @@ __global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
         }
         const uint32_t id = s_rec[j].id;
         const float* fj = s_feat + j * CP;
-        float dot = 0.f;
+        float dsum = 0.f;  // g . colour of this Gaussian
+        float* frow = s_facc + ((size_t)warp * BWDG_FB + (j & (BWDG_FB - 1))) * CP;
 #pragma unroll
         for (int k0 = 0; k0 < CP; k0 += 16) {
           float contrib[16];
@@ -369,16 +375,16 @@ __global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
             const float cc[4] = {c.x, c.y, c.z, c.w};
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-              const float d = cc[q] - A[k0 + k + q];
-              dot = fmaf(d, g[k0 + k + q], dot);
-              A[k0 + k + q] = fmaf(al, d, A[k0 + k + q]);  // lanes that did not blend have al = 0
+              dsum = fmaf(cc[q], g[k0 + k + q], dsum);
               contrib[k + q] = w * g[k0 + k + q];
             }
           }
           const float tot = butterfly16(contrib, lane);
-          const int ch = k0 + my_slot;
-          if ((lane & 1) == 0 && ch < C && tot != 0.f) atomicAdd(gfbase + (size_t)id * C + ch, tot);
+          if ((lane & 1) == 0) frow[k0 + my_slot] = tot;  // this warp's share of dL/dfeature: summed over the warps at the flush
         }
+        const float dot = dsum - S;
+        S = fmaf(al, dot, S);  // lanes that did not blend have al = 0
+        (void)id;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (ok) {
           const float dL_dalpha = dot * T + gob * rcp;
@@ -395,10 +401,23 @@ __global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
         if ((lane & 3) == 0) s_acc[(warp * BWDG_BATCH + j) * 8 + (lane >> 2)] = r8;
         touched |= 1u << (j & 31);
       }
-      if ((j & 31) == 0) {
-        if (lane == 0) s_touched[warp][j >> 5] = touched;
-        touched = 0;
+      if ((j & (BWDG_FB - 1)) == 0) {
+        // ---- records [j, j + BWDG_FB) are complete in every warp: one reduction over the warps per channel ----
+        if (lane == 0) s_touched[warp][j >> 5] = touched;  // (the word keeps accumulating until its 32-record boundary)
+        __syncthreads();
+        for (int e = tid; e < BWDG_FB * CP; e += TILE_PIX) {
+          const int jj = e / CP, ch = e - jj * CP;
+          const int rj = j + jj;
+          if (rj >= cnt || ch >= C) continue;
+          float tot = 0.f;
+#pragma unroll
+          for (int w2 = 0; w2 < NW; w2++)
+            if ((s_touched[w2][rj >> 5] >> (rj & 31)) & 1u) tot += s_facc[((size_t)w2 * BWDG_FB + jj) * CP + ch];
+          if (tot != 0.f) atomicAdd(gfbase + (size_t)s_rec[rj].id * C + ch, tot);
+        }
+        __syncthreads();
       }
+      if ((j & 31) == 0) touched = 0;
     }
     __syncthreads();
     for (int j = tid; j < cnt; j += TILE_PIX) {
@@ -425,7 +444,8 @@ static int launch_backward_generic(cudaStream_t st, dim3 grid, const OcrfShape* 
                                    const float* colors, const float* bg, const float* fT, const uint32_t* nc,
                                    const uint32_t* mc, const float* dL_dcolor, const float* dL_dopa, double* ggrad,
                                    float* dL_dcolors) {
-  const size_t dyn = BWDG_BATCH * sizeof(Record) + (size_t)BWDG_BATCH * CP * 4 + (size_t)(TILE_PIX / 32) * BWDG_BATCH * 8 * 4;
+  const size_t dyn = BWDG_BATCH * sizeof(Record) + (size_t)BWDG_BATCH * CP * 4 + (size_t)(TILE_PIX / 32) * BWDG_BATCH * 8 * 4 +
+                     (size_t)(TILE_PIX / 32) * BWDG_FB * CP * 4;
   cudaError_t e = cudaFuncSetAttribute(render_backward_generic_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)dyn);
   if (e != cudaSuccess) return (int)e;
