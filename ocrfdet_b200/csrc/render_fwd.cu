@@ -277,6 +277,115 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_generic_kernel(
   if (tid == 0) max_contrib[(size_t)view * tiles_per_view + tile] = s_max;
 }
 
+
+// Generic channel count, single traversal (C <= 96): all CP channel accumulators of a pixel live in registers, so the
+// list is walked -- and every alpha evaluated -- once instead of once per 16-channel chunk (C = 80: 5 traversals).
+template <int CP>
+__global__ void __launch_bounds__(TILE_PIX, CP <= 80 ? 2 : 1) render_forward_wide_kernel(
+    int W, int H, int C, int P, int views_per_sample, const uint2* __restrict__ ranges,
+    const Record* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
+    float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ max_contrib,
+    float* __restrict__ out_color, float* __restrict__ out_depth, float* __restrict__ out_opacity) {
+  extern __shared__ __align__(16) unsigned char smem_w[];
+  Record* s_rec = reinterpret_cast<Record*>(smem_w);                                  // [FWDG_BATCH]
+  float* s_feat = reinterpret_cast<float*>(smem_w + FWDG_BATCH * sizeof(Record));     // [FWDG_BATCH][CP]
+  __shared__ uint32_t s_max;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = gridDim.x, tiles_per_view = gridDim.x * gridDim.y;
+  const int view = blockIdx.z;
+  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  const uint2 range = ranges[(size_t)view * tiles_per_view + tile];
+  const int n = (int)(range.y - range.x);
+  const int rounds = (n + FWDG_BATCH - 1) / FWDG_BATCH;
+  const float* fbase = feats + (size_t)(view / views_per_sample) * P * C;
+
+  const int px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
+  const int py = blockIdx.y * TILE + (warp >> 1) * 4 + (lane >> 3);
+  const bool inside = px < W && py < H;
+  const float fx = (float)px, fy = (float)py;
+  const size_t HW = (size_t)H * W;
+  const size_t pix = (size_t)py * W + px;
+  if (tid == 0) s_max = 0;
+
+  bool done = !inside;
+  float T = 1.f, D = 15.f;
+  uint32_t last = 0, lastc = 0;
+  float acc[CP];
+#pragma unroll
+  for (int k = 0; k < CP; k++) acc[k] = 0.f;
+  for (int r = 0; r < rounds; r++) {
+    const int num_done = __syncthreads_count(done);
+    if (num_done == TILE_PIX) break;
+    const int cnt = min(FWDG_BATCH, n - r * FWDG_BATCH);
+    if (tid < cnt) s_rec[tid] = records[range.x + r * FWDG_BATCH + tid];
+    for (int e = tid; e < cnt * (CP / 4); e += TILE_PIX) {  // feature rows, 16 bytes per thread
+      const int j = e / (CP / 4), k4 = (e - j * (CP / 4)) * 4;
+      const uint32_t id = records[range.x + r * FWDG_BATCH + j].id;
+      float4 f;
+      f.x = k4 + 0 < C ? __ldg(fbase + (size_t)id * C + k4 + 0) : 0.f;
+      f.y = k4 + 1 < C ? __ldg(fbase + (size_t)id * C + k4 + 1) : 0.f;
+      f.z = k4 + 2 < C ? __ldg(fbase + (size_t)id * C + k4 + 2) : 0.f;
+      f.w = k4 + 3 < C ? __ldg(fbase + (size_t)id * C + k4 + 3) : 0.f;
+      *reinterpret_cast<float4*>(s_feat + j * CP + k4) = f;
+    }
+    __syncthreads();
+    if (__all_sync(0xffffffffu, done)) continue;
+    for (int j = 0; j < cnt; j++) {  // warp-uniform control flow, see render_forward_c3_kernel
+      const float4 a = reinterpret_cast<const float4*>(&s_rec[j])[0];
+      const float4 b = reinterpret_cast<const float4*>(&s_rec[j])[1];
+      const float dx = a.x - fx, dy = a.y - fy;
+      const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
+      const float alpha = fminf(0.99f, b.y * ex2_approx(power * 1.4426950408889634f));
+      const bool ok = !done && power <= 0.0f && alpha >= 1.0f / 255.0f;
+      if (!__any_sync(0xffffffffu, ok)) continue;
+      const float test_T = T * (1.f - alpha);
+      const bool blend = ok && test_T >= 0.0001f;
+      const bool stop = ok && test_T < 0.0001f;
+      const float w = blend ? alpha * T : 0.f;
+      const float* fj = s_feat + j * CP;
+#pragma unroll
+      for (int k = 0; k < CP; k += 4) {
+        const float4 f = *reinterpret_cast<const float4*>(fj + k);
+        acc[k] = fmaf(f.x, w, acc[k]); acc[k + 1] = fmaf(f.y, w, acc[k + 1]);
+        acc[k + 2] = fmaf(f.z, w, acc[k + 2]); acc[k + 3] = fmaf(f.w, w, acc[k + 3]);
+      }
+      if (blend) {
+        if (T > 0.5f && test_T < 0.5f) D = s_rec[j].depth;
+        T = test_T;
+        last = s_rec[j].orig;
+        lastc = (uint32_t)(r * FWDG_BATCH + j + 1);
+      }
+      done = done || stop;
+      if (__any_sync(0xffffffffu, stop) && __all_sync(0xffffffffu, done)) break;
+    }
+  }
+  if (inside) {
+#pragma unroll
+    for (int k = 0; k < CP; k++)
+      if (k < C) out_color[((size_t)view * C + k) * HW + pix] = acc[k] + T * bg[k];
+    final_T[view * HW + pix] = T;
+    n_contrib[view * HW + pix] = last;
+    if (out_depth) out_depth[view * HW + pix] = D;
+    if (out_opacity) out_opacity[view * HW + pix] = 1.f - T;
+    atomicMax(&s_max, lastc);
+  }
+  __syncthreads();
+  if (tid == 0) max_contrib[(size_t)view * tiles_per_view + tile] = s_max;
+}
+
+template <int CP>
+static int launch_forward_wide(cudaStream_t st, dim3 grid, const OcrfShape* sh, const uint2* ranges, const Record* rec,
+                               const float* colors, const float* bg, float* fT, uint32_t* nc, uint32_t* mc,
+                               float* out_color, float* out_depth, float* out_opacity) {
+  const size_t dyn = FWDG_BATCH * sizeof(Record) + (size_t)FWDG_BATCH * CP * 4;
+  cudaError_t e = cudaFuncSetAttribute(render_forward_wide_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+  if (e != cudaSuccess) return (int)e;
+  render_forward_wide_kernel<CP><<<grid, TILE_PIX, dyn, st>>>(sh->W, sh->H, sh->C, sh->P, sh->views_per_sample, ranges, rec,
+                                                               colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
+  return 0;
+}
+
 }  // namespace ocrf
 
 using namespace ocrf;
@@ -317,9 +426,18 @@ extern "C" int ocrf_render_forward(void* stream, const OcrfShape* sh, uint64_t p
                                                              out_depth, out_opacity);
   } else {
     (void)use_sh;
-    render_forward_generic_kernel<<<grid, TILE_PIX, 0, st>>>(sh->W, sh->H, sh->C, sh->P, sh->views_per_sample, ranges,
-                                                             at<Record>(bin_ws, B.records), colors, bg, fT, nc, mc,
-                                                             out_color, out_depth, out_opacity);
+    const Record* rec = at<Record>(bin_ws, B.records);
+    int rcw = 0;
+    if (sh->C <= 16) rcw = launch_forward_wide<16>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
+    else if (sh->C <= 32) rcw = launch_forward_wide<32>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
+    else if (sh->C <= 48) rcw = launch_forward_wide<48>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
+    else if (sh->C <= 64) rcw = launch_forward_wide<64>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
+    else if (sh->C <= 80) rcw = launch_forward_wide<80>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
+    else if (sh->C <= 96) rcw = launch_forward_wide<96>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
+    else  // wider than the register-resident variants: 16 channels per traversal
+      render_forward_generic_kernel<<<grid, TILE_PIX, 0, st>>>(sh->W, sh->H, sh->C, sh->P, sh->views_per_sample, ranges, rec,
+                                                               colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
+    if (rcw) return rcw;
   }
   OCRF_CHECK_LAST();
   return 0;
