@@ -238,15 +238,15 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
 // Generic channel count (C != 3, e.g. the 80-channel feature rendering of GeoEnhDet).
 //
 // dL/dalpha of a (pixel, Gaussian) pair needs the sum over ALL channels of (c_k - A_k) g_k before the
-// geometry gradients can be formed, so channels cannot be tiled across sweeps as in the forward.
-// One thread per pixel keeps its upstream gradient g[CP] and the behind-colour A[CP] in REGISTERS
-// (CP = C rounded up to 16, fully unrolled; one CTA of 256 threads per SM has 255 registers per
-// thread to spend), the batch's feature rows sit in shared memory and are read as broadcast
-// LDS.128.  The recurrence is applied eagerly, A <- A + alpha (c - A) right after A is used, which is
-// the reference's lazy `last_alpha * last_color + (1 - last_alpha) * accum` evaluated one step
-// earlier -- no per-pixel "last colour" has to be remembered.  Per record the warp reduce-scatters
-// the CP colour gradients 16 at a time (16 shuffles per 16 channels instead of 80) and issues one
-// 64-byte-contiguous global reduction per 16 channels; geometry gradients follow the C = 3 scheme.
+// geometry gradients can be formed, so the list is walked once with the whole upstream gradient g[CP] of the pixel
+// in REGISTERS (CP = C rounded up to 16, fully unrolled); the batch's feature rows sit in shared memory and are read
+// as broadcast LDS.128.  The colour accumulated behind the pixel, A_k, is never formed: only g . A is needed, and
+// that scalar follows the same recurrence, S <- S + alpha (g . c - S), applied eagerly right after it is used (the
+// reference's lazy `last_alpha * last_color + (1 - last_alpha) * accum`, backward.cu:480-490, one step earlier) --
+// one register and one FMA instead of CP of each per (pixel, Gaussian).  Per record the warp reduce-scatters the CP
+// colour gradients 16 at a time (16 shuffles per 16 channels instead of 80) into its own shared-memory row; every 16
+// records the rows of the eight warps are summed and ONE global reduction per (record, channel) is issued (they were
+// 8x as many, and the dominant cost, when every warp issued its own); geometry gradients follow the C = 3 scheme.
 constexpr int BWDG_BATCH = 64;
 constexpr int BWDG_FB = 16;  // records per cross-warp reduction of the feature gradients
 
