@@ -275,8 +275,30 @@ __device__ __forceinline__ float butterfly16(const float* v, int lane) {
   return r;  // value index = h16*8 + h8*4 + h4*2 + h2
 }
 
+// ---- tensor-core helpers for the feature gradients of the generic-channel backward -------------------------------
+// dF[record][channel] = sum over the pixels of a tile of w[pixel][record] * g[pixel][channel] is a dense product.
+// Every warp multiplies ITS 32 pixels: A = w^T [16 records x 32 pixels] (staged through shared memory as the records
+// are walked), B = g [32 pixels x CP channels] (staged once per tile), C = a [16 x CP] partial that the eight warps
+// then add up.  mma.sync.m16n8k8 TF32 with the 3-term split (hi*hi + lo*hi + hi*lo) keeps fp32 accuracy: plain TF32
+// (10-bit mantissa) misses the 1e-4 gradient bar on sums of 256 mixed-sign terms.
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+constexpr int BWDG_WP = 36;  // pitch of a record's 32 pixel weights (== 4 mod 32: conflict-free A fragments)
+
 template <int CP>
-__global__ void __launch_bounds__(TILE_PIX, CP <= 80 ? 2 : 1) render_backward_generic_kernel(
+__global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
     int W, int H, int C, int P, int views_per_sample, const uint2* __restrict__ ranges /* culled lists */,
     const Record* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
     const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
@@ -287,7 +309,10 @@ __global__ void __launch_bounds__(TILE_PIX, CP <= 80 ? 2 : 1) render_backward_ge
   Record* s_rec = reinterpret_cast<Record*>(smem_g);                                   // [BATCH]
   float* s_feat = reinterpret_cast<float*>(smem_g + BWDG_BATCH * sizeof(Record));      // [BATCH][CP]
   float* s_acc = s_feat + BWDG_BATCH * CP;                                             // [NW][BATCH][8]
-  float* s_facc = s_acc + NW * BWDG_BATCH * 8;                                         // [NW][BWDG_FB][CP] feature-gradient rows
+  float* s_facc = s_acc + NW * BWDG_BATCH * 8;                                         // [NW][BWDG_FB][CP] per-warp partial dF
+  constexpr int GP = CP + 8;                                                           // g row pitch (== 8 mod 16: conflict-free B fragments)
+  float* s_g = s_facc + NW * BWDG_FB * CP;                                             // [NW][32][GP] upstream gradients of the tile
+  float* s_w = s_g + NW * 32 * GP;                                                     // [NW][BWDG_FB][BWDG_WP] blend weights
   __shared__ uint32_t s_touched[NW][BWDG_BATCH / 32];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -320,13 +345,17 @@ __global__ void __launch_bounds__(TILE_PIX, CP <= 80 ? 2 : 1) render_backward_ge
   // (backward.cu:480-490) and dots it with dL/dpixel; the dot product obeys the same linear recurrence, so one scalar
   // replaces C registers and C multiply-adds per (pixel, Gaussian)
   float S = 0.f;
+  {
+    float* grow = s_g + ((size_t)warp * 32 + lane) * GP;
+#pragma unroll
+    for (int k = 0; k < CP; k += 4) *reinterpret_cast<float4*>(grow + k) = make_float4(g[k], g[k + 1], g[k + 2], g[k + 3]);
+  }
+  float* my_w = s_w + (size_t)warp * BWDG_FB * BWDG_WP + lane;
   const float gop = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
   const float gob = Tf * (gop - bgdot);
   float T = Tf;
   const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
   const int rounds = (mc + BWDG_BATCH - 1) / BWDG_BATCH;
-  // which 16-lane-pair slot of a 16-channel group this lane owns after butterfly16
-  const int my_slot = ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
 
   for (int r = 0; r < rounds; r++) {
     const int hi = mc - r * BWDG_BATCH;
@@ -354,37 +383,27 @@ __global__ void __launch_bounds__(TILE_PIX, CP <= 80 ? 2 : 1) render_backward_ge
       const float G = ex2_approx_b(power * 1.4426950408889634f);
       const float alpha = fminf(0.99f, b.y * G);
       const bool ok = (int)__float_as_uint(b.z) <= nc && power <= 0.0f && alpha >= 1.0f / 255.0f;
+      float rcp = 1.f, w = 0.f, al = 0.f;
+      if (ok) {
+        rcp = __fdividef(1.f, 1.f - alpha);
+        T *= rcp;
+        w = alpha * T;
+        al = alpha;
+      }
+      my_w[(j & (BWDG_FB - 1)) * BWDG_WP] = w;  // column `lane` of the warp's w^T tile (0 for a pixel that did not blend)
       if (__any_sync(0xffffffffu, ok)) {
-        float rcp = 1.f, w = 0.f, al = 0.f;
-        if (ok) {
-          rcp = __fdividef(1.f, 1.f - alpha);
-          T *= rcp;
-          w = alpha * T;
-          al = alpha;
-        }
-        const uint32_t id = s_rec[j].id;
         const float* fj = s_feat + j * CP;
         float dsum = 0.f;  // g . colour of this Gaussian
-        float* frow = s_facc + ((size_t)warp * BWDG_FB + (j & (BWDG_FB - 1))) * CP;
 #pragma unroll
-        for (int k0 = 0; k0 < CP; k0 += 16) {
-          float contrib[16];
-#pragma unroll
-          for (int k = 0; k < 16; k += 4) {
-            const float4 c = *reinterpret_cast<const float4*>(fj + k0 + k);
-            const float cc[4] = {c.x, c.y, c.z, c.w};
-#pragma unroll
-            for (int q = 0; q < 4; q++) {
-              dsum = fmaf(cc[q], g[k0 + k + q], dsum);
-              contrib[k + q] = w * g[k0 + k + q];
-            }
-          }
-          const float tot = butterfly16(contrib, lane);
-          if ((lane & 1) == 0) frow[k0 + my_slot] = tot;  // this warp's share of dL/dfeature: summed over the warps at the flush
+        for (int k = 0; k < CP; k += 4) {
+          const float4 c = *reinterpret_cast<const float4*>(fj + k);
+          dsum = fmaf(c.x, g[k], dsum);
+          dsum = fmaf(c.y, g[k + 1], dsum);
+          dsum = fmaf(c.z, g[k + 2], dsum);
+          dsum = fmaf(c.w, g[k + 3], dsum);
         }
         const float dot = dsum - S;
         S = fmaf(al, dot, S);  // lanes that did not blend have al = 0
-        (void)id;
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
         if (ok) {
           const float dL_dalpha = dot * T + gob * rcp;
@@ -404,15 +423,46 @@ __global__ void __launch_bounds__(TILE_PIX, CP <= 80 ? 2 : 1) render_backward_ge
       if ((j & (BWDG_FB - 1)) == 0) {
         // ---- records [j, j + BWDG_FB) are complete in every warp: one reduction over the warps per channel ----
         if (lane == 0) s_touched[warp][j >> 5] = touched;  // (the word keeps accumulating until its 32-record boundary)
+        __syncwarp();
+        {  // this warp's partial dF[16 records][CP] = w^T[16 x 32 px] . g[32 px x CP] on the tensor cores
+          const int gid = lane >> 2, tig = lane & 3;
+          const float* wt = s_w + (size_t)warp * BWDG_FB * BWDG_WP;
+          const float* gt = s_g + (size_t)warp * 32 * GP;
+          float cacc[CP / 8][4];
+#pragma unroll
+          for (int nt = 0; nt < CP / 8; nt++) cacc[nt][0] = cacc[nt][1] = cacc[nt][2] = cacc[nt][3] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {
+            uint32_t ahi[4], alo[4];
+            split_tf32(wt[gid * BWDG_WP + 8 * ks + tig], ahi[0], alo[0]);
+            split_tf32(wt[(gid + 8) * BWDG_WP + 8 * ks + tig], ahi[1], alo[1]);
+            split_tf32(wt[gid * BWDG_WP + 8 * ks + tig + 4], ahi[2], alo[2]);
+            split_tf32(wt[(gid + 8) * BWDG_WP + 8 * ks + tig + 4], ahi[3], alo[3]);
+#pragma unroll
+            for (int nt = 0; nt < CP / 8; nt++) {
+              uint32_t bhi[2], blo[2];
+              split_tf32(gt[(8 * ks + tig) * GP + 8 * nt + gid], bhi[0], blo[0]);
+              split_tf32(gt[(8 * ks + tig + 4) * GP + 8 * nt + gid], bhi[1], blo[1]);
+              mma_tf32_16x8x8(cacc[nt], alo, bhi);
+              mma_tf32_16x8x8(cacc[nt], ahi, blo);
+              mma_tf32_16x8x8(cacc[nt], ahi, bhi);
+            }
+          }
+          float* fo = s_facc + (size_t)warp * BWDG_FB * CP;
+#pragma unroll
+          for (int nt = 0; nt < CP / 8; nt++) {
+            *reinterpret_cast<float2*>(fo + gid * CP + 8 * nt + 2 * tig) = make_float2(cacc[nt][0], cacc[nt][1]);
+            *reinterpret_cast<float2*>(fo + (gid + 8) * CP + 8 * nt + 2 * tig) = make_float2(cacc[nt][2], cacc[nt][3]);
+          }
+        }
         __syncthreads();
         for (int e = tid; e < BWDG_FB * CP; e += TILE_PIX) {
           const int jj = e / CP, ch = e - jj * CP;
           const int rj = j + jj;
-          if (rj >= cnt || ch >= C) continue;
+          if (rj >= cnt || ch >= C) continue;  // (rows past the end of the batch hold stale weights)
           float tot = 0.f;
 #pragma unroll
-          for (int w2 = 0; w2 < NW; w2++)
-            if ((s_touched[w2][rj >> 5] >> (rj & 31)) & 1u) tot += s_facc[((size_t)w2 * BWDG_FB + jj) * CP + ch];
+          for (int w2 = 0; w2 < NW; w2++) tot += s_facc[((size_t)w2 * BWDG_FB + jj) * CP + ch];
           if (tot != 0.f) atomicAdd(gfbase + (size_t)s_rec[rj].id * C + ch, tot);
         }
         __syncthreads();
@@ -445,7 +495,8 @@ static int launch_backward_generic(cudaStream_t st, dim3 grid, const OcrfShape* 
                                    const uint32_t* mc, const float* dL_dcolor, const float* dL_dopa, double* ggrad,
                                    float* dL_dcolors) {
   const size_t dyn = BWDG_BATCH * sizeof(Record) + (size_t)BWDG_BATCH * CP * 4 + (size_t)(TILE_PIX / 32) * BWDG_BATCH * 8 * 4 +
-                     (size_t)(TILE_PIX / 32) * BWDG_FB * CP * 4;
+                     (size_t)(TILE_PIX / 32) * BWDG_FB * CP * 4 + (size_t)(TILE_PIX / 32) * 32 * (CP + 8) * 4 +
+                     (size_t)(TILE_PIX / 32) * BWDG_FB * BWDG_WP * 4;
   cudaError_t e = cudaFuncSetAttribute(render_backward_generic_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)dyn);
   if (e != cudaSuccess) return (int)e;

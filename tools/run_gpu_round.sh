@@ -1,4 +1,3 @@
 set -x
-mkdir -p gpurun_out
-timeout 900 ncu --set full --clock-control none -k regex:"render_forward_wide|render_backward_generic" -s 4 -c 2 -o gpurun_out/r1_generic_full -f python tools/generic_profile.py > gpurun_out/ncu_generic.log 2>&1
-tail -2 gpurun_out/ncu_generic.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_reference.py -x -q 2>&1 | tail -4
+timeout 600 python tools/config_sanity.py 2>&1 | grep "config4" | cut -c1-260
