@@ -243,10 +243,13 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
 // as broadcast LDS.128.  The colour accumulated behind the pixel, A_k, is never formed: only g . A is needed, and
 // that scalar follows the same recurrence, S <- S + alpha (g . c - S), applied eagerly right after it is used (the
 // reference's lazy `last_alpha * last_color + (1 - last_alpha) * accum`, backward.cu:480-490, one step earlier) --
-// one register and one FMA instead of CP of each per (pixel, Gaussian).  Per record the warp reduce-scatters the CP
-// colour gradients 16 at a time (16 shuffles per 16 channels instead of 80) into its own shared-memory row; every 16
-// records the rows of the eight warps are summed and ONE global reduction per (record, channel) is issued (they were
-// 8x as many, and the dominant cost, when every warp issued its own); geometry gradients follow the C = 3 scheme.
+// one register and one FMA instead of CP of each per (pixel, Gaussian).  The feature gradients
+// dF[record][channel] = sum_pixels w[pixel][record] g[pixel][channel] are a dense product: every warp keeps the blend
+// weights of its 32 pixels for 16 records in shared memory and multiplies them with its pixels' gradients on the tensor
+// cores (3xTF32 mma.sync, helpers below) instead of CP multiplies and 5 butterfly reductions per record; the eight
+// partial tiles are summed and ONE global reduction per (record, channel) is issued (they were 8x as many when every
+// warp issued its own).  Geometry gradients follow the C = 3 scheme.  Known limit: the resident g tile (90 KB at
+// C = 80) allows one CTA per SM, so the 2.4x fewer instructions buy only 6 % of time -- see DESIGN.md section 8.
 constexpr int BWDG_BATCH = 64;
 constexpr int BWDG_FB = 16;  // records per cross-warp reduction of the feature gradients
 
