@@ -156,3 +156,30 @@ def test_gaussian_heads_checkpoint_keys_and_packing_roundtrip():
         GaussianHeads(80).load_state_dict({k: t for k, t in sd2.items() if k != "R_MLP.fc2.bias"})
     with pytest.raises(Exception):   # no CPU path
         m2(torch.zeros(4, 80), torch.zeros(4, 3))
+
+
+def test_every_dependent_launch_kernel_waits_for_its_predecessor():
+    """Kernels launched through launch_chain() carry the programmatic-stream-serialization attribute: they may start
+    before their predecessor has finished, so each of them must begin with pdl_enter() (griddepcontrol.wait) before it
+    touches global memory.  Static check over the sources."""
+    import glob
+    import re
+    csrc = os.path.join(ROOT, "ocrfdet_b200", "csrc")
+    text = {p: open(p).read() for p in glob.glob(os.path.join(csrc, "*.cu"))}
+    launched = set()
+    for src in text.values():
+        launched |= set(re.findall(r"launch_chain\(\s*([A-Za-z_0-9]+)", src))
+    assert len(launched) >= 10
+    for name in sorted(launched):
+        bodies = []
+        for src in text.values():
+            for m in re.finditer(r"__global__[^;{]*?\b%s\s*\(" % re.escape(name), src):
+                i, depth = m.end(), 1
+                while depth:
+                    depth += {"(": 1, ")": -1}.get(src[i], 0)
+                    i += 1
+                j = src.index("{", i)
+                bodies.append(src[j + 1:j + 200])
+        assert bodies, name
+        for body in bodies:
+            assert body.lstrip().startswith("pdl_enter();"), "%s is launched with PDL but does not wait first" % name
