@@ -183,3 +183,21 @@ def test_every_dependent_launch_kernel_waits_for_its_predecessor():
         assert bodies, name
         for body in bodies:
             assert body.lstrip().startswith("pdl_enter();"), "%s is launched with PDL but does not wait first" % name
+
+
+def test_ctypes_signatures_match_the_header_arity():
+    """Every entry point declared in include/ocrf_raster.h is bound in _lib.py with as many arguments as the header
+    declares (ctypes would silently pass too few or too many)."""
+    import re
+    L = _lib.lib()
+    hdr = open(os.path.join(ROOT, "include", "ocrf_raster.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    decls = re.findall(r"\b(?:int|size_t|const char\s*\*)\s+(ocrf_[a-z0-9_]+)\s*\(([^;]*?)\)\s*;", hdr, flags=re.S)
+    assert len(decls) >= 25
+    for name, params in decls:
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        fn = getattr(L, name)
+        assert fn.argtypes is not None or n == 0, name + " has no argtypes"
+        if fn.argtypes is not None:
+            assert len(fn.argtypes) == n, "%s: header declares %d arguments, _lib.py binds %d" % (name, n, len(fn.argtypes))
