@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define OCRF_ABI_VERSION 2
+#define OCRF_ABI_VERSION 3
 
 #define OCRF_EINVAL (-1)    /* bad argument (null pointer, non-positive size, unsupported channel count) */
 #define OCRF_ECAPACITY (-2) /* workspace too small for the request */
@@ -110,6 +110,9 @@ typedef struct OcrfImageLayout {
 
 int ocrf_abi_version(void);
 const char* ocrf_error_string(int code);
+/* The reference's debug mode (GaussianRasterizationSettings.debug -> CHECK_CUDA, cuda_rasterizer/auxiliary.h:166-173):
+ * wait for everything queued on `stream` and return the first CUDA error, sticky or asynchronous, as a status code. */
+int ocrf_debug_sync(void* stream);
 
 int ocrf_geom_layout(const OcrfShape* shape, int use_sh, OcrfGeomLayout* out);
 int ocrf_bin_layout(const OcrfShape* shape, uint64_t num_pairs, OcrfBinLayout* out);
@@ -130,9 +133,14 @@ int ocrf_preprocess_forward(void* stream, const OcrfShape* shape, const float* m
  * 64-bit (view*tiles+tile | depth) keys + identifyTileRanges + record packing.
  * `pair_capacity` is the number of pairs the binning workspace was laid out for; the true count is
  * read on the device from the geom header, and exceeding the capacity sets header[1] bit 0 and
- * renders nothing rather than overrunning.  colors [S,P,C] (ignored when the SH path produced rgb). */
+ * renders nothing rather than overrunning.  colors [S,P,C] (ignored when the SH path produced rgb).
+ * `sticky_status` (may be NULL): uint32[2] owned by the caller and never cleared by the library; [0] receives (OR) the
+ * error flags of this call (bit 0 = pair overflow, bit 1 = a filtered point although `prefiltered` was set), [1]
+ * (max) its pair count -- the geom header itself is re-zeroed by every forward, so callers that do not read it back
+ * after each call (capacity mode, CUDA-graph replays) watch these words instead. */
 int ocrf_bin_forward(void* stream, const OcrfShape* shape, uint64_t pair_capacity, const int32_t* radii,
-                     const float* colors, int use_sh, uint32_t flags, void* geom_ws, void* bin_ws, void* image_ws);
+                     const float* colors, int use_sh, uint32_t flags, void* geom_ws, void* bin_ws, void* image_ws,
+                     uint32_t* sticky_status);
 /* flags for ocrf_bin_forward */
 #define OCRF_BIN_PAIR_SORT 1u   /* the reference's algorithm: sort all (tile | depth) pairs */
 #define OCRF_BIN_DEPTH_FIRST 2u /* sort the visible Gaussians by depth, emit pairs in that order, sort the tile bits only */

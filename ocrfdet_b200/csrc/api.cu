@@ -10,3 +10,9 @@ extern "C" const char* ocrf_error_string(int code) {
   if (code > 0) return cudaGetErrorString(static_cast<cudaError_t>(code));
   return "ocrf: unknown error";
 }
+
+extern "C" int ocrf_debug_sync(void* stream) {
+  cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+  if (e == cudaSuccess) e = cudaGetLastError();
+  return (int)e;
+}

@@ -127,8 +127,10 @@ __global__ void __launch_bounds__(256) ranges_cull_pack_kernel(OcrfShape sh, uin
                                                                const float* __restrict__ colors,
                                                                uint2* __restrict__ ranges,
                                                                uint2* __restrict__ ranges_render,
-                                                               Record* __restrict__ records) {
+                                                               Record* __restrict__ records,
+                                                               uint32_t* __restrict__ sticky) {
   __shared__ uint32_t s_bounds[2];
+  if (sticky != nullptr && blockIdx.x == 0 && threadIdx.x == 0) publish_status(header, n_cap, sticky);
   __shared__ uint32_t s_warp[8];
   const uint32_t total = header[HDR_NUM_PAIRS];
   const uint32_t n = (uint64_t)total <= n_cap ? total : 0u;
@@ -383,7 +385,7 @@ extern "C" int ocrf_image_layout(const OcrfShape* sh, OcrfImageLayout* out) {
 
 extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair_capacity, const int32_t* radii,
                                 const float* colors, int use_sh, uint32_t flags, void* geom_ws, void* bin_ws,
-                                void* image_ws) {
+                                void* image_ws, uint32_t* sticky_status) {
   if (!sh || !radii || !geom_ws || !bin_ws || !image_ws) return OCRF_EINVAL;
   if (sh->C == 3 && !use_sh && !colors) return OCRF_EINVAL;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -425,7 +427,7 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
     // (2) inclusive scan of tiles_touched in depth order: where every Gaussian's pairs sit in the pair stream
     const uint32_t* vvals = at<uint32_t>(geom_ws, G.vis_vals);
     uint32_t* sorted_offsets = at<uint32_t>(bin_ws, B.split_counts);
-    launch_chain(scan_sorted_tiles_kernel, dim3((unsigned)sblocks), dim3(256), 0, st, header, vvals, at<uint32_t>(geom_ws, G.tiles_touched),
+    OCRF_LAUNCH(scan_sorted_tiles_kernel, dim3((unsigned)sblocks), dim3(256), 0, st, header, vvals, at<uint32_t>(geom_ws, G.tiles_touched),
                                                                 sorted_offsets, sstat, sticket);
     if (multisplit) {
       // (3) one stable multi-split of the pair stream by tile, culled records written directly
@@ -434,7 +436,7 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
                           sorted_offsets, vvals, at<float2>(geom_ws, G.xy), at<float4>(geom_ws, G.conic_opacity),
                           at<float>(geom_ws, G.depths), at<float>(geom_ws, G.rgb), sorted_offsets + n, B.split_words,
                           tile_arrays, at<uint2>(bin_ws, B.keys), at<uint2>(image_ws, I.ranges),
-                          at<uint2>(image_ws, I.ranges_render), at<Record>(bin_ws, B.records));
+                          at<uint2>(image_ws, I.ranges_render), at<Record>(bin_ws, B.records), sticky_status);
       return rc;
     }
     // (3') emit the pairs in depth order, then two stable passes over the tile bits only
@@ -472,7 +474,7 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
       *sh, pair_capacity, use_sh, sh->C == 3, header, at<uint64_t>(bin_ws, B.keys), at<uint32_t>(bin_ws, B.point_list),
       at<float>(geom_ws, G.depths), at<float2>(geom_ws, G.xy), at<float4>(geom_ws, G.conic_opacity),
       at<float>(geom_ws, G.rgb), colors, at<uint2>(image_ws, I.ranges), at<uint2>(image_ws, I.ranges_render),
-      at<Record>(bin_ws, B.records));
+      at<Record>(bin_ws, B.records), sticky_status);
   OCRF_CHECK_LAST();
   return 0;
 }

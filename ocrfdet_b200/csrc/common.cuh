@@ -12,7 +12,33 @@ namespace ocrf {
 
 constexpr int TILE = 16;               // blend tile edge (config.h:16-17 of the reference: BLOCK_X = BLOCK_Y = 16)
 constexpr int TILE_PIX = TILE * TILE;  // pixels per tile
-constexpr int NUM_SMS = 148;           // B200
+constexpr int NUM_SMS_B200 = 148;      // B200; only the fallback of num_sms() below
+
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs).
+inline int num_sms() {
+  static int cache[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return NUM_SMS_B200;
+  if (cache[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = NUM_SMS_B200;
+    cache[dev] = n;
+  }
+  return cache[dev];
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE function attribute: remember per device ordinal
+// (`done_mask`, one static word per call site) where it has been raised already.
+template <typename K>
+inline cudaError_t ensure_dynamic_smem(K kernel, size_t bytes, unsigned long long& done_mask) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  if (dev >= 0 && dev < 64 && ((done_mask >> dev) & 1ull)) return cudaSuccess;
+  e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e == cudaSuccess && dev >= 0 && dev < 64) done_mask |= 1ull << dev;
+  return e;
+}
 
 // geom header slots (uint32)
 constexpr int HDR_NUM_PAIRS = 0;
@@ -21,6 +47,16 @@ constexpr int HDR_TICKET = 2;
 constexpr int HDR_NUM_VIS = 3;  // visible (view, Gaussian) pairs of the batch
 constexpr uint32_t ERR_PAIR_OVERFLOW = 1u;
 constexpr uint32_t ERR_PREFILTERED = 2u;
+
+// Sticky status words of a caller (ocrf_bin_forward's `sticky_status`): the geom header is re-zeroed by every
+// forward, so a caller that does not read it back after each call (capacity mode, graph replays) gives the library
+// two words that are only ever OR-ed / max-ed into: [0] error flags of any call so far, [1] largest pair count.
+__device__ __forceinline__ void publish_status(const uint32_t* header, uint64_t n_cap, uint32_t* sticky) {
+  const uint32_t n = header[HDR_NUM_PAIRS];
+  const uint32_t e = header[HDR_ERROR] | ((uint64_t)n > n_cap ? ERR_PAIR_OVERFLOW : 0u);
+  if (e) atomicOr(&sticky[0], e);
+  atomicMax(&sticky[1], n);
+}
 
 struct Camera {  // OCRF_CAM_STRIDE floats
   float view[16];
@@ -112,7 +148,7 @@ int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity,
                    const float* colors, uint32_t* header, const uint32_t* view_start, const uint32_t* sorted_offsets,
                    const uint32_t* vis_vals, const float2* xy, const float4* conic_opacity, const float* depths,
                    const float* rgb, uint32_t* tables, size_t table_words, uint32_t* tile_arrays, uint2* items,
-                   uint2* ranges, uint2* ranges_render, Record* records);
+                   uint2* ranges, uint2* ranges_render, Record* records, uint32_t* sticky);
 inline uint32_t multisplit_chunk_pairs(uint64_t pair_capacity) {  // pairs per chunk: multiples of 4096, <= ~2048 chunks
   uint64_t rounds = (pair_capacity + 4096ull * 2048 - 1) / (4096ull * 2048);
   return (uint32_t)((rounds < 1 ? 1 : rounds) * 4096);
@@ -246,6 +282,13 @@ __device__ __forceinline__ float warp_sum(float v) {
 __device__ __forceinline__ float fast_exp(float x) { return exp2f(x * 1.4426950408889634f); }
 
 }  // namespace ocrf
+
+// launch_chain() whose failure leaves the enclosing int-returning function with the cudaError_t
+#define OCRF_LAUNCH(...)                                  \
+  do {                                                    \
+    cudaError_t le__ = ocrf::launch_chain(__VA_ARGS__);   \
+    if (le__ != cudaSuccess) return (int)le__;            \
+  } while (0)
 
 #define OCRF_CHECK_LAST()                   \
   do {                                      \

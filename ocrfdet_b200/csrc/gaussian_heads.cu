@@ -870,7 +870,7 @@ static bool gh_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p)
 static int gh_grid(long long n, size_t smem) {
   const long long tiles = (n + GH_ROWS - 1) / GH_ROWS;
   const int per_sm = (int)((220 * 1024) / (smem + 1024));
-  const long long cap = (long long)NUM_SMS * (per_sm < 1 ? 1 : per_sm);
+  const long long cap = (long long)num_sms() * (per_sm < 1 ? 1 : per_sm);
   return (int)(tiles < cap ? tiles : cap);
 }
 
@@ -926,7 +926,7 @@ extern "C" int ocrf_gaussian_heads_backward(void* stream, int64_t n, int32_t F, 
                                          (int)smem1);
     if (e != cudaSuccess) return (int)e;
     const long long tiles1 = (n + GH_ROWS - 1) / GH_ROWS;
-    const long long cap1 = (long long)NUM_SMS * 8;  // residency of the rows kernel: 128 registers x 64 threads, 26 KB
+    const long long cap1 = (long long)num_sms() * 8;  // residency of the rows kernel: 128 registers x 64 threads, 26 KB
     gaussian_heads_backward_rows_kernel<<<(unsigned)(tiles1 < cap1 ? tiles1 : cap1), GH_THREADS, smem1, st>>>(
         n, F, w1t, w2, b2, hidden, g_opacity, g_scales, g_rotations, g_colors, g_hidden, g_feat, g_w2, g_b2);
     const size_t smem2 = (size_t)GHW_STAGES * GHW_ROWS * (F + 4 + GH_HID) * 4;
@@ -934,7 +934,7 @@ extern "C" int ocrf_gaussian_heads_backward(void* stream, int64_t n, int32_t F, 
     if (e != cudaSuccess) return (int)e;
     const long long tiles2 = (n + GHW_ROWS - 1) / GHW_ROWS;
     const int per_sm = (int)((220 * 1024) / (smem2 + 1024));
-    const long long cap = (long long)NUM_SMS * (per_sm < 1 ? 1 : per_sm);
+    const long long cap = (long long)num_sms() * (per_sm < 1 ? 1 : per_sm);
     const int owner_threads = 4 * ((F + 3 + 3) / 4);
     const int threads2 = ((owner_threads + 31) / 32) * 32 + 32;  // + the dL/db1 warp
     gaussian_heads_backward_weights_kernel<<<(unsigned)(tiles2 < cap ? tiles2 : cap), threads2, smem2, st>>>(

@@ -178,7 +178,8 @@ __global__ void __launch_bounds__(MS_THREADS) ms_count_kernel(
 // (B1) exclusive scan over the chunks of every tile (in place) + tile totals, for both tables.
 // One WARP per tile: the lanes take 32 consecutive chunks, so a tile's column is read in
 // ceil(chunks/32) parallel round trips instead of one dependent load per chunk.
-__global__ void __launch_bounds__(256) ms_scan_chunks_kernel(OcrfShape sh, int chunks_max, uint32_t Q,
+__global__ void __launch_bounds__(256) ms_scan_chunks_kernel(OcrfShape sh, int chunks_max, uint32_t Q, uint64_t n_cap,
+                                                             const uint32_t* __restrict__ header,
                                                              const uint32_t* __restrict__ view_start,
                                                              const uint32_t* __restrict__ sorted_offsets,
                                                              uint32_t* __restrict__ cnt_full,
@@ -191,9 +192,12 @@ __global__ void __launch_bounds__(256) ms_scan_chunks_kernel(OcrfShape sh, int c
   const int lane = threadIdx.x & 31;
   const int t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
   if (t >= tiles) return;
+  // capacity overflow: ms_count_kernel left the tables unwritten and the real pair count is not bounded by the
+  // table extent -- touch nothing (ms_scan_tiles_kernel zeroes the range tables)
+  if ((uint64_t)header[HDR_NUM_PAIRS] > n_cap) return;
   uint32_t pb, pe;
   ms_view_pairs(v, view_start, sorted_offsets, pb, pe);
-  const int nchunks = (int)(((uint64_t)(pe - pb) + Q - 1) / Q);
+  const int nchunks = min(chunks_max, (int)(((uint64_t)(pe - pb) + Q - 1) / Q));
   uint32_t* cf = cnt_full + (size_t)v * chunks_max * tiles + t;
   uint32_t* ck = cnt_kept + (size_t)v * chunks_max * tiles + t;
   uint32_t rf = 0, rk = 0;
@@ -236,11 +240,13 @@ __global__ void __launch_bounds__(1024) ms_scan_tiles_kernel(int n_tiles, const 
                                                              const uint32_t* __restrict__ tot_kept,
                                                              uint32_t* __restrict__ tile_offset,
                                                              uint2* __restrict__ ranges,
-                                                             uint2* __restrict__ ranges_render) {
+                                                             uint2* __restrict__ ranges_render,
+                                                             uint32_t* __restrict__ sticky) {
   pdl_enter();
   __shared__ uint32_t s_warp[32];
   __shared__ uint32_t s_carry, s_total;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (sticky != nullptr && tid == 0) publish_status(header, n_cap, sticky);
   if ((uint64_t)header[HDR_NUM_PAIRS] > n_cap) {  // capacity overflow: nothing was binned, render background only
     for (int i = tid; i < n_tiles; i += 1024) {
       ranges[i] = make_uint2(0u, 0u);
@@ -419,7 +425,7 @@ int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity,
                    const float* colors, uint32_t* header, const uint32_t* view_start, const uint32_t* sorted_offsets,
                    const uint32_t* vis_vals, const float2* xy, const float4* conic_opacity, const float* depths,
                    const float* rgb, uint32_t* tables, size_t table_words, uint32_t* tile_arrays, uint2* items,
-                   uint2* ranges, uint2* ranges_render, Record* records) {
+                   uint2* ranges, uint2* ranges_render, Record* records, uint32_t* sticky) {
   const int tiles_v = tiles_x(*sh) * tiles_y(*sh);
   if (tiles_v > 8191) return OCRF_ECAPACITY;
   // chunk size: multiples of MS_ROUND pairs, at most ~2048 chunks for the whole capacity
@@ -435,14 +441,11 @@ int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity,
   uint32_t* tile_offset = tot_kept + (size_t)sh->V * tiles_v;
   const size_t smem_a = (size_t)2 * tiles_v * 4 + MS_ROUND * 2;
   const size_t smem_c = (size_t)2 * tiles_v * 4 + (size_t)(MS_WARPS + 1) * 2 * tiles_v * 2;
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(ms_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    e = cudaFuncSetAttribute(ms_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e != cudaSuccess) return (int)e;
-    attr = true;
-  }
+  static unsigned long long attr_a = 0, attr_c = 0;  // per-device bit masks
+  cudaError_t ae = ensure_dynamic_smem(ms_count_kernel, 100 * 1024, attr_a);
+  if (ae != cudaSuccess) return (int)ae;
+  ae = ensure_dynamic_smem(ms_scatter_kernel, 200 * 1024, attr_c);
+  if (ae != cudaSuccess) return (int)ae;
   if (smem_a > 100 * 1024 || smem_c > 200 * 1024) return OCRF_ECAPACITY;
   const dim3 grid(chunks_max, sh->V);
 #ifdef OCRF_DIAG  // timing experiments only: repeat an idempotent kernel, the stage-time delta is its in-stream cost
@@ -452,16 +455,16 @@ int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity,
 #define OCRF_DIAG_REP(bit) 1
 #endif
   for (int rep = 0; rep < OCRF_DIAG_REP(0); rep++)
-  launch_chain(ms_count_kernel, dim3(grid), dim3(MS_THREADS), smem_a, st, *sh, chunks_max, Q, pair_capacity, header, view_start, sorted_offsets,
+  OCRF_LAUNCH(ms_count_kernel, dim3(grid), dim3(MS_THREADS), smem_a, st, *sh, chunks_max, Q, pair_capacity, header, view_start, sorted_offsets,
                                                     vis_vals, radii, xy, conic_opacity, cnt_full, cnt_kept, items);
-  launch_chain(ms_scan_chunks_kernel, dim3(ceil_div(tiles_v, 8), sh->V), dim3(256), 0, st, *sh, chunks_max, Q, view_start,
-                                                                             sorted_offsets, cnt_full, cnt_kept, tot_full,
+  OCRF_LAUNCH(ms_scan_chunks_kernel, dim3(ceil_div(tiles_v, 8), sh->V), dim3(256), 0, st, *sh, chunks_max, Q, pair_capacity,
+                                                                             header, view_start, sorted_offsets, cnt_full, cnt_kept, tot_full,
                                                                              tot_kept);
   for (int rep = 0; rep < OCRF_DIAG_REP(1); rep++)
-  launch_chain(ms_scan_tiles_kernel, dim3(1), dim3(1024), 0, st, sh->V * tiles_v, header, pair_capacity, tot_full, tot_kept, tile_offset, ranges,
-                                           ranges_render);
+  OCRF_LAUNCH(ms_scan_tiles_kernel, dim3(1), dim3(1024), 0, st, sh->V * tiles_v, header, pair_capacity, tot_full, tot_kept, tile_offset, ranges,
+                                           ranges_render, sticky);
   for (int rep = 0; rep < OCRF_DIAG_REP(2); rep++)
-  launch_chain(ms_scatter_kernel, dim3(grid), dim3(MS_THREADS), smem_c, st, *sh, chunks_max, Q, pair_capacity, use_sh, sh->C == 3, header,
+  OCRF_LAUNCH(ms_scatter_kernel, dim3(grid), dim3(MS_THREADS), smem_c, st, *sh, chunks_max, Q, pair_capacity, use_sh, sh->C == 3, header,
                                                       view_start, sorted_offsets, items, xy, conic_opacity, depths, rgb,
                                                       colors, cnt_full, cnt_kept, tile_offset, records);
   cudaError_t e = cudaGetLastError();

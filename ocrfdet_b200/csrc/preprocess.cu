@@ -251,7 +251,7 @@ extern "C" int ocrf_preprocess_forward(void* stream, const OcrfShape* sh, const 
   const int blocks = bpv * sh->V;
   // header and look-back state are adjacent: one memset resets both
   cudaMemsetAsync(at<char>(geom_ws, L.header), 0, L.depths - L.header, st);
-  launch_chain(preprocess_forward_kernel, dim3(blocks), dim3(PRE_THREADS), 0, st, 
+  OCRF_LAUNCH(preprocess_forward_kernel, dim3(blocks), dim3(PRE_THREADS), 0, st, 
       *sh, bpv, means3D, scales, rotations, cov3D_precomp, opacities, shs, reinterpret_cast<const Camera*>(cams),
       scale_modifier, prefiltered, radii, at<uint32_t>(geom_ws, L.header), at<float>(geom_ws, L.depths),
       at<float2>(geom_ws, L.xy), at<float4>(geom_ws, L.conic_opacity), at<uint32_t>(geom_ws, L.tiles_touched),

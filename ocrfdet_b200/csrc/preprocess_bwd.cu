@@ -277,7 +277,7 @@ extern "C" int ocrf_preprocess_backward(void* stream, const OcrfShape* sh, const
   const size_t smem = (size_t)sh->views_per_sample * sizeof(Camera);
   if (smem > 48 * 1024) return OCRF_ECAPACITY;
   const dim3 grid(ceil_div(sh->P, PB_THREADS), sh->S);
-  launch_chain(preprocess_backward_kernel, dim3(grid), dim3(PB_THREADS), smem, static_cast<cudaStream_t>(stream), 
+  OCRF_LAUNCH(preprocess_backward_kernel, dim3(grid), dim3(PB_THREADS), smem, static_cast<cudaStream_t>(stream), 
       *sh, means3D, scales, rotations, cov3D_precomp, shs, reinterpret_cast<const Camera*>(cams), scale_modifier,
       radii, at<uint8_t>(geom_ws, G.clamped), ggrad, dL_dcolors_view, dL_dmeans3D, dL_dmeans2D, dL_dopacities,
       dL_dscales, dL_drotations, dL_dcov3D, dL_dshs);

@@ -194,14 +194,10 @@ template <int ITEMS>
 static int launch_onesweep(cudaStream_t st, unsigned tiles, const uint64_t* kin, const uint32_t* vin, uint64_t* kout,
                            uint32_t* vout, const uint32_t* n_dev, uint64_t n_cap, int shift, int bits,
                            const uint32_t* hist, uint32_t* status, uint32_t* ticket) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(sort_onesweep_kernel<ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)sort_smem_bytes<ITEMS>());
-    if (e != cudaSuccess) return (int)e;
-    attr_set = true;
-  }
-  launch_chain(sort_onesweep_kernel<ITEMS>, dim3(tiles), dim3(SORT_THREADS), sort_smem_bytes<ITEMS>(), st, kin, vin, kout, vout, n_dev, n_cap, shift,
+  static unsigned long long attr_done = 0;  // per-device bit mask
+  const cudaError_t ae = ensure_dynamic_smem(sort_onesweep_kernel<ITEMS>, sort_smem_bytes<ITEMS>(), attr_done);
+  if (ae != cudaSuccess) return (int)ae;
+  OCRF_LAUNCH(sort_onesweep_kernel<ITEMS>, dim3(tiles), dim3(SORT_THREADS), sort_smem_bytes<ITEMS>(), st, kin, vin, kout, vout, n_dev, n_cap, shift,
                                                                                     bits, hist, status, ticket);
   return 0;
 }
@@ -219,8 +215,8 @@ int sort_pairs_device(cudaStream_t st, const uint32_t* n_dev, uint64_t n_cap, in
   const uint64_t tiles = sort_tiles(n_cap);
   if (!ws_zeroed) cudaMemsetAsync(ws, 0, L.status + (size_t)passes * (tiles + 1) * 256 * 4, st);
   uint32_t* hist = at<uint32_t>(ws, L.hist);
-  const int hgrid = (int)min((uint64_t)NUM_SMS * 8, (n_cap + SORT_THREADS * 4 - 1) / (SORT_THREADS * 4));
-  launch_chain(sort_histogram_kernel, dim3(hgrid), dim3(SORT_THREADS), 0, st, keys_a, n_dev, n_cap, passes, begin_bit, end_bit, hist,
+  const int hgrid = (int)min((uint64_t)num_sms() * 8, (n_cap + SORT_THREADS * 4 - 1) / (SORT_THREADS * 4));
+  OCRF_LAUNCH(sort_histogram_kernel, dim3(hgrid), dim3(SORT_THREADS), 0, st, keys_a, n_dev, n_cap, passes, begin_bit, end_bit, hist,
                zero_extra, zero_words);
   uint64_t* kin = keys_a;
   uint32_t* vin = vals_a;

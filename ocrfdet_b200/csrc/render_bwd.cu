@@ -561,15 +561,15 @@ extern "C" int ocrf_render_backward(void* stream, const OcrfShape* sh, uint64_t 
     static const int ppt = env_int_b("OCRF_BWD_PPT", 4);
     const Record* rec = at<Record>(bin_ws, B.records);
     if (ppt == 4)
-      launch_chain(render_backward_c3_kernel<4>, dim3(grid), dim3(TILE_PIX / 4), 0, st, sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
+      OCRF_LAUNCH(render_backward_c3_kernel<4>, dim3(grid), dim3(TILE_PIX / 4), 0, st, sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
                                                                   ranges, rec, bg, fT, nc, mc, dL_dcolor,
                                                                   dL_dopacity_map, ggrad, dL_dcolors);
     else if (ppt == 2)
-      launch_chain(render_backward_c3_kernel<2>, dim3(grid), dim3(TILE_PIX / 2), 0, st, sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
+      OCRF_LAUNCH(render_backward_c3_kernel<2>, dim3(grid), dim3(TILE_PIX / 2), 0, st, sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
                                                                   ranges, rec, bg, fT, nc, mc, dL_dcolor,
                                                                   dL_dopacity_map, ggrad, dL_dcolors);
     else
-      launch_chain(render_backward_c3_kernel<1>, dim3(grid), dim3(TILE_PIX), 0, st, sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
+      OCRF_LAUNCH(render_backward_c3_kernel<1>, dim3(grid), dim3(TILE_PIX), 0, st, sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
                                                               ranges, rec, bg, fT, nc, mc, dL_dcolor, dL_dopacity_map,
                                                               ggrad, dL_dcolors);
   } else {
@@ -601,8 +601,8 @@ extern "C" int ocrf_clear_gradients(void* stream, const OcrfShape* sh, int use_s
   const size_t n_color = use_sh ? n_pairs * 3 : (size_t)sh->S * sh->P * sh->C;
   if (n_pairs == 0) return 0;
   const size_t want = (n_pairs + 255) / 256;
-  const unsigned grid = (unsigned)(want < (size_t)NUM_SMS * 8 ? want : (size_t)NUM_SMS * 8);
-  launch_chain(clear_gradients_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), n_pairs, radii, ggrad,
+  const unsigned grid = (unsigned)(want < (size_t)num_sms() * 8 ? want : (size_t)num_sms() * 8);
+  OCRF_LAUNCH(clear_gradients_kernel, dim3(grid), dim3(256), 0, static_cast<cudaStream_t>(stream), n_pairs, radii, ggrad,
                n_color / 4, n_color, dL_dcolors);
   OCRF_CHECK_LAST();
   return 0;

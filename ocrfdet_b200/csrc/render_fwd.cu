@@ -416,13 +416,13 @@ extern "C" int ocrf_render_forward(void* stream, const OcrfShape* sh, uint64_t p
     static const int ppt = env_int("OCRF_FWD_PPT", 2);
     const Record* rec = at<Record>(bin_ws, B.records);
     if (ppt == 4)
-      launch_chain(render_forward_c3_kernel<4>, dim3(grid), dim3(TILE_PIX / 4), 0, st, sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
+      OCRF_LAUNCH(render_forward_c3_kernel<4>, dim3(grid), dim3(TILE_PIX / 4), 0, st, sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
                                                                  out_depth, out_opacity);
     else if (ppt == 2)
-      launch_chain(render_forward_c3_kernel<2>, dim3(grid), dim3(TILE_PIX / 2), 0, st, sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
+      OCRF_LAUNCH(render_forward_c3_kernel<2>, dim3(grid), dim3(TILE_PIX / 2), 0, st, sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
                                                                  out_depth, out_opacity);
     else
-      launch_chain(render_forward_c3_kernel<1>, dim3(grid), dim3(TILE_PIX), 0, st, sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
+      OCRF_LAUNCH(render_forward_c3_kernel<1>, dim3(grid), dim3(TILE_PIX), 0, st, sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
                                                              out_depth, out_opacity);
   } else {
     (void)use_sh;

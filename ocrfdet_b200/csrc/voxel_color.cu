@@ -145,7 +145,7 @@ extern "C" int ocrf_retain_valid_pixels(void* stream, int32_t V, int64_t M, int3
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const size_t n = (size_t)V * C * H * W;
   const size_t want = (n / 4 + 255) / 256;
-  fill_value_kernel<<<(unsigned)(want < (size_t)NUM_SMS * 8 ? (want ? want : 1) : (size_t)NUM_SMS * 8), 256, 0, st>>>(
+  fill_value_kernel<<<(unsigned)(want < (size_t)num_sms() * 8 ? (want ? want : 1) : (size_t)num_sms() * 8), 256, 0, st>>>(
       n / 4, n, fill, out);
   if (M > 0) {
     const dim3 grid((unsigned)((M + 255) / 256), (unsigned)V);

@@ -83,4 +83,9 @@ class GraphedRenderStep:
         return self.outs, self.grads
 
     def check_overflow(self):
-        R.check_overflow()
+        """Raise if ANY replay since the last check overflowed `pair_capacity`.  Every replay ORs its error flags into
+        the device's sticky status words (`sticky_status` of ocrf_bin_forward), which no forward clears -- the geom
+        header itself is re-zeroed by each replay's preprocess -- so one read-back covers any number of replays.
+        The captured step also mirrors those words into pinned host memory, so the same error surfaces without a
+        synchronisation at the next eager `render_batch` call."""
+        R.check_overflow(self.cams.device)

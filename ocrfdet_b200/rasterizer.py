@@ -81,6 +81,59 @@ def _require_cuda(t, name):
         raise _lib.OcrfError("%s must be a CUDA tensor: the render path has no CPU implementation" % name)
 
 
+class _Status:
+    """Per-device sticky status words of the render path (`sticky_status` of ocrf_bin_forward).
+
+    The library ORs the error flags of every call into `dev[0]` and keeps the largest pair count in `dev[1]`; it
+    never clears them.  Capacity-mode calls (no host read-back) queue an 8-byte copy into the pinned mirror `host`
+    after their forward, and every later entry into the path (`render_batch`, the autograd backward,
+    `check_overflow`) looks at the mirror: an overflow is reported at the next call without any synchronisation --
+    a training loop cannot keep rendering background images unnoticed.  Device words, not Python state, carry the
+    flag, so concurrent streams and CUDA-graph replays all land in the same place.
+    """
+    _per_device = {}
+
+    def __init__(self, device):
+        self.dev = torch.zeros(2, dtype=torch.int32, device=device)
+        self.host = torch.zeros(2, dtype=torch.int32).pin_memory()
+        self.host_np = self.host.numpy()  # same memory: polling costs a numpy scalar read, not a tensor op
+
+    @classmethod
+    def get(cls, device):
+        device = torch.device(device)
+        if device.index is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        st = cls._per_device.get(device.index)
+        if st is None:
+            st = cls._per_device[device.index] = cls(device)
+        return st
+
+    def mirror(self):
+        """Queue the 8-byte copy of the status words into the pinned mirror (asynchronous, capturable)."""
+        self.host.copy_(self.dev, non_blocking=True)
+
+    def _raise(self, flags, pairs):
+        self.dev.zero_()
+        self.host_np[:] = 0
+        if flags & 1:
+            raise _lib.OcrfError("binning workspace overflow: %d (tile, Gaussian) pairs exceed pair_capacity; that "
+                                 "call rendered background only" % (pairs & 0xFFFFFFFF))
+        raise _lib.OcrfError("Point is filtered although prefiltered is set. This shouldn't happen!")
+
+    def poll(self):
+        """Non-blocking: raise if a mirrored status word shows an error of an earlier call."""
+        flags = int(self.host_np[0])
+        if flags & 3:
+            self._raise(flags, int(self.host_np[1]))
+
+    def check(self):
+        """Blocking: read the device words (8 bytes) and raise if any call since the last check failed."""
+        h = self.dev.cpu()
+        flags = int(h[0])
+        if flags & 3:
+            self._raise(flags, int(h[1]))
+
+
 class _Workspaces:
     """Byte layouts of the three caller-owned workspaces (one query each, no GPU work)."""
 
@@ -103,6 +156,14 @@ class _RasterizeBatch(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, means3D, means2D, shs, colors, opacities, scales, rotations, cov3D_precomp, cams, bg, cfg):
+        _Status.get(means3D.device).poll()  # an overflow of an earlier capacity-mode call surfaces here, sync-free
+        args = (ctx, means3D, means2D, shs, colors, opacities, scales, rotations, cov3D_precomp, cams, bg, cfg)
+        if cfg.get("debug"):
+            return _debug_guard("forward", "snapshot_fw.dump", args[1:], lambda: _RasterizeBatch._forward_impl(*args))
+        return _RasterizeBatch._forward_impl(*args)
+
+    @staticmethod
+    def _forward_impl(ctx, means3D, means2D, shs, colors, opacities, scales, rotations, cov3D_precomp, cams, bg, cfg):
         L = _lib.lib()
         S, P = means3D.shape[0], means3D.shape[1]
         V = cams.shape[0]
@@ -112,6 +173,8 @@ class _RasterizeBatch(torch.autograd.Function):
         shape = OcrfShape(S, P, V, V // S, W, H, Cc, cfg["sh_degree"], shs.shape[2] if use_sh else 0)
         dev = means3D.device
         stream = current_stream()
+        status = _Status.get(dev)
+        debug = bool(cfg.get("debug"))
         if use_sh and cfg.get("colors_ready") is not None:
             torch.cuda.current_stream().wait_event(cfg["colors_ready"])
         ws = _Workspaces(shape, use_sh)
@@ -127,6 +190,8 @@ class _RasterizeBatch(torch.autograd.Function):
                                         C.c_float(cfg["scale_modifier"]), int(cfg["prefiltered"]), ptr(radii),
                                         ptr(geom)), "ocrf_preprocess_forward")
         _stage("preprocess")
+        if debug:
+            _debug_sync("preprocess")
         if cfg.get("colors_ready") is not None and not use_sh:   # SH coefficients are read by the preprocess itself
             torch.cuda.current_stream().wait_event(cfg["colors_ready"])
         capacity = cfg.get("pair_capacity")
@@ -135,25 +200,33 @@ class _RasterizeBatch(torch.autograd.Function):
             # rasterizer_impl.cu:281)
             hdr = geom[ws.geom.header:ws.geom.header + 8].view(torch.int32).cpu()
             num_pairs, err = int(hdr[0]) & 0xFFFFFFFF, int(hdr[1])
-            if err & 2:
+            if err & 2:  # the reference traps on the device here (CR/auxiliary.h:156-160)
+                status.dev.zero_()
                 raise _lib.OcrfError("Point is filtered although prefiltered is set. This shouldn't happen!")
             capacity = num_pairs
         else:
             num_pairs = None
+            capacity = max(int(capacity), 1)
         binl = _Workspaces.bin_layout(shape, capacity)
         binning = torch.empty(binl.total, dtype=torch.uint8, device=dev)
         check(L.ocrf_bin_forward(stream, C.byref(shape), C.c_uint64(capacity), ptr(radii), ptr(colors), int(use_sh),
                                  C.c_uint32({"pairsort": _lib.OCRF_BIN_PAIR_SORT, "depthfirst": _lib.OCRF_BIN_DEPTH_FIRST}
                                             .get(cfg.get("binning"), 0)),
-                                 ptr(geom), ptr(binning), ptr(image)), "ocrf_bin_forward")
+                                 ptr(geom), ptr(binning), ptr(image), ptr(status.dev)), "ocrf_bin_forward")
         _stage("binning")
+        if debug:
+            _debug_sync("binning")
+            status.check()
         check(L.ocrf_render_forward(stream, C.byref(shape), C.c_uint64(capacity), ptr(colors), int(use_sh), ptr(bg),
                                     ptr(geom), ptr(binning), ptr(image), ptr(color), ptr(depth), ptr(opac)),
               "ocrf_render_forward")
         _stage("render_forward")
+        if debug:
+            _debug_sync("render_forward")
+        if num_pairs is None:
+            status.mirror()  # capacity mode: the next entry into the path sees this call's flags without a sync
 
-        global _LAST_HEADER, _LAST_STATE
-        _LAST_HEADER = geom[ws.geom.header:ws.geom.header + 8]
+        global _LAST_STATE
         if KEEP_STATE:
             _LAST_STATE = dict(shape=shape, layouts=(ws.geom, binl, ws.image), geom=geom, binning=binning, image=image,
                                radii=radii, capacity=capacity, colors=colors, use_sh=use_sh,
@@ -170,12 +243,21 @@ class _RasterizeBatch(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g_color, _g_radii, _g_depth, g_opac):
+        _Status.get(ctx.saved_tensors[0].device).poll()
+        if ctx.cfg.get("debug"):
+            return _debug_guard("backward", "snapshot_bw.dump", tuple(ctx.saved_tensors) + (g_color, g_opac, ctx.cfg),
+                                lambda: _RasterizeBatch._backward_impl(ctx, g_color, g_opac))
+        return _RasterizeBatch._backward_impl(ctx, g_color, g_opac)
+
+    @staticmethod
+    def _backward_impl(ctx, g_color, g_opac):
         L = _lib.lib()
         means3D, shs, colors, scales, rotations, cov3D_precomp, cams, bg, radii, geom, binning, image = ctx.saved_tensors
         shape, cfg, use_sh = ctx.shape, ctx.cfg, ctx.use_sh
         S, P, V, Cc = shape.S, shape.P, shape.V, shape.C
         dev = means3D.device
         stream = current_stream()
+        debug = bool(cfg.get("debug"))
         _stage("backward_begin")
         if g_color is None:
             g_color = torch.zeros((V, Cc, shape.H, shape.W), dtype=torch.float32, device=dev)
@@ -189,6 +271,8 @@ class _RasterizeBatch(torch.autograd.Function):
                                      ptr(bg), ptr(geom), ptr(binning), ptr(image), ptr(g_color), ptr(g_opac),
                                      ptr(ggrad), ptr(g_feat)), "ocrf_render_backward")
         _stage("render_backward")
+        if debug:
+            _debug_sync("render_backward")
         g_means3D = torch.empty_like(means3D)
         # dL/dmean2D is only materialised when the caller holds a means2D leaf (the reference's screenspace_points)
         g_means2D = torch.empty((V, P, 3), dtype=torch.float32, device=dev) if ctx.needs_input_grad[1] else None
@@ -204,11 +288,12 @@ class _RasterizeBatch(torch.autograd.Function):
                                          ptr(g_means3D), ptr(g_means2D), ptr(g_opacities), ptr(g_scales), ptr(g_rots),
                                          ptr(g_cov), ptr(g_shs)), "ocrf_preprocess_backward")
         _stage("preprocess_backward")
+        if debug:
+            _debug_sync("preprocess_backward")
         return (g_means3D, g_means2D, g_shs, None if use_sh else g_feat, g_opacities, g_scales, g_rots, g_cov, None,
                 None, None)
 
 
-_LAST_HEADER = None  # geom header of the most recent forward (for check_overflow in capacity mode)
 KEEP_STATE = False   # tests / bench statistics: keep the workspaces of the most recent forward alive
 _LAST_STATE = None
 STAGE_HOOK = None    # bench: callable(name) invoked on the launching stream after each stage's launches
@@ -217,6 +302,29 @@ STAGE_HOOK = None    # bench: callable(name) invoked on the launching stream aft
 def _stage(name):
     if STAGE_HOOK is not None:
         STAGE_HOOK(name)
+
+
+def _debug_sync(stage):
+    """`debug=True` (PKG:83-90 -> CHECK_CUDA, CR/auxiliary.h:166-173): synchronise after every stage and raise
+    on the first CUDA error, naming the stage."""
+    rc = _lib.lib().ocrf_debug_sync(current_stream())
+    if rc != 0:
+        raise _lib.OcrfError("%s failed (debug mode): %s (code %d)"
+                             % (stage, _lib.lib().ocrf_error_string(rc).decode(), rc))
+
+
+def _debug_guard(which, dump_name, args, fn):
+    """PKG:83-90 / PKG:132-139: copy the arguments to the CPU before the call; if it raises, save them as
+    `snapshot_fw.dump` / `snapshot_bw.dump` in the working directory and re-raise."""
+    plain = (int, float, bool, str, type(None))
+    cpu_args = tuple(a.detach().cpu().clone() if torch.is_tensor(a) else
+                     ({k: v for k, v in a.items() if isinstance(v, plain)} if isinstance(a, dict) else a) for a in args)
+    try:
+        return fn()
+    except Exception:
+        torch.save(cpu_args, dump_name)
+        print("\nAn error occured in %s. Please forward %s for debugging." % (which, dump_name))
+        raise
 
 
 def last_state(reference_lists=False):
@@ -277,7 +385,8 @@ def last_state(reference_lists=False):
 
 def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors_precomp=None, shs=None, scales=None,
                  rotations=None, cov3D_precomp=None, means2D=None, scale_modifier=1.0, sh_degree=0, prefiltered=False,
-                 pair_capacity: Optional[int] = None, binning: Optional[str] = None, colors_ready=None):
+                 pair_capacity: Optional[int] = None, binning: Optional[str] = None, colors_ready=None,
+                 debug: bool = False):
     """Render V = cams.shape[0] views of S = means3D.shape[0] samples in one launch sequence.
 
     means3D [S,P,3]; opacities [S,P,1]; colors_precomp [S,P,C] or shs [S,P,M,3]; scales [S,P,3] and
@@ -293,28 +402,53 @@ def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors
     launching stream waits for the event only after the preprocess has been queued.
     `pair_capacity`: if given, the binning workspace is sized for that many (tile, Gaussian) pairs
     and NO host synchronisation happens (CUDA-graph friendly); an overflow renders background and
-    raises on the next `check_overflow`.
+    raises at the next entry into the path (`render_batch`, the backward) or `check_overflow()`, whichever comes first.
+    `debug`: the reference's debug mode (PKG:83-90,132-139; CR/auxiliary.h:166-173): synchronise and check for CUDA
+    errors after every stage, and on any failure save the CPU copy of the arguments as `snapshot_fw.dump` /
+    `snapshot_bw.dump` before re-raising.
     """
     _require_cuda(means3D, "means3D")
     if means3D.dim() != 3 or means3D.shape[-1] != 3:
         raise Exception("means3D must have dimensions (samples, num_points, 3)")
     S, P = means3D.shape[0], means3D.shape[1]
+    if cams.dim() != 2 or cams.shape[1] != _lib.OCRF_CAM_STRIDE:
+        raise Exception("cams must have dimensions (views, %d): build it with pack_cameras" % _lib.OCRF_CAM_STRIDE)
     V = cams.shape[0]
-    if V % S != 0:
-        raise Exception("the number of views must be a multiple of the number of samples")
+    if V == 0 or V % S != 0:
+        raise Exception("the number of views must be a positive multiple of the number of samples")
     if (shs is None) == (colors_precomp is None):
         raise Exception('Please provide excatly one of either SHs or precomputed colors!')
     if ((scales is None or rotations is None) and cov3D_precomp is None) or \
             ((scales is not None or rotations is not None) and cov3D_precomp is not None):
         raise Exception('Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!')
+    Cc = 3 if shs is not None else colors_precomp.shape[-1]
+
+    def expect(t, name, *tail):
+        if t is not None and tuple(t.shape) != (S, P) + tail:
+            raise Exception("%s must have dimensions %s, got %s" % (name, (S, P) + tail, tuple(t.shape)))
+
+    if opacities.numel() != S * P:
+        raise Exception("opacities must have dimensions (%d, %d, 1), got %s" % (S, P, tuple(opacities.shape)))
+    expect(colors_precomp, "colors_precomp", Cc)
+    expect(scales, "scales", 3)
+    expect(rotations, "rotations", 4)
+    expect(cov3D_precomp, "cov3D_precomp", 6)
+    if shs is not None and (shs.dim() != 4 or tuple(shs.shape[:2]) != (S, P) or shs.shape[3] != 3):
+        raise Exception("shs must have dimensions (%d, %d, M, 3), got %s" % (S, P, tuple(shs.shape)))
+    if bg.numel() < Cc:  # the kernels read bg[k] for every channel k
+        raise Exception("bg must hold one value per channel (%d), got %d" % (Cc, bg.numel()))
+    if Cc > 96 and torch.is_grad_enabled() and any(
+            t is not None and t.requires_grad for t in (means3D, opacities, colors_precomp, scales, rotations,
+                                                        cov3D_precomp, means2D)):
+        raise Exception("more than 96 feature channels are forward-only: the blend backward keeps a pixel's upstream "
+                        "gradient in registers (C <= 96)")
     f = lambda t: None if t is None else t.float().contiguous()  # noqa: E731
     if means2D is None:  # gradient holder only, never read: no fill, and no dL/dmean2D output in backward
         means2D = torch.empty((V, P, 3), dtype=torch.float32, device=means3D.device)
     cfg = dict(W=int(image_width), H=int(image_height), scale_modifier=float(scale_modifier), sh_degree=int(sh_degree),
-               prefiltered=bool(prefiltered), pair_capacity=pair_capacity, colors_ready=colors_ready,
+               prefiltered=bool(prefiltered), pair_capacity=pair_capacity, colors_ready=colors_ready, debug=bool(debug),
                binning=binning if binning is not None else os.environ.get("OCRF_BINNING", "split"))
     if P == 0:
-        Cc = 3 if shs is not None else colors_precomp.shape[-1]
         z = lambda c: torch.zeros((V, c, cfg["H"], cfg["W"]), dtype=torch.float32, device=means3D.device)  # noqa
         return z(Cc), torch.zeros((V, 0), dtype=torch.int32, device=means3D.device), z(1), z(1)
     return _RasterizeBatch.apply(f(means3D), means2D, f(shs), f(colors_precomp), f(opacities), f(scales), f(rotations),
@@ -345,7 +479,8 @@ def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales,
     color, radii, depth, opac = render_batch(
         u(means3D), u(opacities.reshape(P, 1)), cams, H, W, st.bg.to(dev), colors_precomp=u(colors_precomp),
         shs=u(sh), scales=u(scales), rotations=u(rotations), cov3D_precomp=u(cov3Ds_precomp), means2D=m2d,
-        scale_modifier=st.scale_modifier, sh_degree=st.sh_degree, prefiltered=st.prefiltered)
+        scale_modifier=st.scale_modifier, sh_degree=st.sh_degree, prefiltered=st.prefiltered,
+        debug=bool(getattr(st, "debug", False)))
     out = (color[0], radii[0], depth[0])
     return out + ((opac[0],) if return_opacity else ())
 
@@ -387,11 +522,10 @@ class GaussianRasterizer(nn.Module):
         return out if self.return_depth else out[:2] + out[3:]
 
 
-def check_overflow():
-    """Raise if the last capacity-mode render overflowed its binning workspace (reads 8 bytes: synchronises)."""
-    if _LAST_HEADER is None:
+def check_overflow(device=None):
+    """Raise if any capacity-mode render on `device` since the last check overflowed its binning workspace (such a
+    call renders background only).  Reads 8 bytes back: synchronises.  Calling it is optional -- the same error is
+    raised without a synchronisation at the next `render_batch` / backward after the overflowing call."""
+    if not torch.cuda.is_available():
         return
-    hdr = _LAST_HEADER.view(torch.int32)[:2].cpu()
-    if int(hdr[1]) & 1:
-        raise _lib.OcrfError("binning workspace overflow: %d (tile, Gaussian) pairs exceed pair_capacity"
-                             % (int(hdr[0]) & 0xFFFFFFFF))
+    _Status.get(device if device is not None else torch.device("cuda", torch.cuda.current_device())).check()

@@ -5,10 +5,23 @@ The reference scales by plain data parallelism over samples (MMDistributedDataPa
 cross-sample assembly point is `torch.cat(opacity_alpha_list, 0)` feeding the HOA lift
 (/root/reference/mmdet3d/models/necks/view_transformer_ocrf.py:1196).  Here every rank renders a
 contiguous block of (sample, view) pairs -- a sample's views stay on one rank so its Gaussian
-gradients need no reduction -- and the per-view opacity maps are assembled with ONE all-gather
-(NCCL over NVLink on the GPU box, gloo in the CPU tests), issued on a side stream so it overlaps the
-backward pass.
+gradients need no reduction -- and the per-view opacity maps are assembled with ONE all-gather.
+
+On the GPU box the gather does not run on the SMs.  The blend backward it overlaps with is bound by FP32 issue on
+all 148 SMs, and an NCCL all-gather takes SMs away from it (measured in round 1: the backward went from 0.268 ms
+at 1 GPU to 0.2875 ms at 8).  `gather_opacity_maps` therefore PUSHES the local maps into a symmetric buffer of
+every peer with plain device-to-device copies over the NVLink peer mapping -- copy-engine traffic, issued on a side
+stream -- bracketed by two single-CTA signal-pad barriers (torch symmetric memory: cuMem allocations exchanged over
+the process group's store, no NVSHMEM).  `transport="nccl"` (and every non-CUDA tensor: gloo in the CPU tests)
+uses `all_gather_into_tensor`.
+
+The gather is differentiable like the `torch.cat` it replaces: the backward hands every rank the gradient slice of
+its own maps (`grad="local"`, the consumer is replicated on every rank as in the reference's data parallelism, so
+the local loss already carries the whole gradient), or the sum of that slice over all ranks (`grad="sum"`, one
+reduce-scatter, for consumers that compute rank-specific losses from the gathered maps).
 """
+import os
+import warnings
 from typing import List, Tuple
 
 import torch
@@ -30,39 +43,128 @@ def shard_views(num_samples: int, views_per_sample: int, world_size: int, rank: 
     return [(s, v) for s in range(b, e) for v in range(views_per_sample)]
 
 
+class _PeerBuffers:
+    """Symmetric gather buffers [world, vmax, 1, H, W], one allocation per (group, shape), mapped into every rank."""
+    _cache = {}
+    _failed = None
+
+    def __init__(self, group, vmax, H, W, dtype, device):
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        n = self.world * vmax * H * W
+        self.buf = symm.empty(n, dtype=dtype, device=device)
+        pg = group if group is not None else dist.group.WORLD
+        self.hdl = symm.rendezvous(self.buf, pg)
+        shape = (self.world, vmax, 1, H, W)
+        self.views = [self.hdl.get_buffer(r, shape, dtype) for r in range(self.world)]
+
+    @classmethod
+    def get(cls, group, vmax, H, W, dtype, device):
+        key = (id(group), vmax, H, W, dtype, str(device))
+        if key not in cls._cache:
+            cls._cache[key] = cls(group, vmax, H, W, dtype, device)
+        return cls._cache[key]
+
+    def all_gather(self, send):
+        """Runs on the CURRENT stream.  Returns this rank's buffer [world, vmax, 1, H, W]; it is overwritten by the
+        next gather of the same shape (the opening barrier of that call waits until every rank got there, i.e. is
+        done with the previous contents in stream order)."""
+        self.hdl.barrier(channel=0)
+        for i in range(self.world):  # start with myself, then ring order: no two ranks push to the same peer first
+            peer = (self.rank + i) % self.world
+            self.views[peer][self.rank].copy_(send)  # contiguous same-dtype copy: cudaMemcpyAsync -> copy engine
+        self.hdl.barrier(channel=1)  # every rank's pushes are complete and visible
+        return self.views[self.rank]
+
+
+def _nccl_all_gather(send, world, vmax, group):
+    out = send.new_empty((world * vmax,) + tuple(send.shape[1:]))
+    dist.all_gather_into_tensor(out, send, group=group)
+    return out.view((world, vmax) + tuple(send.shape[1:]))
+
+
+def _gather_raw(send, world, vmax, group, transport):
+    """send [vmax,1,H,W] contiguous -> [world, vmax, 1, H, W] on the current stream."""
+    if send.is_cuda and transport == "peer" and _PeerBuffers._failed is None:
+        try:
+            pb = _PeerBuffers.get(group, vmax, send.shape[-2], send.shape[-1], send.dtype, send.device)
+        except Exception as e:  # noqa: BLE001  (no peer access / symmetric memory unavailable on this system)
+            _PeerBuffers._failed = e
+            warnings.warn("opacity-map gather: symmetric-memory peer copies unavailable (%s); using the NCCL "
+                          "all-gather, which shares the SMs with the blend backward" % (e,))
+        else:
+            return pb.all_gather(send)
+    return _nccl_all_gather(send, world, vmax, group)
+
+
+class _GatherMaps(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, local_maps, counts, group, stream, transport, grad_mode):
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        vmax = max(counts)
+        send = local_maps.detach()
+        if send.shape[0] != vmax:
+            pad = send.new_zeros((vmax,) + tuple(send.shape[1:]))
+            pad[:send.shape[0]] = send
+            send = pad
+        send = send.contiguous()
+        side = stream is not None and send.is_cuda
+        if side:
+            stream.wait_stream(torch.cuda.current_stream())
+            send.record_stream(stream)
+        with torch.cuda.stream(stream) if side else _null():
+            out = _gather_raw(send, world, vmax, group, transport)
+            if all(c == vmax for c in counts):
+                out = out.view((world * vmax,) + tuple(send.shape[1:]))
+            else:
+                out = torch.cat([out[r, :counts[r]] for r in range(world)], 0)
+        if side:
+            out.record_stream(torch.cuda.current_stream())  # produced on `stream`, consumed on the caller's stream
+        ctx.meta = (counts, rank, world, group, grad_mode, vmax)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        counts, rank, world, group, grad_mode, vmax = ctx.meta
+        begin = sum(counts[:rank])
+        if grad_mode == "local":
+            return g[begin:begin + counts[rank]], None, None, None, None, None
+        # grad == "sum": every rank's consumer produced a gradient for my maps
+        padded = g.new_zeros((world, vmax) + tuple(g.shape[1:]))
+        off = 0
+        for r in range(world):
+            padded[r, :counts[r]] = g[off:off + counts[r]]
+            off += counts[r]
+        mine = g.new_empty((vmax,) + tuple(g.shape[1:]))
+        dist.reduce_scatter_tensor(mine, padded.view((world * vmax,) + tuple(g.shape[1:])), group=group)
+        return mine[:counts[rank]], None, None, None, None, None
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def gather_opacity_maps(local_maps: torch.Tensor, num_samples: int, views_per_sample: int, group=None,
-                        stream: "torch.cuda.Stream" = None) -> torch.Tensor:
+                        stream: "torch.cuda.Stream" = None, transport: str = None, grad: str = "local") -> torch.Tensor:
     """All-gather per-view opacity maps [V_local,1,H,W] into [num_samples*views_per_sample,1,H,W]
-    (global sample-major order).  Works for uneven shards (pads to the largest shard).
-    With `stream`, the collective is enqueued there after the producer stream's current work and the
-    caller must `torch.cuda.current_stream().wait_stream(stream)` before consuming the result."""
+    (global sample-major order).  Works for uneven shards (pads to the largest shard).  Differentiable (see the
+    module docstring for `grad`).
+    With `stream`, the transfer is enqueued there after the producer stream's current work and the
+    caller must `torch.cuda.current_stream().wait_stream(stream)` before consuming the result.
+    `transport`: "peer" (default on CUDA: copy-engine pushes over NVLink peer mappings; the result aliases a
+    persistent symmetric buffer that the next gather of the same shape overwrites) or "nccl"; the environment
+    variable OCRF_GATHER overrides the default."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return local_maps
+    if grad not in ("local", "sum"):
+        raise ValueError("grad must be 'local' or 'sum'")
+    if transport is None:
+        transport = os.environ.get("OCRF_GATHER", "peer")
     world = dist.get_world_size(group)
     counts = [(shard_samples(num_samples, world, r)[1] - shard_samples(num_samples, world, r)[0]) * views_per_sample
               for r in range(world)]
-    vmax = max(counts)
-    H, W = local_maps.shape[-2:]
-    send = local_maps
-    if local_maps.shape[0] != vmax:
-        send = local_maps.new_zeros((vmax, 1, H, W))
-        send[:local_maps.shape[0]] = local_maps
-    out = local_maps.new_empty((world * vmax, 1, H, W))
-
-    def run():
-        dist.all_gather_into_tensor(out, send.contiguous(), group=group)
-
-    if stream is not None and local_maps.is_cuda:
-        stream.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(stream):
-            run()
-        send.record_stream(stream)
-    else:
-        run()
-    if all(c == vmax for c in counts):
-        return out
-    parts = [out[r * vmax:r * vmax + counts[r]] for r in range(world)]
-    if stream is not None and local_maps.is_cuda:
-        with torch.cuda.stream(stream):
-            return torch.cat(parts, 0)
-    return torch.cat(parts, 0)
+    return _GatherMaps.apply(local_maps, counts, group, stream, transport, grad)

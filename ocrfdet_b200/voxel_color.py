@@ -4,7 +4,10 @@ Mirrors three methods of the OcRF view transformer
 (/root/reference/mmdet3d/models/necks/view_transformer_ocrf.py):
   * `lidar_points_to_image_values` (:924-942) + `color_voxels` (:945-971) -> `color_voxels_from_images`
   * `retain_valid_pixels` (:1004-1022)                                   -> `retain_valid_pixels`
-with the reference's argument shapes.  No gradients (the reference has none on these paths).
+with the reference's argument shapes.  Scope: the RGB path (`imgs_wo_norm` -> the colour head's `rgb` input,
+:1065-1071), which carries no gradient in the reference.  The same two reference methods are also called on the
+`alpha_img` planes (:1116-1118), where `grid_sample` back-propagates into the sigma MLP: `color_voxels_from_images`
+REFUSES an input that requires grad instead of silently cutting that gradient.
 There is no PyTorch fallback: both call libocrf_raster.so.
 """
 import torch
@@ -27,6 +30,10 @@ def color_voxels_from_images(pillars, imgs, mask, divisor=1.0):
     L = _lib.lib()
     if not (pillars.is_cuda and imgs.is_cuda and mask.is_cuda):
         raise _lib.OcrfError("color_voxels_from_images: tensors must live on a CUDA device (there is no CPU path)")
+    if imgs.requires_grad and torch.is_grad_enabled():
+        raise _lib.OcrfError("color_voxels_from_images has no backward: it covers the RGB path (no gradient in the "
+                             "reference); for the alpha planes of view_transformer_ocrf.py:1116-1118 keep the "
+                             "differentiable torch formulation or detach explicitly")
     B, N, P, Q, two = pillars.shape
     if two != 2 or tuple(mask.shape[:4]) != (B, N, P, Q):
         raise ValueError("pillars must be [B,N,P,Q,2] and mask [B,N,P,Q,1]")

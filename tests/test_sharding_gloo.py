@@ -32,8 +32,17 @@ def _worker(rank, world, port, num_samples, vps, q):
     H, W = 4, 6
     local = torch.stack([torch.full((1, H, W), float(s * vps + v)) for s in range(b, e) for v in range(vps)]) \
         if e > b else torch.zeros((0, 1, H, W))
+    local.requires_grad_(True)
     out = gather_opacity_maps(local, num_samples, vps)
-    q.put((rank, out[:, 0, 0, 0].tolist(), tuple(out.shape)))
+    # the gather is differentiable like the torch.cat it replaces (view_transformer_ocrf.py:1196)
+    weight = torch.arange(1, out.shape[0] + 1, dtype=torch.float32).view(-1, 1, 1, 1) * (rank + 1)
+    (out * weight).sum().backward()
+    g_local = local.grad[:, 0, 0, 0].tolist() if e > b else []
+    local.grad = None
+    out_sum = gather_opacity_maps(local, num_samples, vps, grad="sum")
+    (out_sum * weight).sum().backward()
+    g_sum = local.grad[:, 0, 0, 0].tolist() if e > b else []
+    q.put((rank, out[:, 0, 0, 0].tolist(), tuple(out.shape), (b * vps, e * vps), g_local, g_sum))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -50,9 +59,12 @@ def test_opacity_map_all_gather_world2_gloo(num_samples, vps):
     res = [q.get(timeout=120) for _ in procs]
     [p.join(timeout=60) for p in procs]
     assert all(p.exitcode == 0 for p in procs)
-    for _rank, vals, shape in res:
+    for rank, vals, shape, (vb, ve), g_local, g_sum in res:
         assert shape == (num_samples * vps, 1, 4, 6)
         assert vals == [float(i) for i in range(num_samples * vps)]  # global sample-major order on every rank
+        # grad="local": this rank's own loss only (weight (i+1)*(rank+1)); grad="sum": over both ranks' losses
+        assert g_local == [float((i + 1) * (rank + 1)) for i in range(vb, ve)]
+        assert g_sum == [float((i + 1) * 3) for i in range(vb, ve)]
 
 
 def test_single_process_gather_is_identity():
