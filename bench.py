@@ -10,15 +10,23 @@ Contract (see DESIGN.md "Measurement"):
   * `value`  = views/s with inputs resident in HBM, CUDA-event timed per step on the launching
     stream, L2 flushed (256 MB write) before every timed step, max over ranks.
   * `e2e`    = the same metric through the public API with HOST (pinned) buffers: H2D of the
-    Gaussian parameters, forward, backward, D2H of the parameter gradients, inside the timed region.
-  * `roofline` for the dominant kernel (algorithmic bytes / its event-timed duration vs the measured
-    HBM peak) plus per-stage times; `cpu_baseline` = the C oracle port on the host cores (1 view).
+    Gaussian parameters, forward, backward, D2H of the loss AND every parameter gradient, inside
+    the timed region; `e2e_loss_only` = the same with the gradients left on the device.
+  * `dropin_per_view` = the unmodified caller: one `GaussianRasterizer` call + backward per view
+    through the reference's import name (no batching, no capacity mode).
+  * `roofline` for the dominant kernel: the blend kernels are FP32-issue bound, so `achieved` is
+    executed warp instructions per second (instruction count of the committed ncu capture of this
+    workload / the live event-timed duration) against SMs x 4 schedulers x measured SM clock; the
+    HBM figures (algorithmic bytes and real DRAM traffic against MEASURED_PEAKS.json) sit beside it
+    under `roofline.hbm` and, per stage, under `stages`.  `cpu_baseline` = the C oracle port on the
+    host cores (whole steps of the same workload).
   * --impl reference: the reference's OWN rasterizer.  Its render path is CUDA-only, so "the
     reference's implementation on this box" is oracle/_ref/libinria_ref.so (the vendored Inria
-    kernels, unmodified) called once per view like OcRFDet does; if that library is absent the arm
-    falls back to the CPU oracle port.
+    kernels, unmodified) called once per view like OcRFDet does, on EVERY rank's GPU (replicas, max
+    over ranks); `kernel_only` times the same library in a tight allocation-free loop.  If that
+    library is absent the arm falls back to the CPU oracle port on rank 0.
   * N > 1 (torchrun): every rank renders its own sample (weak scaling) and the per-view opacity maps
-    are all-gathered (the path's single collective).
+    are all-gathered (the path's single collective; copy-engine pushes over NVLink peer mappings).
 """
 import argparse
 import json
@@ -293,27 +301,44 @@ def run_ours(args, rank, world, device):
               "render_backward": "render_backward_c3_kernel", "preprocess_backward": "preprocess_backward_kernel"}
     cand = {k: v for k, v in stage_ms.items() if k in single}
     dom = max(cand, key=cand.get) if cand else "render_backward"
-    ach = alg[dom] / (stage_ms[dom] * 1e-3) / 1e9 if stage_ms.get(dom) else None
-    traffic, issue_pct = None, None
+    # Per-launch counters of the committed ncu capture of this very workload (profiles/kernel_counters.json, written
+    # by tools/summarize_ncu.py): executed warp instructions and DRAM bytes are properties of the (deterministic,
+    # seeded) workload, the DURATION they are divided by is measured live above.
+    counters = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(dom)
+        counters = json.load(open(os.path.join(ROOT, "profiles", "kernel_counters.json")))
     except Exception:
         pass
-    try:
-        import csv
-        for row in csv.DictReader(open(os.path.join(ROOT, "profiles", "r1_ncu_full_summary.csv"))):
-            if row["kernel"].startswith(single[dom]):
-                issue_pct = float(row["issue_active_pct"])
-    except Exception:
-        pass
-    roofline = {"bound": "hbm", "kernel": single.get(dom, dom), "stage": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": (ach / peak) if ach else None, "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes": alg[dom], "kernel_ms": stage_ms.get(dom), "issue_active_pct_ncu": issue_pct,
-                "note": "the blend kernels are FP32-issue/MUFU bound, not HBM bound (SURVEY 8d): issue_active_pct_ncu is "
-                        "the binding utilisation, pair_rate the throughput; per-stage GB/s incl. the binning chain under "
-                        "`stages`"}
+    cnt = counters.get(dom, {})
+    kernel_s = stage_ms[dom] * 1e-3 if stage_ms.get(dom) else None
+    hbm_ach = alg[dom] / kernel_s / 1e9 if kernel_s else None
+    sm_mhz = clocks.get("sm_mhz") or clocks.get("sm_max_mhz") or 1965.0
+    n_sms = torch.cuda.get_device_properties(device).multi_processor_count
+    issue_peak = n_sms * 4 * sm_mhz * 1e6 / 1e9  # Gwarp-inst/s: 4 schedulers per SM, one warp instruction per clock each
+    warp_insts = cnt.get("warp_insts")
+    issue_ach = warp_insts / kernel_s / 1e9 if (warp_insts and kernel_s) else None
+    if dom in ("render_forward", "render_backward") and issue_ach:
+        # the blend kernels are bound by the issue slots (~20 FP32 ops + 1 ex2 per pair against 0.2 B of
+        # DRAM): the roofline is warp instructions per second against SMs x 4 schedulers x measured SM clock
+        roofline = {"bound": "fp32_issue", "kernel": single[dom], "stage": dom, "achieved": issue_ach, "peak": issue_peak,
+                    "unit": "Gwarp-inst/s", "frac": issue_ach / issue_peak, "traffic": cnt.get("dram_bytes"),
+                    "warp_insts_per_launch": warp_insts, "kernel_ms": stage_ms.get(dom),
+                    "peak_source": "%d SMs x 4 schedulers x %.0f MHz (median SM clock sampled during the timed region)"
+                                   % (n_sms, sm_mhz),
+                    "counters_source": "profiles/kernel_counters.json (ncu capture of this workload, per launch)",
+                    "hbm": {"achieved": hbm_ach, "peak": peak, "unit": "GB/s", "frac": hbm_ach / peak if hbm_ach else None,
+                            "algorithmic_bytes": alg[dom], "peak_source": peak_src,
+                            "dram_frac": (cnt["dram_bytes"] / kernel_s / 1e9 / peak) if cnt.get("dram_bytes") else None}}
+    else:
+        roofline = {"bound": "hbm", "kernel": single.get(dom, dom), "stage": dom, "achieved": hbm_ach, "peak": peak,
+                    "unit": "GB/s", "frac": (hbm_ach / peak) if hbm_ach else None, "traffic": cnt.get("dram_bytes"),
+                    "peak_source": peak_src, "algorithmic_bytes": alg[dom], "kernel_ms": stage_ms.get(dom)}
     stages = {k: {"ms": round(v, 4), "alg_GB": round(alg[k] / 1e9, 4),
-                  "GBps": round(alg[k] / (v * 1e-3) / 1e9, 1) if v > 0 else None} for k, v in stage_ms.items()}
+                  "GBps": round(alg[k] / (v * 1e-3) / 1e9, 1) if v > 0 else None,
+                  "dram_GB": round(counters[k]["dram_bytes"] / 1e9, 4) if counters.get(k, {}).get("dram_bytes") else None,
+                  "dram_GBps": round(counters[k]["dram_bytes"] / (v * 1e-3) / 1e9, 1)
+                  if (v > 0 and counters.get(k, {}).get("dram_bytes")) else None}
+              for k, v in stage_ms.items()}
     pair_rate = {"N_pair_per_step": stats["N_pair"],
                  "fwd_Gpairs_per_s": stats["N_pair"] / (stage_ms["render_forward"] * 1e-3) / 1e9
                  if stage_ms.get("render_forward") else None,
@@ -321,21 +346,18 @@ def run_ours(args, rank, world, device):
                  if stage_ms.get("render_backward") else None}
 
     # ---- end to end through the public API with host buffers ----
-    # A step = pinned host parameters -> H2D -> forward -> loss -> backward (gradients stay on the device, where an
-    # optimiser consumes them) -> D2H of the step's result, the loss.  OCRF_E2E_D2H=grads additionally reads every
-    # parameter gradient back (5.6 MB), the most a host-side consumer could ask for.
-    d2h_grads = os.environ.get("OCRF_E2E_D2H", "loss") == "grads"
+    # A step = pinned host parameters -> H2D -> forward -> loss -> backward -> D2H of the step's results: the loss AND
+    # every parameter gradient (5.6 MB; what a host-side optimiser would consume).  That variant is the `e2e` figure;
+    # `e2e_loss_only` (gradients stay on the device, where a device-side optimiser consumes them; 4 bytes come back) is
+    # reported beside it.
     grads_host = {k: torch.empty_like(host[k]).pin_memory() for k in names}
     loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
     h2d = sum(host[k].numel() * 4 for k in names)
-    d2h = 4 + (sum(grads_host[k].numel() * 4 for k in names) if d2h_grads else 0)
     e2e_steps = max(3, min(args.steps, 20))
-
     gcol_flat, gop_flat = gcol.reshape(-1), gop.reshape(-1)
-
     copy_stream = torch.cuda.Stream()
 
-    def e2e_step():
+    def e2e_step(d2h_grads):
         # geometry first on the launching stream; the colours -- first read by the binning stage -- follow on a second
         # stream, so their copy runs under the preprocess and the depth sort (render_batch(colors_ready=...))
         t = {k: host[k].to(device, non_blocking=True).requires_grad_(True) for k in names if k != "colors"}
@@ -357,26 +379,73 @@ def run_ours(args, rank, world, device):
             for k in names:
                 grads_host[k].copy_(t[k].grad, non_blocking=True)
 
-    for _ in range(2):
-        e2e_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t_tot = 0.0
-    for _ in range(e2e_steps):
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        e2e_step()
-        e1.record()
-        e1.synchronize()
-        t_tot += e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([t_tot], device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_tot = float(t[0])
-    e2e = {"value": world * VIEWS / (t_tot / e2e_steps / 1e3), "unit": "views/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "ms_per_step": t_tot / e2e_steps, "steps": e2e_steps}
+    def time_e2e(d2h_grads):
+        for _ in range(2):
+            e2e_step(d2h_grads)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t_tot = 0.0
+        for _ in range(e2e_steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            e2e_step(d2h_grads)
+            e1.record()
+            e1.synchronize()  # the step's results are on the host
+            t_tot += e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([t_tot], device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t_tot = float(tt[0])
+        d2h = 4 + (sum(grads_host[k].numel() * 4 for k in names) if d2h_grads else 0)
+        return {"value": world * VIEWS / (t_tot / e2e_steps / 1e3), "unit": "views/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": t_tot / e2e_steps, "steps": e2e_steps,
+                "d2h": "loss + all parameter gradients" if d2h_grads else "loss only"}
+
+    e2e = time_e2e(True)
+    e2e_loss_only = time_e2e(False)
+
+    # ---- the UNMODIFIED caller: one GaussianRasterizer call per view through the reference's import name ----
+    # (GR:39-70 as called from VT:1153: settings tuple per view, a zeros means2D leaf, exact sizing with its 8-byte
+    # read-back per call, the 3-tuple return, one backward per view) -- what swapping the package and changing nothing
+    # else gives.  `value` above additionally uses render_batch + capacity mode, which the reference API does not have.
+    dropin = None
+    if world == 1:
+        from diff_gaussian_rasterization import GaussianRasterizationSettings, GaussianRasterizer
+        settings = [GaussianRasterizationSettings(
+            image_height=H, image_width=W, tanfovx=c["tanfovx"], tanfovy=c["tanfovy"], bg=bg, scale_modifier=1.0,
+            viewmatrix=torch.from_numpy(c["viewmatrix"]).to(device), projmatrix=torch.from_numpy(c["projmatrix"]).to(device),
+            sh_degree=3, campos=torch.from_numpy(c["campos"]).to(device), prefiltered=False) for c in cams]
+        flat = {k: dev[k].detach()[0].clone().requires_grad_(True) for k in names}
+
+        def dropin_step():
+            for k in names:
+                flat[k].grad = None
+            for v in range(VIEWS):
+                means2D = torch.zeros_like(flat["means3D"], requires_grad=True)
+                image, _radii, _depth = GaussianRasterizer(raster_settings=settings[v])(
+                    means3D=flat["means3D"], means2D=means2D, shs=None, colors_precomp=flat["colors"],
+                    opacities=flat["opacities"], scales=flat["scales"], rotations=flat["rotations"], cov3D_precomp=None)
+                image.backward(gcol[v])
+
+        for _ in range(3):
+            dropin_step()
+        torch.cuda.synchronize()
+        d_steps = max(3, min(args.steps, 20))
+        t_tot = 0.0
+        for _ in range(d_steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dropin_step()
+            e1.record()
+            e1.synchronize()
+            t_tot += e0.elapsed_time(e1)
+        dropin = {"value": VIEWS / (t_tot / d_steps / 1e3), "unit": "views/s", "ms_per_step": t_tot / d_steps,
+                  "steps": d_steps, "pattern": "one GaussianRasterizer call + backward per view through "
+                                               "`diff_gaussian_rasterization`, exact sizing (8-byte read-back per call), "
+                                               "colour only (the reference API returns no opacity map)"}
 
     R.check_overflow()  # raises if any capacity-mode step overflowed its binning workspace
     cpu = None
@@ -394,7 +463,7 @@ def run_ours(args, rank, world, device):
                       "sizing": "exact (1 host read-back per batch)" if cap["n"] is None else
                       "sync-free: pair capacity %d = 1.3 x previous count, overflow flag checked after the run" % cap["n"],
                       "parallelism": "(sample,view) shards, %d rank(s); opacity-map all-gather" % world},
-           "clocks": clocks, "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
+           "clocks": clocks, "e2e": e2e, "e2e_loss_only": e2e_loss_only, "dropin_per_view": dropin, "gpu_launches": launches_per_step * args.steps,
            "gpu_launches_per_step": launches_per_step, "roofline": roofline, "stages": stages, "pair_rate": pair_rate,
            "workload_stats": stats, "impl": "ours"}
     if cpu is not None:
@@ -426,22 +495,35 @@ def cpu_baseline(g, cams, gcol, gop, min_seconds=10.0):
 
 
 def run_reference(args, rank, world, device):
-    """The reference's own rasterizer on this box, called per view as OcRFDet does (VT:1153)."""
+    """The reference's own rasterizer on this box, called per view as OcRFDet does (VT:1153).
+
+    Every rank runs it on its own GPU (replicas: the reference scales by plain data parallelism), the
+    timing is the max over ranks and `value` counts the views of all ranks, like our arm.  Two call patterns:
+      * as used (`value`): what the reference's torch binding does per view -- fresh output / gradient tensors
+        (torch::full + nine torch::zeros, rasterize_points.cu:68-69,151-159), its blocking num_rendered read-back;
+      * `kernel_only`: a tight loop over the same library entry points with every buffer allocated once and ONE fill
+        for the gradient accumulators -- the reference's kernels + CUB + its own read-back, nothing else.
+    """
     from oracle import ref
-    if rank != 0:
+    use_cuda = ref.available() and torch.cuda.is_available()
+    if not use_cuda and rank != 0:
         return None
-    g, cams, gcol_np, gop_np = make_inputs(0, device)
+    g, cams, gcol_np, gop_np = make_inputs(rank if use_cuda else 0, device)
     base = {"metric": METRIC, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": "BASELINE config 2: 1 sample x 6 views 256x704, 100k voxel-grid Gaussians, fwd+bwd",
-                       "views_per_step_per_gpu": VIEWS, "gaussians": P, "image": [H, W], "channels": C}}
-    if not (ref.available() and torch.cuda.is_available()):
+            "config": {"workload": "BASELINE config 2: 1 sample x 6 views 256x704, 100k voxel-grid Gaussians, fwd+bwd, "
+                                   "per GPU", "views_per_step_per_gpu": VIEWS, "gaussians": P, "image": [H, W],
+                       "channels": C, "l2": "flushed (256 MB write) before each timed step",
+                       "parallelism": "%d independent replica(s), one per GPU" % world}}
+    if not use_cuda:
         cpu = cpu_baseline(g, cams, gcol_np, gop_np)
-        base.update({"value": cpu["value"], "ms_per_step": 1e3 * VIEWS / cpu["value"], "cpu_baseline": cpu,
+        base.update({"value": cpu["value"], "n_gpus": 0, "ms_per_step": 1e3 * VIEWS / cpu["value"], "cpu_baseline": cpu,
                      "e2e": {"value": cpu["value"], "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                      "config": dict(base["config"], note="reference CUDA library absent: CPU oracle port timed instead")})
         return base
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
     names = ("means3D", "scales", "rotations", "opacities", "colors")
     t = {k: torch.from_numpy(g[k]).to(device) for k in names}
     bg = torch.zeros(3, device=device)
@@ -449,8 +531,9 @@ def run_reference(args, rank, world, device):
     cam_t = [{k: (torch.from_numpy(c[k]).to(device) if isinstance(c[k], np.ndarray) else c[k]) for k in c} for c in cams]
     rr = ref.RefRasterizer()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    out_buf, radii_buf, gflat, gviews = rr.alloc_io(P, W, H, device)
 
-    def step():
+    def step_as_used():
         for v in range(VIEWS):
             c = cam_t[v]
             col, radii, n = rr.forward(t["means3D"], t["opacities"], t["colors"], c["viewmatrix"], c["projmatrix"],
@@ -459,35 +542,67 @@ def run_reference(args, rank, world, device):
             rr.backward(t["means3D"], t["colors"], c["viewmatrix"], c["projmatrix"], c["campos"], c["tanfovx"],
                         c["tanfovy"], bg, radii, gcol[v], scales=t["scales"], rotations=t["rotations"])
 
-    for _ in range(args.warmup):
-        step()
-    torch.cuda.synchronize()
-    sampler = ClockSampler(torch.cuda.current_device())
-    sampler.start()
+    def step_kernel_only():
+        for v in range(VIEWS):
+            c = cam_t[v]
+            rr.forward_into(out_buf, radii_buf, t["means3D"], t["opacities"], t["colors"], c["viewmatrix"],
+                            c["projmatrix"], c["campos"], W, H, c["tanfovx"], c["tanfovy"], bg, t["scales"],
+                            t["rotations"])
+            rr.backward_into(gflat, gviews, t["means3D"], t["colors"], c["viewmatrix"], c["projmatrix"], c["campos"],
+                             c["tanfovx"], c["tanfovy"], bg, radii_buf, gcol[v], t["scales"], t["rotations"])
+
     import gc
-    gc.collect()
-    gc.disable()  # no collector pauses on the launching thread inside the timed region (N ranks wait for the slowest)
-    evs = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        step()
-        e1.record()
-        evs.append((e0, e1))
-    torch.cuda.synchronize()
-    gc.enable()
-    clocks = sampler.stop()
-    ms = sum(a.elapsed_time(b) for a, b in evs) / args.steps
-    value = VIEWS / (ms / 1e3)
+
+    def timed(step, steps, sample_clocks):
+        for _ in range(args.warmup):
+            step()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(torch.cuda.current_device()) if sample_clocks else None
+        if sampler:
+            sampler.start()
+        gc.collect()
+        gc.disable()  # no collector pauses on the launching thread inside the timed region
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        if sampler:
+            sampler.sm, sampler.bits = [], 0
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        gc.enable()
+        clocks = sampler.stop() if sampler else None
+        total = sum(a.elapsed_time(b) for a, b in evs)
+        if world > 1:
+            tt = torch.tensor([total], device=device)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            total = float(tt[0])
+        return total / steps, clocks
+
+    ms, clocks = timed(step_as_used, args.steps, True)
+    ms_tight, _ = timed(step_kernel_only, args.steps, False)
+    value = world * VIEWS / (ms / 1e3)
     base.update({"value": value, "ms_per_step": ms, "ms_per_render": ms / VIEWS, "clocks": clocks,
+                 "kernel_only": {"value": world * VIEWS / (ms_tight / 1e3), "unit": "views/s", "ms_per_step": ms_tight,
+                                 "note": "tight loop: buffers allocated once, one fill for the nine gradient accumulators; "
+                                         "the reference's own num_rendered read-back per view remains (it is inside "
+                                         "CudaRasterizer::Rasterizer::forward)"},
                  "cpu_baseline": {"value": value, "unit": "views/s", "cores": 0, "kind": "reference",
                                   "sample": "the reference render path is CUDA-only: this arm runs its vendored CUDA "
-                                            "rasterizer (oracle/_ref, unmodified kernels + CUB) on the same B200, one "
+                                            "rasterizer (oracle/_ref, unmodified kernels + CUB) on the same B200s, one "
                                             "call per view with its blocking num_rendered read-back, no depth/opacity"},
                  "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
     rr.close()
-    return base
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return base if rank == 0 else None
 
 
 def main():

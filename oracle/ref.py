@@ -85,6 +85,43 @@ class RefRasterizer:
             raise RuntimeError("reference backward failed")
         return g
 
+    # ---- allocation-free variants for the "kernel-only" timing of bench.py --impl reference ----
+    def alloc_io(self, P, W, H, device, M=1):
+        """Outputs of one forward/backward pair, allocated ONCE: (out_color, radii, flat gradient buffer, views)."""
+        z = lambda *s: torch.zeros(s, dtype=torch.float32, device=device)  # noqa: E731
+        sizes = dict(means2D=(P, 3), conic=(P, 2, 2), opacities=(P, 1), colors=(P, 3), means3D=(P, 3), cov3D=(P, 6),
+                     shs=(P, max(M, 1), 3), scales=(P, 3), rotations=(P, 4))
+        flat = z(sum(int(torch.tensor(v).prod()) for v in sizes.values()))
+        g, off = {}, 0
+        for k, shp in sizes.items():
+            n = int(torch.tensor(shp).prod())
+            g[k] = flat[off:off + n].view(shp)
+            off += n
+        return z(3, H, W), torch.zeros((P,), dtype=torch.int32, device=device), flat, g
+
+    def forward_into(self, out, radii, means3D, opacities, colors, viewmatrix, projmatrix, campos, W, H, tanfovx,
+                     tanfovy, bg, scales, rotations):
+        P = means3D.shape[0]
+        n = lib().ref_forward(self.h, P, 0, 0, _p(bg), W, H, _p(means3D), None, _p(colors), _p(opacities), _p(scales),
+                              1.0, _p(rotations), None, _p(viewmatrix), _p(projmatrix), _p(campos), tanfovx, tanfovy, 0,
+                              _p(out), _p(radii))
+        if n < 0:
+            raise RuntimeError("reference forward failed")
+        self.meta = dict(P=P, W=W, H=H, R=n, M=0, D=0)
+        return n
+
+    def backward_into(self, flat, g, means3D, colors, viewmatrix, projmatrix, campos, tanfovx, tanfovy, bg, radii,
+                      dL_dpix, scales, rotations):
+        m = self.meta
+        flat.zero_()  # ONE fill for the nine accumulators (the binding issues nine torch::zeros, rasterize_points.cu:151-159)
+        rc = lib().ref_backward(self.h, m["P"], 0, 0, m["R"], _p(bg), m["W"], m["H"], _p(means3D), None, _p(colors),
+                                _p(scales), 1.0, _p(rotations), None, _p(viewmatrix), _p(projmatrix), _p(campos),
+                                tanfovx, tanfovy, _p(radii), _p(dL_dpix), _p(g["means2D"]), _p(g["conic"]),
+                                _p(g["opacities"]), _p(g["colors"]), _p(g["means3D"]), _p(g["cov3D"]), _p(g["shs"]),
+                                _p(g["scales"]), _p(g["rotations"]))
+        if rc != 0:
+            raise RuntimeError("reference backward failed")
+
     def state(self):
         """Internal buffers of the last forward: keys, point list, ranges, ... (device tensors)."""
         m = self.meta

@@ -1,7 +1,8 @@
 """Turns `ncu -i REPORT --page raw --csv` into the two files kept under profiles/:
   <out>_summary.csv  selected counters per kernel launch
-  traffic.json       dram bytes (read + write) per stage of one step, read by bench.py for roofline.traffic
-usage: python tools/summarize_ncu.py REPORT.ncu-rep profiles/r1_ncu_full_summary.csv profiles/traffic.json"""
+  kernel_counters.json   per stage of ONE step: dram bytes (read + write), executed warp instructions and the ncu
+                         duration; read by bench.py for roofline.{achieved,traffic}
+usage: python tools/summarize_ncu.py REPORT.ncu-rep profiles/r2_ncu_full_summary.csv profiles/kernel_counters.json"""
 import csv
 import json
 import subprocess
@@ -26,7 +27,7 @@ KEEP = [
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "smem_bank_conflicts"),
 ]
 STAGE = [("preprocess_forward", "preprocess"), ("preprocess_backward", "preprocess_backward"),
-         ("render_forward", "render_forward"), ("render_backward", "render_backward"), ("clear_gradients", "render_backward"),
+         ("render_forward", "render_forward"), ("render_backward", "render_backward"), ("clear_gradients", "clear_gradients"),
          ("sort_", "binning"), ("scan_sorted", "binning"), ("ms_", "binning"), ("duplicate", "binning"),
          ("ranges_cull", "binning"), ("gaussian_heads_forward", "heads_forward"), ("gaussian_heads_backward", "heads_backward")]
 UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6}
@@ -52,7 +53,10 @@ def main(rep, out_csv, out_traffic):
         out.append(rec)
         for pat, st in STAGE:
             if pat in name:
-                per_stage[st] = per_stage.get(st, 0.0) + rec.get("dram_read", 0.0) + rec.get("dram_write", 0.0)
+                d = per_stage.setdefault(st, {"dram_bytes": 0.0, "warp_insts": 0.0, "time_us_ncu": 0.0})
+                d["dram_bytes"] += rec.get("dram_read", 0.0) + rec.get("dram_write", 0.0)
+                d["warp_insts"] += rec.get("warp_insts", 0.0)
+                d["time_us_ncu"] += rec.get("time_us", 0.0)
                 counts.setdefault(st, {}).setdefault(name, 0)
                 counts[st][name] += 1
                 break
@@ -65,8 +69,10 @@ def main(rep, out_csv, out_traffic):
     if out_traffic:
         # the capture may hold several steps: normalise to ONE step by the launch count of a once-per-step kernel
         steps = max(1, max((n for st in counts.values() for k, n in st.items() if "preprocess_forward" in k), default=1))
-        json.dump({k: v / steps for k, v in per_stage.items()}, open(out_traffic, "w"), indent=1)
-    print("kernels:", len(out), "stages:", {k: round(v / 1e6, 1) for k, v in per_stage.items()})
+        res = {k: {m: x / steps for m, x in v.items()} for k, v in per_stage.items()}
+        res["_source"] = "%s -> %s (%d step(s) captured)" % (rep, out_csv, steps)
+        json.dump(res, open(out_traffic, "w"), indent=1)
+    print("kernels:", len(out), "stages:", {k: round(v["dram_bytes"] / 1e6, 1) for k, v in per_stage.items()})
 
 
 if __name__ == "__main__":
