@@ -190,8 +190,8 @@ __global__ void __launch_bounds__(256) ranges_cull_pack_kernel(OcrfShape sh, uin
         r = __ldg(c); gg = __ldg(c + 1); bb = __ldg(c + 2);
       }
       float4* out = reinterpret_cast<float4*>(records + dst);
-      out[0] = make_float4(p.x, p.y, co.x, co.y);
-      out[1] = make_float4(co.z, co.w, __uint_as_float(i - lo + 1), r);
+      out[0] = record_head(p, co);
+      out[1] = make_float4(record_qc(co), co.w, __uint_as_float(i - lo + 1), r);
       out[2] = make_float4(gg, bb, __uint_as_float(id), depths[g]);
     }
     kept_total += chunk_total;

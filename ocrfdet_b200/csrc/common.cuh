@@ -68,9 +68,13 @@ struct Camera {  // OCRF_CAM_STRIDE floats
 static_assert(sizeof(Camera) == OCRF_CAM_STRIDE * 4, "camera record size");
 
 // One (tile, Gaussian) pair as the blend kernels consume it (C == 3).
+// The conic (A, B, C) is stored PRE-SCALED into the exponent the kernels evaluate: with d = mean - pixel,
+//   log2(G) = power * log2(e) = qa dx^2 + qb dx dy + qc dy^2,   qa = -A log2(e)/2, qb = -B log2(e), qc = -C log2(e)/2
+// (the reference's power = -0.5 (A dx^2 + C dy^2) - B dx dy, forward.cu:336), so a test costs no -0.5 and no log2(e)
+// multiply per (pixel, Gaussian); the backward recovers A, B, C once per record (record_conic below).
 struct __align__(16) Record {
-  float x, y, cA, cB;  // pixel-space mean, conic A, B            (read for every test)
-  float cC, op;        // conic C, opacity                         (read for every test)
+  float x, y, qa, qb;  // pixel-space mean, scaled conic A, B     (read for every test)
+  float qc, op;        // scaled conic C, opacity                  (read for every test)
   uint32_t orig;       // 1-based position in the tile's full (unculled) sorted list == the reference's "contributor"
   float r;             // red
   float g, b;          // green, blue                              (read only when blending)
@@ -78,6 +82,18 @@ struct __align__(16) Record {
   float depth;         // view-space depth (median-depth output)
 };
 static_assert(sizeof(Record) == OCRF_RECORD_BYTES, "record size");
+
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+__device__ __forceinline__ float4 record_head(float2 xy, float4 conic_opacity) {  // first float4 of a Record
+  return make_float4(xy.x, xy.y, conic_opacity.x * (-0.5f * LOG2E), conic_opacity.y * (-LOG2E));
+}
+__device__ __forceinline__ float record_qc(float4 conic_opacity) { return conic_opacity.z * (-0.5f * LOG2E); }
+__device__ __forceinline__ void record_conic(float qa, float qb, float qc, float& A, float& B, float& C) {
+  A = qa * (-2.f * LN2);
+  B = qb * (-LN2);
+  C = qc * (-2.f * LN2);
+}
 
 __host__ __device__ inline size_t align128(size_t x) { return (x + 127) & ~size_t(127); }
 __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
@@ -270,6 +286,31 @@ __device__ __forceinline__ unsigned long long lookback_warp(unsigned long long* 
   if (lane == 0) atomicExch(&status[bid], LBK_FLAG_INCL | (excl + total));
   return excl;
 }
+
+// ---- packed FP32 (sm_100: FFMA2 / FMUL2 / FADD2 issue two fp32 operations per lane per instruction) ----
+// A float2 whose halves are the same value is encoded by ptxas as a broadcast operand (Rx.F32): no move is spent.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rc, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rb, {%4,%5};\nmov.b64 rc, {%6,%7};\n"
+      "fma.rn.f32x2 rd, ra, rb, rc;\nmov.b64 {%0,%1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+  return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rb, {%4,%5};\nmul.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0,%1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) {
+  float2 d;
+  asm("{\n.reg .b64 ra, rb, rd;\nmov.b64 ra, {%2,%3};\nmov.b64 rb, {%4,%5};\nadd.rn.f32x2 rd, ra, rb;\n"
+      "mov.b64 {%0,%1}, rd;\n}"
+      : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+  return d;
+}
+__device__ __forceinline__ float2 bcast2(float v) { return make_float2(v, v); }
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -403,8 +403,8 @@ __global__ void __launch_bounds__(MS_THREADS) ms_scatter_kernel(
         r = __ldg(col); gg = __ldg(col + 1); bb = __ldg(col + 2);
       }
       float4* out = reinterpret_cast<float4*>(records + dst);
-      out[0] = make_float4(p.x, p.y, co.x, co.y);
-      out[1] = make_float4(co.z, co.w, __uint_as_float(orig), r);
+      out[0] = record_head(p, co);
+      out[1] = make_float4(record_qc(co), co.w, __uint_as_float(orig), r);
       out[2] = make_float4(gg, bb, __uint_as_float(id), depths[g]);
     }
     __syncthreads();

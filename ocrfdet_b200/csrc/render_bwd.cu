@@ -26,6 +26,13 @@ __device__ __forceinline__ float ex2_approx_b(float x) {
   return y;
 }
 
+// 1 / x for x in [0.01, 1] (x = 1 - alpha): one MUFU.RCP, no range fix-up code
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Reduce-scatter of 8 values over the warp: afterwards lane L (any L) holds the warp total of value
 // index ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1).
 __device__ __forceinline__ float butterfly8(float (&v)[8], int lane) {
@@ -53,7 +60,7 @@ __device__ __forceinline__ float butterfly8(float (&v)[8], int lane) {
 }
 
 template <int PPT>
-__global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
+__global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_scalar_kernel(
     int W, int H, int P, int views_per_sample, int colors_per_view, const uint2* __restrict__ ranges /* culled lists */,
     const Record* __restrict__ records, const float* __restrict__ bg, const float* __restrict__ final_T,
     const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ max_contrib,
@@ -147,8 +154,8 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
       for (int p = 0; p < PPT; p++) {
         dx[p] = a.x - fx[p];
         dy[p] = a.y - fy[p];
-        const float power = -0.5f * (a.z * dx[p] * dx[p] + b.x * dy[p] * dy[p]) - a.w * dx[p] * dy[p];
-        G[p] = ex2_approx_b(power * 1.4426950408889634f);
+        const float power = a.z * dx[p] * dx[p] + b.x * dy[p] * dy[p] + a.w * dx[p] * dy[p];  // log2 domain (scaled conic)
+        G[p] = ex2_approx_b(power);
         alpha[p] = fminf(0.99f, b.y * G[p]);
         ok[p] = (int)__float_as_uint(b.z) <= nc[p] && power <= 0.0f && alpha[p] >= 1.0f / 255.0f;
         any = any || ok[p];
@@ -216,8 +223,10 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
       const Record rec = s_rec[st][j];
       const uint32_t id = rec.id;
       // q = (m0, mx, my, mxx, mxy, myy): dmean2D = -(conic . m1) * NDC scale, dconic = -1/2 m2, dopacity = m0 / opacity
-      const float gmx = -(rec.cA * q[1] + rec.cB * q[2]) * ddelx_dx;
-      const float gmy = -(rec.cC * q[2] + rec.cB * q[1]) * ddely_dy;
+      float cA, cB, cC;
+      record_conic(rec.qa, rec.qb, rec.qc, cA, cB, cC);
+      const float gmx = -(cA * q[1] + cB * q[2]) * ddelx_dx;
+      const float gmy = -(cC * q[2] + cB * q[1]) * ddely_dy;
       double* gg = ggrad + ((size_t)view * P + id) * OCRF_GGRAD_STRIDE;
       atomicAdd(gg + 0, (double)gmx);
       atomicAdd(gg + 1, (double)gmy);
@@ -229,6 +238,214 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
       atomicAdd(gc, q[6]);
       atomicAdd(gc + 1, q[7]);
       atomicAdd(gc + 2, q[8]);
+    }
+    __syncthreads();  // stage `st` and the partial sums are consumed: only now may round r+2 land
+    if (tid == 0 && r + 2 < rounds) issue(r + 2);
+  }
+}
+
+// The production C == 3 kernel.  Same traversal, staging and cross-warp reduction as the scalar kernel above; the
+// per-(pixel, Gaussian) arithmetic is restructured around three facts:
+//   * a thread owns PPT pixels of ONE column, so dx is common to them: of the six raw moments of t = dL/dG * G only
+//     s0 = sum t, s1 = sum t dy, s2 = sum t dy^2 are accumulated per pixel; (m_x, m_xx, m_xy) = (dx s0, dx^2 s0, dx s1)
+//     follow once per (thread, record);
+//   * only g . A of the colour A accumulated behind a pixel is needed, and it obeys the same recurrence as A
+//     (S <- S + alpha (g . c - S), applied eagerly): one register and one FMA per pixel instead of seven registers and
+//     thirteen instructions (the reference's lazy last_alpha / last_color form, backward.cu:480-490);
+//   * pixels that do not take part get alpha = 0 and G = 0, after which every formula is exact for them (1/(1-0) = 1,
+//     all contributions 0), so the gradient arithmetic runs unpredicated and PACKED two pixels per instruction
+//     (FFMA2 / FMUL2 / FADD2; record scalars are broadcast operands).
+template <int PPT>
+__global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_kernel(
+    int W, int H, int P, int views_per_sample, int colors_per_view, const uint2* __restrict__ ranges /* culled lists */,
+    const Record* __restrict__ records, const float* __restrict__ bg, const float* __restrict__ final_T,
+    const uint32_t* __restrict__ n_contrib, const uint32_t* __restrict__ max_contrib,
+    const float* __restrict__ dL_dpix, const float* __restrict__ dL_dopa, double* __restrict__ ggrad,
+    float* __restrict__ dL_dcolors) {
+  pdl_enter();
+  static_assert(PPT == 2 || PPT == 4, "pixel pairs");
+  constexpr int NT = TILE_PIX / PPT;
+  constexpr int NW = NT / 32;
+  constexpr int NQ = PPT / 2;
+  constexpr int BWD_BATCH = BwdBatch<PPT>::value;
+  __shared__ __align__(128) Record s_rec[2][BWD_BATCH];
+  __shared__ __align__(16) float s_acc[NW][BWD_BATCH][BWD_ACC];
+  __shared__ uint32_t s_touched[NW][BWD_BATCH / 32];
+  __shared__ __align__(8) uint64_t s_bar[2];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = gridDim.x, tiles_per_view = gridDim.x * gridDim.y;
+  const int view = blockIdx.z;
+  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  const size_t vt = (size_t)view * tiles_per_view + tile;
+  const int mc = (int)max_contrib[vt];
+  if (mc == 0) return;
+  const uint2 range = ranges[vt];
+  const Record* src = records + range.x;
+  const int rounds = (mc + BWD_BATCH - 1) / BWD_BATCH;
+
+  const size_t HW = (size_t)H * W;
+  const int px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
+  const int py0 = blockIdx.y * TILE + (warp >> 1) * (4 * PPT) + (lane >> 3);
+  const float fx = (float)px;
+  float2 nfy[NQ], T[NQ], S[NQ], g0[NQ], g1[NQ], g2[NQ], gob[NQ];
+  int nc[PPT];
+  const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+#pragma unroll
+  for (int p = 0; p < PPT; p++) {
+    const int py = py0 + 4 * p;
+    const bool inside = px < W && py < H;
+    const size_t pix = (size_t)py * W + px;
+    const float Tf = inside ? final_T[view * HW + pix] : 0.f;
+    nc[p] = inside ? (int)n_contrib[view * HW + pix] : 0;
+    const float c0 = inside ? dL_dpix[((size_t)view * 3 + 0) * HW + pix] : 0.f;
+    const float c1 = inside ? dL_dpix[((size_t)view * 3 + 1) * HW + pix] : 0.f;
+    const float c2 = inside ? dL_dpix[((size_t)view * 3 + 2) * HW + pix] : 0.f;
+    const float gop = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
+    // d(out)/d(alpha_i) through the final transmittance: opacity map (+) and background (-)
+    const float gb = Tf * (gop - (bg0 * c0 + bg1 * c1 + bg2 * c2));
+    const int q = p >> 1;
+    if (p & 1) { nfy[q].y = -(float)py; T[q].y = Tf; g0[q].y = c0; g1[q].y = c1; g2[q].y = c2; gob[q].y = gb; }
+    else       { nfy[q].x = -(float)py; T[q].x = Tf; g0[q].x = c0; g1[q].x = c1; g2[q].x = c2; gob[q].x = gb; }
+  }
+#pragma unroll
+  for (int q = 0; q < NQ; q++) S[q] = make_float2(0.f, 0.f);
+  const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+  // round r covers culled-list indices [lo_r, hi_r) with hi_r = mc - r*BATCH (back to front)
+  auto issue = [&](int r) {
+    const int hi = mc - r * BWD_BATCH;
+    const int lo = max(0, hi - BWD_BATCH);
+    const uint32_t bytes = (uint32_t)(hi - lo) * sizeof(Record);
+    mbar_expect_tx(&s_bar[r & 1], bytes);
+    bulk_g2s(&s_rec[r & 1][0], src + lo, bytes, &s_bar[r & 1]);
+  };
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    issue(0);
+    if (rounds > 1) issue(1);
+  }
+
+  for (int r = 0; r < rounds; r++) {
+    const int st = r & 1;
+    const int hi = mc - r * BWD_BATCH;
+    const int lo = max(0, hi - BWD_BATCH);
+    const int cnt = hi - lo;
+    mbar_wait(&s_bar[st], (r >> 1) & 1);
+    const float4* rec4 = reinterpret_cast<const float4*>(&s_rec[st][0]);
+    uint32_t touched = 0;  // warp-uniform: bit (j & 31) set when this warp reduced record j
+
+    for (int j = cnt - 1; j >= 0; j--) {
+      // pixel p blended this record iff its reference list position (b.z) <= n_contrib[p] and the tests pass
+      const float4 a = rec4[3 * j], b = rec4[3 * j + 1];  // x, y, qa, qb | qc, op, orig, r
+      const float dx = a.x - fx;
+      const float u = a.z * dx * dx;  // qa dx^2
+      const float w = a.w * dx;       // qb dx
+      const int orig = (int)__float_as_uint(b.z);
+      float2 dy[NQ], araw[NQ];
+      bool ok[PPT];
+      bool any = false;
+#pragma unroll
+      for (int q = 0; q < NQ; q++) {
+        dy[q] = fadd2(bcast2(a.y), nfy[q]);
+        const float2 t = ffma2(bcast2(b.x), dy[q], bcast2(w));
+        const float2 pw = ffma2(t, dy[q], bcast2(u));
+        const float2 G = make_float2(ex2_approx_b(pw.x), ex2_approx_b(pw.y));
+        araw[q] = fmul2(bcast2(b.y), G);  // opacity * G: alpha before the 0.99 clamp
+        ok[2 * q] = orig <= nc[2 * q] && pw.x <= 0.0f && araw[q].x >= 1.0f / 255.0f;
+        ok[2 * q + 1] = orig <= nc[2 * q + 1] && pw.y <= 0.0f && araw[q].y >= 1.0f / 255.0f;
+        any = any || ok[2 * q] || ok[2 * q + 1];
+      }
+      if (__any_sync(0xffffffffu, any)) {
+        const float2 c = *reinterpret_cast<const float2*>(&rec4[3 * j + 2]);  // g, b
+        float2 s0 = make_float2(0.f, 0.f), s1 = s0, s2 = s0, k0 = s0, k1 = s0, k2 = s0;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          float2 og;  // opacity * G, zero for a pixel that does not take part
+          og.x = ok[2 * q] ? araw[q].x : 0.f;
+          og.y = ok[2 * q + 1] ? araw[q].y : 0.f;
+          const float2 al = make_float2(fminf(0.99f, og.x), fminf(0.99f, og.y));
+          const float2 om = fadd2(bcast2(1.f), make_float2(-al.x, -al.y));
+          const float2 rcp = make_float2(rcp_approx(om.x), rcp_approx(om.y));
+          T[q] = fmul2(T[q], rcp);
+          const float2 wgt = fmul2(al, T[q]);
+          float2 gc = fmul2(g0[q], bcast2(b.w));  // g . colour of this Gaussian
+          gc = ffma2(g1[q], bcast2(c.x), gc);
+          gc = ffma2(g2[q], bcast2(c.y), gc);
+          const float2 dot = fadd2(gc, make_float2(-S[q].x, -S[q].y));
+          const float2 dL_dalpha = ffma2(dot, T[q], fmul2(gob[q], rcp));
+          S[q] = ffma2(al, dot, S[q]);
+          const float2 t = fmul2(og, dL_dalpha);  // dL/dG * G
+          const float2 tdy = fmul2(t, dy[q]);
+          s0 = fadd2(s0, t);
+          s1 = fadd2(s1, tdy);
+          s2 = ffma2(tdy, dy[q], s2);
+          k0 = ffma2(wgt, g0[q], k0);
+          k1 = ffma2(wgt, g1[q], k1);
+          k2 = ffma2(wgt, g2[q], k2);
+        }
+        const float m0 = s0.x + s0.y, my = s1.x + s1.y, myy = s2.x + s2.y;
+        float v[8];
+        v[0] = m0;
+        v[1] = m0 * dx;       // sum t dx
+        v[2] = my;            // sum t dy
+        v[3] = v[1] * dx;     // sum t dx^2
+        v[4] = my * dx;       // sum t dx dy
+        v[5] = myy;           // sum t dy^2
+        v[6] = k0.x + k0.y;
+        v[7] = k1.x + k1.y;
+        const float v8 = k2.x + k2.y;
+        const float r8 = butterfly8(v, lane);
+        const float r1 = warp_sum(v8);
+        if ((lane & 3) == 0) s_acc[warp][j][lane >> 2] = r8;
+        if (lane == 1) s_acc[warp][j][8] = r1;
+        touched |= 1u << (j & 31);
+      }
+      if ((j & 31) == 0) {
+        if (lane == 0) s_touched[warp][j >> 5] = touched;
+        touched = 0;
+      }
+    }
+    __syncthreads();  // partial sums of this batch are complete
+    // flush: one thread per record adds the valid warp rows and issues the global reductions
+    for (int j = tid; j < cnt; j += NT) {
+      float q[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      bool hit = false;
+#pragma unroll
+      for (int w2 = 0; w2 < NW; w2++) {
+        if ((s_touched[w2][j >> 5] >> (j & 31)) & 1u) {
+          hit = true;
+          const float4 q0 = *reinterpret_cast<const float4*>(&s_acc[w2][j][0]);
+          const float4 q1 = *reinterpret_cast<const float4*>(&s_acc[w2][j][4]);
+          q[0] += q0.x; q[1] += q0.y; q[2] += q0.z; q[3] += q0.w;
+          q[4] += q1.x; q[5] += q1.y; q[6] += q1.z; q[7] += q1.w;
+          q[8] += s_acc[w2][j][8];
+        }
+      }
+      if (!hit) continue;
+      const Record rec = s_rec[st][j];
+      const uint32_t id = rec.id;
+      float cA, cB, cC;
+      record_conic(rec.qa, rec.qb, rec.qc, cA, cB, cC);
+      // q = (m0, mx, my, mxx, mxy, myy): dmean2D = -(conic . m1) * NDC scale, dconic = -1/2 m2, dopacity = m0 / opacity
+      const float gmx = -(cA * q[1] + cB * q[2]) * ddelx_dx;
+      const float gmy = -(cC * q[2] + cB * q[1]) * ddely_dy;
+      double* gg = ggrad + ((size_t)view * P + id) * OCRF_GGRAD_STRIDE;
+      atomicAdd(gg + 0, (double)gmx);
+      atomicAdd(gg + 1, (double)gmy);
+      atomicAdd(gg + 2, (double)(-0.5f * q[3]));
+      atomicAdd(gg + 3, (double)(-0.5f * q[4]));
+      atomicAdd(gg + 4, (double)(-0.5f * q[5]));
+      atomicAdd(gg + 5, (double)__fdividef(q[0], rec.op));
+      float* gcol = dL_dcolors + ((size_t)(colors_per_view ? view : view / views_per_sample) * P + id) * 3;
+      atomicAdd(gcol, q[6]);
+      atomicAdd(gcol + 1, q[7]);
+      atomicAdd(gcol + 2, q[8]);
     }
     __syncthreads();  // stage `st` and the partial sums are consumed: only now may round r+2 land
     if (tid == 0 && r + 2 < rounds) issue(r + 2);
@@ -382,8 +599,8 @@ __global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
       const float4 a = reinterpret_cast<const float4*>(&s_rec[j])[0];
       const float4 b = reinterpret_cast<const float4*>(&s_rec[j])[1];
       const float dx = a.x - fx, dy = a.y - fy;
-      const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-      const float G = ex2_approx_b(power * 1.4426950408889634f);
+      const float power = a.z * dx * dx + b.x * dy * dy + a.w * dx * dy;  // log2 domain (scaled conic)
+      const float G = ex2_approx_b(power);
       const float alpha = fminf(0.99f, b.y * G);
       const bool ok = (int)__float_as_uint(b.z) <= nc && power <= 0.0f && alpha >= 1.0f / 255.0f;
       float rcp = 1.f, w = 0.f, al = 0.f;
@@ -412,8 +629,9 @@ __global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
           const float dL_dalpha = dot * T + gob * rcp;
           const float dL_dG = b.y * dL_dalpha;
           const float gdx = G * dx, gdy = G * dy;
-          v[0] = dL_dG * (-gdx * a.z - gdy * a.w) * ddelx_dx;
-          v[1] = dL_dG * (-gdy * b.x - gdx * a.w) * ddely_dy;
+          // conic recovered from the scaled record: A = -2 ln2 qa, B = -ln2 qb, C = -2 ln2 qc
+          v[0] = dL_dG * (LN2 * (2.f * gdx * a.z + gdy * a.w)) * ddelx_dx;
+          v[1] = dL_dG * (LN2 * (2.f * gdy * b.x + gdx * a.w)) * ddely_dy;
           v[2] = -0.5f * gdx * dx * dL_dG;
           v[3] = -0.5f * gdx * dy * dL_dG;
           v[4] = -0.5f * gdy * dy * dL_dG;
@@ -559,19 +777,16 @@ extern "C" int ocrf_render_backward(void* stream, const OcrfShape* sh, uint64_t 
   const uint32_t* mc = at<uint32_t>(image_ws, I.max_contrib);
   if (sh->C == 3) {
     static const int ppt = env_int_b("OCRF_BWD_PPT", 4);
+    static const int packed = env_int_b("OCRF_BWD_PACKED", 1);  // 0: the scalar kernel (A/B measurements)
     const Record* rec = at<Record>(bin_ws, B.records);
-    if (ppt == 4)
-      OCRF_LAUNCH(render_backward_c3_kernel<4>, dim3(grid), dim3(TILE_PIX / 4), 0, st, sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
-                                                                  ranges, rec, bg, fT, nc, mc, dL_dcolor,
-                                                                  dL_dopacity_map, ggrad, dL_dcolors);
-    else if (ppt == 2)
-      OCRF_LAUNCH(render_backward_c3_kernel<2>, dim3(grid), dim3(TILE_PIX / 2), 0, st, sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
-                                                                  ranges, rec, bg, fT, nc, mc, dL_dcolor,
-                                                                  dL_dopacity_map, ggrad, dL_dcolors);
-    else
-      OCRF_LAUNCH(render_backward_c3_kernel<1>, dim3(grid), dim3(TILE_PIX), 0, st, sh->W, sh->H, sh->P, sh->views_per_sample, use_sh,
-                                                              ranges, rec, bg, fT, nc, mc, dL_dcolor, dL_dopacity_map,
-                                                              ggrad, dL_dcolors);
+#define OCRF_BWD_ARGS sh->W, sh->H, sh->P, sh->views_per_sample, use_sh, ranges, rec, bg, fT, nc, mc, dL_dcolor, \
+                      dL_dopacity_map, ggrad, dL_dcolors
+    if (packed && ppt == 2) OCRF_LAUNCH(render_backward_c3_kernel<2>, dim3(grid), dim3(TILE_PIX / 2), 0, st, OCRF_BWD_ARGS);
+    else if (packed) OCRF_LAUNCH(render_backward_c3_kernel<4>, dim3(grid), dim3(TILE_PIX / 4), 0, st, OCRF_BWD_ARGS);
+    else if (ppt == 4) OCRF_LAUNCH(render_backward_c3_scalar_kernel<4>, dim3(grid), dim3(TILE_PIX / 4), 0, st, OCRF_BWD_ARGS);
+    else if (ppt == 2) OCRF_LAUNCH(render_backward_c3_scalar_kernel<2>, dim3(grid), dim3(TILE_PIX / 2), 0, st, OCRF_BWD_ARGS);
+    else OCRF_LAUNCH(render_backward_c3_scalar_kernel<1>, dim3(grid), dim3(TILE_PIX), 0, st, OCRF_BWD_ARGS);
+#undef OCRF_BWD_ARGS
   } else {
     if (!colors) return OCRF_EINVAL;
     const Record* rec = at<Record>(bin_ws, B.records);

@@ -29,7 +29,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 template <int PPT>
-__global__ void __launch_bounds__(TILE_PIX / PPT) render_forward_c3_kernel(
+__global__ void __launch_bounds__(TILE_PIX / PPT) render_forward_c3_scalar_kernel(
     int W, int H, const uint2* __restrict__ ranges /* culled lists */, const Record* __restrict__ records,
     const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
     uint32_t* __restrict__ max_contrib, float* __restrict__ out_color, float* __restrict__ out_depth,
@@ -110,8 +110,8 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_forward_c3_kernel(
 #pragma unroll
         for (int p = 0; p < PPT; p++) {
           const float dx = a.x - fx[p], dy = a.y - fy[p];
-          const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-          const float alpha = fminf(0.99f, b.y * ex2_approx(power * 1.4426950408889634f));
+          const float power = a.z * dx * dx + b.x * dy * dy + a.w * dx * dy;  // log2 domain (scaled conic)
+          const float alpha = fminf(0.99f, b.y * ex2_approx(power));
           const bool ok = !done[p] && power <= 0.0f && alpha >= 1.0f / 255.0f;
           alpha_p[p] = ok ? alpha : 0.f;
           any_blend = any_blend || ok;
@@ -182,6 +182,186 @@ __global__ void __launch_bounds__(TILE_PIX / PPT) render_forward_c3_kernel(
   if (tid == 0) max_contrib[(size_t)view * tiles_per_view + tile] = s_max;
 }
 
+// The production C == 3 kernel: the scalar kernel above with the per-(pixel, Gaussian) arithmetic PACKED two pixels
+// per instruction (sm_100 FFMA2 / FMUL2 / FADD2).  A thread owns PPT pixels of ONE column (same x, rows 4 apart), so
+//   log2 G = qa dx^2 + qb dx dy + qc dy^2 = (qc dy + qb dx) dy + qa dx^2
+// costs 1 FADD + 3 FMUL once per thread (the dx terms) and 1 FADD2 + 2 FFMA2 per pixel PAIR; the record's scalars
+// enter the packed instructions as broadcast operands.  The blend itself (1 - alpha, T (1 - alpha), alpha T, the three
+// colour accumulations) is packed the same way.  A finished (or out-of-image) pixel is marked by a NaN row coordinate:
+// its power is NaN, `power <= 0` is false, and it needs no predicate of its own in the test.
+template <int PPT>
+__global__ void __launch_bounds__(TILE_PIX / PPT) render_forward_c3_kernel(
+    int W, int H, const uint2* __restrict__ ranges /* culled lists */, const Record* __restrict__ records,
+    const float* __restrict__ bg, float* __restrict__ final_T, uint32_t* __restrict__ n_contrib,
+    uint32_t* __restrict__ max_contrib, float* __restrict__ out_color, float* __restrict__ out_depth,
+    float* __restrict__ out_opacity) {
+  pdl_enter();
+  static_assert(PPT == 2 || PPT == 4, "pixel pairs");
+  constexpr int NT = TILE_PIX / PPT;
+  constexpr int NQ = PPT / 2;
+  __shared__ __align__(128) Record s_rec[2][FWD_BATCH];
+  __shared__ __align__(8) uint64_t s_bar[2];
+  __shared__ uint32_t s_max;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = gridDim.x, tiles_per_view = gridDim.x * gridDim.y;
+  const int view = blockIdx.z;
+  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  const uint2 range = ranges[(size_t)view * tiles_per_view + tile];
+  const int n = (int)(range.y - range.x);
+  const int rounds = (n + FWD_BATCH - 1) / FWD_BATCH;
+  const Record* src = records + range.x;
+
+  // pixel column of this thread: x = px, rows py0 + 4 p
+  const int px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
+  const int py0 = blockIdx.y * TILE + (warp >> 1) * (4 * PPT) + (lane >> 3);
+  const float fx = (float)px;
+  float2 nfy[NQ];  // minus the row coordinate of the pair's pixels; NaN = pixel finished / outside the image
+  const float qnan = __int_as_float(0x7fc00000);
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    const int y0 = py0 + 8 * q, y1 = y0 + 4;
+    nfy[q].x = (px < W && y0 < H) ? -(float)y0 : qnan;
+    nfy[q].y = (px < W && y1 < H) ? -(float)y1 : qnan;
+  }
+
+  if (tid == 0) {
+    mbar_init(&s_bar[0], 1);
+    mbar_init(&s_bar[1], 1);
+    mbar_fence_init();
+    s_max = 0;
+  }
+  __syncthreads();
+  if (tid == 0) {
+#pragma unroll
+    for (int r = 0; r < 2; r++)
+      if (r < rounds) {
+        const uint32_t bytes = (uint32_t)min(FWD_BATCH, n - r * FWD_BATCH) * sizeof(Record);
+        mbar_expect_tx(&s_bar[r], bytes);
+        bulk_g2s(&s_rec[r][0], src + r * FWD_BATCH, bytes, &s_bar[r]);
+      }
+  }
+
+  float2 T[NQ], C0[NQ], C1[NQ], C2[NQ], D[NQ];
+  uint32_t last[PPT];   // reference numbering (position in the unculled list), stored as n_contrib
+  uint32_t lastc = 0;   // position in the culled list of the last record any of my pixels blended
+#pragma unroll
+  for (int q = 0; q < NQ; q++) {
+    T[q] = make_float2(1.f, 1.f);
+    D[q] = make_float2(15.f, 15.f);
+    C0[q] = C1[q] = C2[q] = make_float2(0.f, 0.f);
+    last[2 * q] = last[2 * q + 1] = 0;
+  }
+  auto all_finished = [&]() {
+    bool f = true;
+#pragma unroll
+    for (int q = 0; q < NQ; q++) f = f && (nfy[q].x != nfy[q].x) && (nfy[q].y != nfy[q].y);
+    return f;
+  };
+
+  for (int r = 0; r < rounds; r++) {
+    const int st = r & 1;
+    mbar_wait(&s_bar[st], (r >> 1) & 1);
+    const int cnt = min(FWD_BATCH, n - r * FWD_BATCH);
+    const float4* rec4 = reinterpret_cast<const float4*>(&s_rec[st][0]);
+    // Control flow inside the batch is WARP-UNIFORM (votes over the full warp), see the scalar kernel.
+    bool all_done = all_finished();
+    if (!__all_sync(0xffffffffu, all_done)) {
+      for (int j = 0; j < cnt; j++) {
+        const float4 a = rec4[3 * j], b = rec4[3 * j + 1];  // x, y, qa, qb | qc, op, orig, r
+        const float dx = a.x - fx;
+        const float u = a.z * dx * dx;  // qa dx^2
+        const float w = a.w * dx;       // qb dx
+        float2 araw[NQ];  // opacity * G, not yet clamped: the clamp and the zeroing of non-participants wait for the blend
+        bool ok[PPT];
+        bool any_blend = false;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          const float2 dy = fadd2(bcast2(a.y), nfy[q]);
+          const float2 t = ffma2(bcast2(b.x), dy, bcast2(w));
+          const float2 pw = ffma2(t, dy, bcast2(u));
+          const float2 g = make_float2(ex2_approx(pw.x), ex2_approx(pw.y));
+          araw[q] = fmul2(bcast2(b.y), g);
+          // min(0.99, alpha) >= 1/255 <=> alpha >= 1/255; the NaN power of a finished pixel compares false
+          ok[2 * q] = pw.x <= 0.0f && araw[q].x >= 1.0f / 255.0f;
+          ok[2 * q + 1] = pw.y <= 0.0f && araw[q].y >= 1.0f / 255.0f;
+          any_blend = any_blend || ok[2 * q] || ok[2 * q + 1];
+        }
+        if (!__any_sync(0xffffffffu, any_blend)) continue;  // nobody in the warp blends this Gaussian
+        const float4 c = rec4[3 * j + 2];  // g, b, id, depth
+        bool newly_done = false;
+        bool blended = false;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+          const bool on0 = ok[2 * q], on1 = ok[2 * q + 1];
+          float2 alq;
+          alq.x = on0 ? fminf(0.99f, araw[q].x) : 0.f;
+          alq.y = on1 ? fminf(0.99f, araw[q].y) : 0.f;
+          const float2 om = fadd2(bcast2(1.f), make_float2(-alq.x, -alq.y));
+          const float2 tT = fmul2(T[q], om);
+          float2 wgt = fmul2(alq, T[q]);  // 0 for a pixel that does not take part (alpha == 0)
+          const bool stop0 = on0 && tT.x < 0.0001f, stop1 = on1 && tT.y < 0.0001f;
+          const bool bl0 = on0 && !stop0, bl1 = on1 && !stop1;
+          wgt.x = stop0 ? 0.f : wgt.x;
+          wgt.y = stop1 ? 0.f : wgt.y;
+          C0[q] = ffma2(bcast2(b.w), wgt, C0[q]);
+          C1[q] = ffma2(bcast2(c.x), wgt, C1[q]);
+          C2[q] = ffma2(bcast2(c.y), wgt, C2[q]);
+          if (bl0 && T[q].x > 0.5f && tT.x < 0.5f) D[q].x = c.w;
+          if (bl1 && T[q].y > 0.5f && tT.y < 0.5f) D[q].y = c.w;
+          T[q].x = bl0 ? tT.x : T[q].x;
+          T[q].y = bl1 ? tT.y : T[q].y;
+          last[2 * q] = bl0 ? __float_as_uint(b.z) : last[2 * q];
+          last[2 * q + 1] = bl1 ? __float_as_uint(b.z) : last[2 * q + 1];
+          blended = blended || bl0 || bl1;
+          nfy[q].x = stop0 ? qnan : nfy[q].x;
+          nfy[q].y = stop1 ? qnan : nfy[q].y;
+          newly_done = newly_done || stop0 || stop1;
+        }
+        if (blended) lastc = (uint32_t)(r * FWD_BATCH + j + 1);
+        if (__any_sync(0xffffffffu, newly_done)) {
+          all_done = all_finished();
+          if (__all_sync(0xffffffffu, all_done)) break;
+        }
+      }
+    }
+    // everyone is finished with stage `st`; leave early once the whole tile is saturated
+    const int num_done = __syncthreads_count(all_done);
+    if (num_done == NT) {
+      if (r + 1 < rounds) mbar_wait(&s_bar[(r + 1) & 1], ((r + 1) >> 1) & 1);  // drain the copy in flight
+      break;
+    }
+    if (tid == 0 && r + 2 < rounds) {
+      const uint32_t bytes = (uint32_t)min(FWD_BATCH, n - (r + 2) * FWD_BATCH) * sizeof(Record);
+      mbar_expect_tx(&s_bar[st], bytes);
+      bulk_g2s(&s_rec[st][0], src + (r + 2) * FWD_BATCH, bytes, &s_bar[st]);
+    }
+  }
+
+  const size_t HW = (size_t)H * W;
+  const float bg0 = bg[0], bg1 = bg[1], bg2 = bg[2];
+#pragma unroll
+  for (int p = 0; p < PPT; p++) {
+    const int q = p >> 1;
+    const int py = py0 + 8 * q + 4 * (p & 1);
+    if (!(px < W && py < H)) continue;
+    const float Tp = (p & 1) ? T[q].y : T[q].x;
+    const size_t pix = (size_t)py * W + px;
+    final_T[view * HW + pix] = Tp;
+    n_contrib[view * HW + pix] = last[p];
+    float* oc = out_color + (size_t)view * 3 * HW + pix;
+    oc[0] = ((p & 1) ? C0[q].y : C0[q].x) + Tp * bg0;
+    oc[HW] = ((p & 1) ? C1[q].y : C1[q].x) + Tp * bg1;
+    oc[2 * HW] = ((p & 1) ? C2[q].y : C2[q].x) + Tp * bg2;
+    if (out_depth) out_depth[view * HW + pix] = (p & 1) ? D[q].y : D[q].x;
+    if (out_opacity) out_opacity[view * HW + pix] = 1.f - Tp;
+  }
+  const uint32_t my_max = __reduce_max_sync(0xffffffffu, lastc);
+  if (lane == 0 && my_max) atomicMax(&s_max, my_max);
+  __syncthreads();
+  if (tid == 0) max_contrib[(size_t)view * tiles_per_view + tile] = s_max;
+}
+
 // Generic channel count: 32-byte records, features gathered by id, CK channels per traversal.
 constexpr int FWD_CK = 16;
 constexpr int FWDG_BATCH = 128;
@@ -236,8 +416,8 @@ __global__ void __launch_bounds__(TILE_PIX) render_forward_generic_kernel(
         const float4 a = reinterpret_cast<const float4*>(&s_rec[j])[0];
         const float4 b = reinterpret_cast<const float4*>(&s_rec[j])[1];
         const float dx = a.x - fx, dy = a.y - fy;
-        const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-        const float alpha = fminf(0.99f, b.y * ex2_approx(power * 1.4426950408889634f));
+        const float power = a.z * dx * dx + b.x * dy * dy + a.w * dx * dy;  // log2 domain (scaled conic)
+        const float alpha = fminf(0.99f, b.y * ex2_approx(power));
         const bool ok = !done && power <= 0.0f && alpha >= 1.0f / 255.0f;
         if (!__any_sync(0xffffffffu, ok)) continue;
         const float test_T = T * (1.f - alpha);
@@ -335,8 +515,8 @@ __global__ void __launch_bounds__(TILE_PIX, CP <= 80 ? 2 : 1) render_forward_wid
       const float4 a = reinterpret_cast<const float4*>(&s_rec[j])[0];
       const float4 b = reinterpret_cast<const float4*>(&s_rec[j])[1];
       const float dx = a.x - fx, dy = a.y - fy;
-      const float power = -0.5f * (a.z * dx * dx + b.x * dy * dy) - a.w * dx * dy;
-      const float alpha = fminf(0.99f, b.y * ex2_approx(power * 1.4426950408889634f));
+      const float power = a.z * dx * dx + b.x * dy * dy + a.w * dx * dy;  // log2 domain (scaled conic)
+      const float alpha = fminf(0.99f, b.y * ex2_approx(power));
       const bool ok = !done && power <= 0.0f && alpha >= 1.0f / 255.0f;
       if (!__any_sync(0xffffffffu, ok)) continue;
       const float test_T = T * (1.f - alpha);
@@ -414,16 +594,15 @@ extern "C" int ocrf_render_forward(void* stream, const OcrfShape* sh, uint64_t p
   uint32_t* mc = at<uint32_t>(image_ws, I.max_contrib);
   if (sh->C == 3) {
     static const int ppt = env_int("OCRF_FWD_PPT", 2);
+    static const int packed = env_int("OCRF_FWD_PACKED", 1);  // 0: the scalar kernel (A/B measurements)
     const Record* rec = at<Record>(bin_ws, B.records);
-    if (ppt == 4)
-      OCRF_LAUNCH(render_forward_c3_kernel<4>, dim3(grid), dim3(TILE_PIX / 4), 0, st, sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
-                                                                 out_depth, out_opacity);
-    else if (ppt == 2)
-      OCRF_LAUNCH(render_forward_c3_kernel<2>, dim3(grid), dim3(TILE_PIX / 2), 0, st, sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
-                                                                 out_depth, out_opacity);
-    else
-      OCRF_LAUNCH(render_forward_c3_kernel<1>, dim3(grid), dim3(TILE_PIX), 0, st, sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color,
-                                                             out_depth, out_opacity);
+#define OCRF_FWD_ARGS sh->W, sh->H, ranges, rec, bg, fT, nc, mc, out_color, out_depth, out_opacity
+    if (packed && ppt == 4) OCRF_LAUNCH(render_forward_c3_kernel<4>, dim3(grid), dim3(TILE_PIX / 4), 0, st, OCRF_FWD_ARGS);
+    else if (packed) OCRF_LAUNCH(render_forward_c3_kernel<2>, dim3(grid), dim3(TILE_PIX / 2), 0, st, OCRF_FWD_ARGS);
+    else if (ppt == 4) OCRF_LAUNCH(render_forward_c3_scalar_kernel<4>, dim3(grid), dim3(TILE_PIX / 4), 0, st, OCRF_FWD_ARGS);
+    else if (ppt == 2) OCRF_LAUNCH(render_forward_c3_scalar_kernel<2>, dim3(grid), dim3(TILE_PIX / 2), 0, st, OCRF_FWD_ARGS);
+    else OCRF_LAUNCH(render_forward_c3_scalar_kernel<1>, dim3(grid), dim3(TILE_PIX), 0, st, OCRF_FWD_ARGS);
+#undef OCRF_FWD_ARGS
   } else {
     (void)use_sh;
     const Record* rec = at<Record>(bin_ws, B.records);

@@ -51,16 +51,21 @@ class GraphedRenderStep:
         """Fill the static buffers with `example` (representative inputs: they only serve as warm-up), run the step a
         few times on a side stream, then capture it."""
         self._load(example)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                self._step()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.outs, self.grads = self._step()
+        status = R._Status.get(self.cams.device)
+        status.muted = True  # an overflow of the warm-up inputs must not raise out of the middle of the capture;
+        try:                 # it stays in the device's sticky words and is reported by check_overflow()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    self._step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph):
+                self.outs, self.grads = self._step()
+        finally:
+            status.muted = False
         return self
 
     def _load(self, inputs):

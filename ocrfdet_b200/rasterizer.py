@@ -97,6 +97,7 @@ class _Status:
         self.dev = torch.zeros(2, dtype=torch.int32, device=device)
         self.host = torch.zeros(2, dtype=torch.int32).pin_memory()
         self.host_np = self.host.numpy()  # same memory: polling costs a numpy scalar read, not a tensor op
+        self.muted = False  # GraphedRenderStep: no exception out of the middle of a capture (replays never poll)
 
     @classmethod
     def get(cls, device):
@@ -122,6 +123,8 @@ class _Status:
 
     def poll(self):
         """Non-blocking: raise if a mirrored status word shows an error of an earlier call."""
+        if self.muted:
+            return
         flags = int(self.host_np[0])
         if flags & 3:
             self._raise(flags, int(self.host_np[1]))
@@ -374,7 +377,7 @@ def last_state(reference_lists=False):
         img2 = torch.empty_like(image)
         check(L.ocrf_bin_forward(current_stream(), C.byref(shape), C.c_uint64(st["capacity"]), ptr(st["radii"]),
                                  ptr(st["colors"]), int(st["use_sh"]), C.c_uint32(_lib.OCRF_BIN_PAIR_SORT), ptr(geom),
-                                 ptr(bin2), ptr(img2)), "ocrf_bin_forward(pair sort)")
+                                 ptr(bin2), ptr(img2), None), "ocrf_bin_forward(pair sort)")
         out["keys_ref"] = view(bin2, b.keys, N, torch.int64, N)
         out["point_list_ref"] = view(bin2, b.point_list, N, torch.int32, N)
         out["records_ref"] = view(bin2, b.records, 12 * N, torch.int32, N, 12)
