@@ -210,9 +210,10 @@ def run_ours(args, rank, world, device):
         tile_passes = (end_bit - 32 + 7) // 8
         launches_per_step = 1 + (1 + vis_passes) + 2 + (1 + tile_passes) + 1 + 4
     else:
-        # default multi-split: preprocess | histogram + passes over (view|depth) | scan | count, scan chunks,
+        # default multi-split: preprocess | on-chip cluster sort of the visible Gaussians (+ scan) | count, scan chunks,
         # scan tiles, scatter | fwd | clear grads | bwd | preprocess bwd
-        launches_per_step = 1 + (1 + vis_passes) + 1 + 4 + 4
+        onchip = not os.environ.get("OCRF_VIS_SORT", "").startswith("g")
+        launches_per_step = 1 + (1 if onchip else (1 + vis_passes) + 1) + 4 + 4
 
     # ---- device-resident throughput ----
     sampler = ClockSampler(torch.cuda.current_device())

@@ -409,26 +409,36 @@ extern "C" int ocrf_bin_forward(void* stream, const OcrfShape* sh, uint64_t pair
   const bool multisplit = !pairsort && !(flags & OCRF_BIN_DEPTH_FIRST) && tiles_v <= 4096;
   (void)gxh; (void)gyh;
   if (!pairsort) {
-    // (1) depth-sort the visible Gaussians: same onesweep sort, ~30x fewer elements than the pair sort
-    const int vbit = vis_sort_end_bit(sh->V);
-    const int vpasses = (vbit + 7) / 8;
-    uint64_t* ka = at<uint64_t>(geom_ws, (vpasses & 1) ? G.vis_keys_tmp : G.vis_keys);
-    uint32_t* va = at<uint32_t>(geom_ws, (vpasses & 1) ? G.vis_vals_tmp : G.vis_vals);
-    uint64_t* kb = at<uint64_t>(geom_ws, (vpasses & 1) ? G.vis_keys : G.vis_keys_tmp);
-    uint32_t* vb = at<uint32_t>(geom_ws, (vpasses & 1) ? G.vis_vals : G.vis_vals_tmp);
-    // The sort workspace was zeroed together with the geom header (ocrf_preprocess_forward); the look-back state of
-    // the scan below is cleared by the sort's histogram kernel: no memset node between preprocess and the blend.
-    unsigned long long* sstat = at<unsigned long long>(bin_ws, B.split_tiles);
-    const size_t sblocks = (n + 1023) / 1024;
-    uint32_t* sticket = reinterpret_cast<uint32_t*>(sstat + sblocks + 1);
-    rc = sort_pairs_device(st, header + HDR_NUM_VIS, n, 0, vbit, ka, va, kb, vb, at<char>(geom_ws, G.vis_sort_ws), true,
-                           reinterpret_cast<uint32_t*>(sstat), (uint32_t)(((sblocks + 1) * 8 + 64) / 4));
-    if (rc) return rc;
-    // (2) inclusive scan of tiles_touched in depth order: where every Gaussian's pairs sit in the pair stream
+    // (1) depth-sort the visible Gaussians of every view and (2) scan their tile counts in that order: where every
+    //     Gaussian's pairs sit in the pair stream
     const uint32_t* vvals = at<uint32_t>(geom_ws, G.vis_vals);
     uint32_t* sorted_offsets = at<uint32_t>(bin_ws, B.split_counts);
-    OCRF_LAUNCH(scan_sorted_tiles_kernel, dim3((unsigned)sblocks), dim3(256), 0, st, header, vvals, at<uint32_t>(geom_ws, G.tiles_touched),
-                                                                sorted_offsets, sstat, sticket);
+    const size_t sblocks = (n + 1023) / 1024;
+    if (vis_sort_onchip()) {
+      // one cluster of 8 CTAs per view: four digit passes through distributed shared memory + the scan, one launch
+      rc = visible_sort(st, sh, at<uint32_t>(geom_ws, G.view_start), at<uint64_t>(geom_ws, G.vis_keys),
+                        at<uint32_t>(geom_ws, G.vis_vals), at<uint64_t>(geom_ws, G.vis_keys_tmp),
+                        at<uint32_t>(geom_ws, G.vis_vals_tmp), at<uint32_t>(geom_ws, G.tiles_touched),
+                        at<uint32_t>(geom_ws, G.offsets), sorted_offsets);
+      if (rc) return rc;
+    } else {
+      // round 1: the global onesweep sort over (view | depth) + a look-back scan (kept for A/B measurements)
+      const int vbit = vis_sort_end_bit(sh->V);
+      const int vpasses = (vbit + 7) / 8;
+      uint64_t* ka = at<uint64_t>(geom_ws, (vpasses & 1) ? G.vis_keys_tmp : G.vis_keys);
+      uint32_t* va = at<uint32_t>(geom_ws, (vpasses & 1) ? G.vis_vals_tmp : G.vis_vals);
+      uint64_t* kb = at<uint64_t>(geom_ws, (vpasses & 1) ? G.vis_keys : G.vis_keys_tmp);
+      uint32_t* vb = at<uint32_t>(geom_ws, (vpasses & 1) ? G.vis_vals : G.vis_vals_tmp);
+      // The sort workspace was zeroed together with the geom header (ocrf_preprocess_forward); the look-back state of
+      // the scan below is cleared by the sort's histogram kernel: no memset node between preprocess and the blend.
+      unsigned long long* sstat = at<unsigned long long>(bin_ws, B.split_tiles);
+      uint32_t* sticket = reinterpret_cast<uint32_t*>(sstat + sblocks + 1);
+      rc = sort_pairs_device(st, header + HDR_NUM_VIS, n, 0, vbit, ka, va, kb, vb, at<char>(geom_ws, G.vis_sort_ws), true,
+                             reinterpret_cast<uint32_t*>(sstat), (uint32_t)(((sblocks + 1) * 8 + 64) / 4));
+      if (rc) return rc;
+      OCRF_LAUNCH(scan_sorted_tiles_kernel, dim3((unsigned)sblocks), dim3(256), 0, st, header, vvals,
+                  at<uint32_t>(geom_ws, G.tiles_touched), sorted_offsets, sstat, sticket);
+    }
     if (multisplit) {
       // (3) one stable multi-split of the pair stream by tile, culled records written directly
       uint32_t* tile_arrays = at<uint32_t>(bin_ws, B.split_tiles + align128((sblocks + 1) * 8 + 128));

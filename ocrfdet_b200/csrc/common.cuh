@@ -158,6 +158,17 @@ inline int view_bits(int V) {            // bits needed for view indices 0..V-1
   return b;
 }
 inline int vis_sort_end_bit(int V) { return 32 + view_bits(V); }
+// The visible Gaussians are sorted by the on-chip cluster sort (visible_sort.cu: 4 passes over the depth bits, input
+// and result in the same half of the ping-pong) unless OCRF_VIS_SORT=global asks for round 1's global onesweep sort
+// over (view | depth) (A/B measurements; its pass count decides in which half the compacted input must start).
+inline bool vis_sort_onchip() {
+  static const bool on = !(getenv("OCRF_VIS_SORT") != nullptr && getenv("OCRF_VIS_SORT")[0] == 'g');
+  return on;
+}
+inline bool vis_sort_starts_in_tmp(int V) { return vis_sort_onchip() ? false : ((((vis_sort_end_bit(V) + 7) / 8) & 1) != 0); }
+int visible_sort(cudaStream_t st, const OcrfShape* sh, const uint32_t* view_start, uint64_t* keys0, uint32_t* vals0,
+                 uint64_t* keys1, uint32_t* vals1, const uint32_t* tiles_touched, const uint32_t* offsets,
+                 uint32_t* sorted_offsets);
 // multisplit.cu
 struct Record;
 int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity, int use_sh, const int32_t* radii,

@@ -258,8 +258,8 @@ extern "C" int ocrf_preprocess_forward(void* stream, const OcrfShape* sh, const 
       at<uint32_t>(geom_ws, L.offsets), at<float>(geom_ws, L.rgb), at<uint8_t>(geom_ws, L.clamped),
       at<unsigned long long>(geom_ws, L.scan_status),
       // the sort of the visible Gaussians ends in (vis_keys, vis_vals): start in the tmp half when its pass count is odd
-      at<uint64_t>(geom_ws, (((vis_sort_end_bit(sh->V) + 7) / 8) & 1) ? L.vis_keys_tmp : L.vis_keys),
-      at<uint32_t>(geom_ws, (((vis_sort_end_bit(sh->V) + 7) / 8) & 1) ? L.vis_vals_tmp : L.vis_vals),
+      at<uint64_t>(geom_ws, vis_sort_starts_in_tmp(sh->V) ? L.vis_keys_tmp : L.vis_keys),
+      at<uint32_t>(geom_ws, vis_sort_starts_in_tmp(sh->V) ? L.vis_vals_tmp : L.vis_vals),
       at<uint32_t>(geom_ws, L.view_start));
   OCRF_CHECK_LAST();
   return 0;

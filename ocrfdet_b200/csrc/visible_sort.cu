@@ -1,0 +1,203 @@
+// Stage 2, first step: depth-sort the VISIBLE Gaussians of every view, on chip, and scan their tile counts.
+//
+// The reference sorts every (tile | depth) pair (cuda_rasterizer/rasterizer_impl.cu:303-308).  Here only the visible
+// Gaussians of a view (~19 k at the headline shape, 228 KB of (key, value) pairs) are sorted by depth; the pair stream
+// is then split stably by tile (multisplit.cu).  Round 1 pushed these 114 k keys through the global onesweep sort: a
+// histogram kernel and five chained passes, 77 us for 1.4 MB -- a fixed chain of launches and L2 round trips.
+//
+// One thread-block CLUSTER of 8 CTAs owns a view (the views are already segments of the compacted key array, so the
+// view bits need no pass).  Per 8-bit digit place, CTA r of the cluster
+//   (1) counts the digits of ITS eighth of the segment into shared memory,
+//   (2) after a cluster barrier reads the eight histograms through distributed shared memory and derives, per digit,
+//       the global base + the keys of lower-ranked CTAs: the stable destination of its own keys,
+//   (3) ranks its keys (warp match_any multi-split, the ranking of radix_sort.cu) and writes them to the other half
+//       of the ping-pong (L2-resident),
+// and a second cluster barrier ends the pass.  Four passes cover the 32 depth bits; no look-back chain, no global
+// histogram, one launch.  The epilogue replaces scan_sorted_tiles_kernel: the inclusive scan of tiles_touched in sorted
+// order (where every Gaussian's pairs sit in the pair stream), the cluster exchanging eight partial sums.
+// Any segment size works (a CTA loops over sub-tiles of 4096 keys).
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace ocrf {
+
+constexpr int VS_CLUSTER = 8;
+constexpr int VS_THREADS = 256;
+constexpr int VS_WARPS = VS_THREADS / 32;
+constexpr int VS_ITEMS = 16;
+constexpr int VS_SUBTILE = VS_THREADS * VS_ITEMS;
+
+__device__ __forceinline__ uint32_t vs_exclusive_scan_256(uint32_t v, uint32_t* s_warp /*[8]*/) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t incl = v;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  __syncthreads();  // s_warp may still be read from the previous use
+  if (lane == 31) s_warp[warp] = incl;
+  __syncthreads();
+  uint32_t off = 0;
+#pragma unroll
+  for (int w = 0; w < VS_WARPS; w++)
+    if (w < warp) off += s_warp[w];
+  return off + incl - v;
+}
+
+__global__ void __cluster_dims__(VS_CLUSTER, 1, 1) __launch_bounds__(VS_THREADS) visible_sort_kernel(
+    int P, const uint32_t* __restrict__ view_start, uint64_t* keys0, uint32_t* vals0, uint64_t* keys1, uint32_t* vals1,
+    const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ offsets,
+    uint32_t* __restrict__ sorted_offsets) {
+  pdl_enter();
+  cg::cluster_group cluster = cg::this_cluster();
+  __shared__ uint32_t s_hist[256];                 // digit counts of my part of the segment (read by the other CTAs)
+  __shared__ uint32_t s_base[256];                 // running destination of my next key of every digit
+  __shared__ uint32_t s_warp_hist[VS_WARPS][256];
+  __shared__ uint32_t s_scan[VS_WARPS];
+  __shared__ uint32_t s_total;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = cluster.block_rank();
+  const int v = blockIdx.y;
+  const uint32_t seg_b = view_start[v], n = view_start[v + 1] - seg_b;
+  const uint32_t per = (n + VS_CLUSTER - 1) / VS_CLUSTER;
+  const uint32_t cb = seg_b + min(n, rank * per), ce = seg_b + min(n, (rank + 1) * per);
+  const uint32_t lt_mask = (1u << lane) - 1;
+
+  for (int pass = 0; pass < 4; pass++) {
+    const uint64_t* src_k = (pass & 1) ? keys1 : keys0;
+    const uint32_t* src_v = (pass & 1) ? vals1 : vals0;
+    uint64_t* dst_k = (pass & 1) ? keys0 : keys1;
+    uint32_t* dst_v = (pass & 1) ? vals0 : vals1;
+    const int shift = 8 * pass;
+    // (1) digit counts of my part
+    s_hist[tid] = 0;
+    __syncthreads();
+    for (uint32_t i = cb + tid; i < ce; i += VS_THREADS) atomicAdd(&s_hist[(uint32_t)(src_k[i] >> shift) & 255u], 1u);
+    __syncthreads();
+    cluster.sync();
+    // (2) thread d: keys with digit d in the whole segment, and in the parts before mine
+    uint32_t total = 0, before = 0;
+#pragma unroll
+    for (uint32_t r = 0; r < VS_CLUSTER; r++) {
+      const uint32_t c = *cluster.map_shared_rank(&s_hist[tid], r);
+      total += c;
+      before += r < rank ? c : 0u;
+    }
+    const uint32_t excl = vs_exclusive_scan_256(total, s_scan);
+    s_base[tid] = seg_b + excl + before;
+    // (3) stable ranks + scatter, one sub-tile of 4096 keys at a time
+    for (uint32_t sub = cb; sub < ce; sub += VS_SUBTILE) {
+      const uint32_t n_valid = min((uint32_t)VS_SUBTILE, ce - sub);
+#pragma unroll
+      for (int w = 0; w < VS_WARPS; w++) s_warp_hist[w][tid] = 0;
+      __syncthreads();  // (also orders s_base of the previous sub-tile / of step (2))
+      uint64_t key[VS_ITEMS];
+      uint32_t rk[VS_ITEMS];
+      uint32_t* my_hist = s_warp_hist[warp];
+      const uint32_t warp_base = warp * (32 * VS_ITEMS);
+#pragma unroll
+      for (int i = 0; i < VS_ITEMS; i++) {
+        const uint32_t loc = warp_base + i * 32 + lane;  // index order inside the warp: the ranking below is stable
+        key[i] = loc < n_valid ? src_k[sub + loc] : 0ull;
+      }
+#pragma unroll
+      for (int i = 0; i < VS_ITEMS; i++) {
+        const uint32_t loc = warp_base + i * 32 + lane;
+        const bool valid = loc < n_valid;
+        const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u + lane);
+        uint32_t b4 = 0;
+        if (valid) b4 = my_hist[d];
+        __syncwarp();
+        if (valid && (peers & lt_mask) == 0) my_hist[d] = b4 + __popc(peers);
+        __syncwarp();
+        rk[i] = b4 + __popc(peers & lt_mask);
+      }
+      __syncthreads();
+      uint32_t tile_count = 0;
+#pragma unroll
+      for (int w = 0; w < VS_WARPS; w++) {  // thread d: exclusive prefix over the warps
+        const uint32_t c = s_warp_hist[w][tid];
+        s_warp_hist[w][tid] = tile_count;
+        tile_count += c;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int i = 0; i < VS_ITEMS; i++) {
+        const uint32_t loc = warp_base + i * 32 + lane;
+        if (loc < n_valid) {
+          const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
+          const uint32_t pos = s_base[d] + my_hist[d] + rk[i];
+          dst_k[pos] = key[i];
+          dst_v[pos] = src_v[sub + loc];
+        }
+      }
+      __syncthreads();
+      s_base[tid] += tile_count;
+    }
+    __threadfence();
+    cluster.sync();  // the pass is complete and visible to the whole cluster; s_hist may be reused
+  }
+
+  // ---- epilogue: inclusive scan of tiles_touched over the sorted order (four passes end in keys0 / vals0) ----
+  uint32_t mine = 0;
+  for (uint32_t i = cb + tid; i < ce; i += VS_THREADS) {
+    const uint32_t x = tiles_touched[vals0[i]];
+    sorted_offsets[i] = x;  // parked; rewritten below
+    mine += x;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+  if (lane == 0) s_scan[warp] = mine;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < VS_WARPS; w++) t += s_scan[w];
+    s_total = t;
+  }
+  __syncthreads();
+  cluster.sync();
+  uint32_t run = v ? offsets[(size_t)v * P - 1] : 0u;  // pairs of the views before mine (preprocess's scan)
+  for (uint32_t r = 0; r < rank; r++) run += *cluster.map_shared_rank(&s_total, r);
+  for (uint32_t sub = cb; sub < ce; sub += VS_THREADS * 4) {
+    uint32_t x[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t j = sub + tid * 4 + k;
+      x[k] = j < ce ? sorted_offsets[j] : 0u;
+      sum += x[k];
+    }
+    const uint32_t excl = vs_exclusive_scan_256(sum, s_scan);
+    uint32_t acc = run + excl;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      const uint32_t j = sub + tid * 4 + k;
+      acc += x[k];
+      if (j < ce) sorted_offsets[j] = acc;
+    }
+    // total of this sub-tile: the last thread's inclusive value
+    __syncthreads();
+    if (tid == VS_THREADS - 1) s_scan[0] = excl + sum;
+    __syncthreads();
+    run += s_scan[0];
+  }
+  cluster.sync();  // no CTA leaves while a peer may still read its shared memory
+}
+
+// keys0 / vals0: where the preprocess compacted the visible Gaussians AND where the sorted result lands (4 passes);
+// keys1 / vals1: the other half of the ping-pong.
+int visible_sort(cudaStream_t st, const OcrfShape* sh, const uint32_t* view_start, uint64_t* keys0, uint32_t* vals0,
+                 uint64_t* keys1, uint32_t* vals1, const uint32_t* tiles_touched, const uint32_t* offsets,
+                 uint32_t* sorted_offsets) {
+  OCRF_LAUNCH(visible_sort_kernel, dim3(VS_CLUSTER, sh->V), dim3(VS_THREADS), 0, st, sh->P, view_start, keys0, vals0, keys1,
+              vals1, tiles_touched, offsets, sorted_offsets);
+  return 0;
+}
+
+}  // namespace ocrf
