@@ -203,6 +203,25 @@ int ocrf_opacity_mask_backward(void* stream, int32_t B, int32_t C, int32_t H, in
                                const float* w, const float* mask, const float* stats, const float* g_out,
                                float* g_x, float* g_w, float* g_opacity_bev, float* scratch);
 
+/* Stage 5a: the height-aware opacity lift proper (view_transformer_ocrf.py:1159-1161),
+ *   opacity_alpha = interpolate(DeformableAttention2D(interpolate(opacity, /6), interpolate(alpha_lidar, /6)), full) + opacity
+ * with DeformableAttention2D of mmdet3d/ops/cross_attention_2d.py:93-220 in OcRFDet's configuration
+ * (view_transformer_ocrf.py:639-648: dim 13, one head of 8, one offset group, 6x6 stride-4 offset conv, scale 4).
+ * opacity, alpha, out [B,13,H,W] (bilinear resizes with align_corners=True, coarse size (H/6, W/6));
+ * params: the module's OCRF_HOA_ATTN_PARAMS parameters concatenated in named_parameters() order
+ *   (to_offsets.0.weight, .0.bias, to_offsets.2.weight, rel_pos_bias.mlp.{0.0,1.0,2}.{weight,bias}, to_q, to_k, to_v,
+ *    to_out.weight, to_out.bias);
+ * keep (may be NULL): dropout keep-mask [B, (H/6)(W/6), keys] already divided by 1 - p (the reference's p = 0.1);
+ * workspace: ocrf_hoa_lift_workspace_floats(...) floats, shared by forward and backward (no state is carried).
+ * Backward writes g_opacity, g_alpha [B,13,H,W] and ACCUMULATES g_params (zero it first). */
+#define OCRF_HOA_ATTN_PARAMS 766
+size_t ocrf_hoa_lift_workspace_floats(int32_t B, int32_t dim, int32_t H, int32_t W);
+int ocrf_hoa_lift_forward(void* stream, int32_t B, int32_t dim, int32_t H, int32_t W, const float* opacity,
+                          const float* alpha, const float* params, const float* keep, float* out, float* workspace);
+int ocrf_hoa_lift_backward(void* stream, int32_t B, int32_t dim, int32_t H, int32_t W, const float* opacity,
+                           const float* alpha, const float* params, const float* keep, const float* g_out,
+                           float* g_opacity, float* g_alpha, float* g_params, float* workspace);
+
 /* Stage 0 (scope row a12, "next" f-1): OcRF Gaussian construction, the four MLP heads of
  * view_transformer_ocrf.py:272-320 evaluated at :1130-1133, in one pass over the voxel features.
  * feat [n,F] (F <= 125), rgb [n,3].  Packed parameters (input-major first layer):
