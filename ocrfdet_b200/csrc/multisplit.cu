@@ -323,10 +323,11 @@ __global__ void __launch_bounds__(MS_THREADS) ms_scatter_kernel(
   const uint32_t cb = (uint32_t)cb64, ce = (uint32_t)min((uint64_t)pe, cb64 + Q);
   const int tiles = ceil_div(sh.W, TILE) * ceil_div(sh.H, TILE);
   uint32_t* s_base = s_dyn;
-  uint16_t* s_wc = reinterpret_cast<uint16_t*>(s_dyn + 2 * tiles);
-  uint16_t* s_rt = s_wc + (size_t)MS_WARPS * 2 * tiles;  // [2][tiles] totals of the current round
-  uint16_t* my_full = s_wc + (size_t)warp * 2 * tiles;
-  uint16_t* my_kept = my_full + tiles;
+  // per-warp counts / prefixes of the round, ONE word per (warp, tile): low half = pairs, high half = kept pairs
+  // (both are updated by the same lane with one load and one store)
+  uint32_t* s_wc = s_dyn + 2 * tiles;                                    // [MS_WARPS][tiles]
+  uint16_t* s_rt = reinterpret_cast<uint16_t*>(s_wc + (size_t)MS_WARPS * tiles);  // [2][tiles] totals of the current round
+  uint32_t* my_cnt = s_wc + (size_t)warp * tiles;
   const size_t row = ((size_t)v * chunks_max + c) * tiles;
   const uint32_t* toff = tile_offset + (size_t)v * tiles;
   for (int t = tid; t < tiles; t += MS_THREADS) {
@@ -340,33 +341,43 @@ __global__ void __launch_bounds__(MS_THREADS) ms_scatter_kernel(
   for (uint32_t rb = cb; rb < ce; rb += MS_ROUND) {
     const uint32_t n_items = min((uint32_t)MS_ROUND, ce - rb);
     __syncthreads();
-    for (int i = tid; i < MS_WARPS * tiles; i += MS_THREADS) reinterpret_cast<uint32_t*>(s_wc)[i] = 0;  // 2 u16 per word
+    for (int i = tid; i < MS_WARPS * tiles; i += MS_THREADS) s_wc[i] = 0;
     __syncthreads();
     // rank inside the warp, one row of 32 consecutive pairs at a time (stable)
     uint32_t st[MS_ITEMS];  // tile | rank_full << 13 | rank_kept << 22 | keep << 31   (ranks < 512 per warp-round)
     uint32_t gi[MS_ITEMS];
+    // groups of four rows: the four (independent) peer matches are issued together, then the four dependent
+    // load-add-store steps on the warp's counters follow
 #pragma unroll
-    for (int i = 0; i < MS_ITEMS; i++) {
-      const uint32_t pos = warp * (32 * MS_ITEMS) + i * 32 + lane;
-      const bool valid = pos < n_items;
-      uint2 it = make_uint2(0xffffu, 0u);
-      if (valid) it = items[rb + pos];
-      const uint32_t t = it.x & 0x1fffu;
-      const bool keep = valid && (it.x & MS_KEEP);
-      gi[i] = it.y;
-      const uint32_t peers = __match_any_sync(0xffffffffu, valid ? t : 0xffff0000u | lane);
-      const uint32_t kpeers = __match_any_sync(0xffffffffu, keep ? t : 0xffff0000u | lane);
-      uint32_t bf = 0, bk = 0;
-      if (valid) {
-        bf = my_full[t];
-        bk = my_kept[t];
+    for (int i0 = 0; i0 < MS_ITEMS; i0 += 4) {
+      uint32_t tt[4], peers[4], kpeers[4];
+      bool vld[4], kp[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const uint32_t pos = warp * (32 * MS_ITEMS) + (i0 + u) * 32 + lane;
+        vld[u] = pos < n_items;
+        uint2 it = make_uint2(0xffffu, 0u);
+        if (vld[u]) it = items[rb + pos];
+        tt[u] = it.x & 0x1fffu;
+        kp[u] = vld[u] && (it.x & MS_KEEP);
+        gi[i0 + u] = it.y;
       }
-      __syncwarp();
-      if (valid && (peers & lt_mask) == 0) my_full[t] = (uint16_t)(bf + __popc(peers));
-      if (keep && (kpeers & lt_mask) == 0) my_kept[t] = (uint16_t)(bk + __popc(kpeers));
-      __syncwarp();
-      const uint32_t rf = bf + __popc(peers & lt_mask), rk = bk + __popc(kpeers & lt_mask);
-      st[i] = valid ? (t | (rf << 13) | (rk << 22) | (keep ? MS_KEEP : 0u)) : 0xffffffffu;
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        peers[u] = __match_any_sync(0xffffffffu, vld[u] ? tt[u] : 0xffff0000u | lane);
+        // the kept pairs of my tile among my peers: no second match, the keep flags of the warp are one vote away
+        kpeers[u] = peers[u] & __ballot_sync(0xffffffffu, kp[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        uint32_t b4 = 0;
+        if (vld[u]) b4 = my_cnt[tt[u]];
+        __syncwarp();
+        if (vld[u] && (peers[u] & lt_mask) == 0) my_cnt[tt[u]] = b4 + __popc(peers[u]) + (__popc(kpeers[u]) << 16);
+        __syncwarp();
+        const uint32_t rf = (b4 & 0xffffu) + __popc(peers[u] & lt_mask), rk = (b4 >> 16) + __popc(kpeers[u] & lt_mask);
+        st[i0 + u] = vld[u] ? (tt[u] | (rf << 13) | (rk << 22) | (kp[u] ? MS_KEEP : 0u)) : 0xffffffffu;
+      }
     }
     __syncthreads();
     // per tile: exclusive prefix over the warps (stored back into the per-warp slots) and the round totals
@@ -374,12 +385,11 @@ __global__ void __launch_bounds__(MS_THREADS) ms_scatter_kernel(
       uint32_t rf = 0, rk = 0;
 #pragma unroll
       for (int w = 0; w < MS_WARPS; w++) {
-        uint16_t* f = s_wc + (size_t)w * 2 * tiles;
-        const uint32_t xf = f[t], xk = f[tiles + t];
-        f[t] = (uint16_t)rf;
-        f[tiles + t] = (uint16_t)rk;
-        rf += xf;
-        rk += xk;
+        uint32_t* f = s_wc + (size_t)w * tiles;
+        const uint32_t x = f[t];
+        f[t] = rf | (rk << 16);
+        rf += x & 0xffffu;
+        rk += x >> 16;
       }
       s_rt[t] = (uint16_t)rf;
       s_rt[tiles + t] = (uint16_t)rk;
@@ -391,8 +401,9 @@ __global__ void __launch_bounds__(MS_THREADS) ms_scatter_kernel(
       const uint32_t s = st[i];
       if (s == 0xffffffffu || !(s & MS_KEEP)) continue;
       const uint32_t t = s & 0x1fffu, rf = (s >> 13) & 0x1ffu, rk = (s >> 22) & 0x1ffu;
-      const uint32_t orig = s_base[t] + my_full[t] + rf + 1;          // 1-based position in the tile's full list
-      const uint32_t dst = s_base[tiles + t] + my_kept[t] + rk;       // record slot
+      const uint32_t wpre = my_cnt[t];                                   // this warp's prefix inside the round
+      const uint32_t orig = s_base[t] + (wpre & 0xffffu) + rf + 1;        // 1-based position in the tile's full list
+      const uint32_t dst = s_base[tiles + t] + (wpre >> 16) + rk;         // record slot
       const uint32_t g = gi[i];
       const float2 p = xy[g];
       const float4 co = conic_opacity[g];
@@ -440,7 +451,7 @@ int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity,
   uint32_t* tot_kept = tot_full + (size_t)sh->V * tiles_v;
   uint32_t* tile_offset = tot_kept + (size_t)sh->V * tiles_v;
   const size_t smem_a = (size_t)2 * tiles_v * 4 + MS_ROUND * 2;
-  const size_t smem_c = (size_t)2 * tiles_v * 4 + (size_t)(MS_WARPS + 1) * 2 * tiles_v * 2;
+  const size_t smem_c = (size_t)2 * tiles_v * 4 + (size_t)MS_WARPS * tiles_v * 4 + (size_t)2 * tiles_v * 2;
   static unsigned long long attr_a = 0, attr_c = 0;  // per-device bit masks
   cudaError_t ae = ensure_dynamic_smem(ms_count_kernel, 100 * 1024, attr_a);
   if (ae != cudaSuccess) return (int)ae;

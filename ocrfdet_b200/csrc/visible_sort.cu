@@ -7,15 +7,17 @@
 //
 // One thread-block CLUSTER of 8 CTAs owns a view (the views are already segments of the compacted key array, so the
 // view bits need no pass).  Per 8-bit digit place, CTA r of the cluster
-//   (1) counts the digits of ITS eighth of the segment into shared memory,
-//   (2) after a cluster barrier reads the eight histograms through distributed shared memory and derives, per digit,
-//       the global base + the keys of lower-ranked CTAs: the stable destination of its own keys,
-//   (3) ranks its keys (warp match_any multi-split, the ranking of radix_sort.cu) and writes them to the other half
-//       of the ping-pong (L2-resident),
-// and a second cluster barrier ends the pass.  Four passes cover the 32 depth bits; no look-back chain, no global
-// histogram, one launch.  The epilogue replaces scan_sorted_tiles_kernel: the inclusive scan of tiles_touched in sorted
-// order (where every Gaussian's pairs sit in the pair stream), the cluster exchanging eight partial sums.
-// Any segment size works (a CTA loops over sub-tiles of 4096 keys).
+//   (1) reads the eight digit histograms of the pass through distributed shared memory and derives, per digit, the
+//       global base + the keys of lower-ranked CTAs: the stable destination of its own keys,
+//   (2) ranks its eighth of the segment (warp match_any multi-split, the ranking of radix_sort.cu; 1024 threads x 4
+//       keys, so the serial part of the ranking is four steps) and writes keys and values to the other half of the
+//       ping-pong (L2-resident),
+//   (3) and, with the same scatter, counts the NEXT pass's digit of every key it writes into the histogram of the CTA
+//       that will own the destination (a distributed-shared-memory reduction),
+// so ONE cluster barrier per pass orders both the data and the next histograms.  Four passes cover the 32 depth bits;
+// no look-back chain, no global histogram, one launch.  The epilogue replaces scan_sorted_tiles_kernel: the inclusive
+// scan of tiles_touched in sorted order (where every Gaussian's pairs sit in the pair stream), the cluster exchanging
+// eight partial sums.  Any segment size works (a CTA loops over sub-tiles of 4096 keys).
 #include <cooperative_groups.h>
 
 #include "common.cuh"
@@ -25,11 +27,12 @@ namespace cg = cooperative_groups;
 namespace ocrf {
 
 constexpr int VS_CLUSTER = 8;
-constexpr int VS_THREADS = 256;
+constexpr int VS_THREADS = 1024;
 constexpr int VS_WARPS = VS_THREADS / 32;
-constexpr int VS_ITEMS = 16;
+constexpr int VS_ITEMS = 4;
 constexpr int VS_SUBTILE = VS_THREADS * VS_ITEMS;
 
+// exclusive scan of one value per thread over the first 256 threads (8 warps); every thread of the CTA calls
 __device__ __forceinline__ uint32_t vs_exclusive_scan_256(uint32_t v, uint32_t* s_warp /*[8]*/) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint32_t incl = v;
@@ -39,13 +42,18 @@ __device__ __forceinline__ uint32_t vs_exclusive_scan_256(uint32_t v, uint32_t* 
     if (lane >= d) incl += t;
   }
   __syncthreads();  // s_warp may still be read from the previous use
-  if (lane == 31) s_warp[warp] = incl;
+  if (lane == 31 && warp < 8) s_warp[warp] = incl;
   __syncthreads();
   uint32_t off = 0;
 #pragma unroll
-  for (int w = 0; w < VS_WARPS; w++)
+  for (int w = 0; w < 8; w++)
     if (w < warp) off += s_warp[w];
   return off + incl - v;
+}
+
+__device__ __forceinline__ void dsmem_add_u32(uint32_t* remote, uint32_t v) {
+  // remote: a generic address returned by cluster.map_shared_rank (shared::cluster window)
+  atomicAdd(remote, v);
 }
 
 __global__ void __cluster_dims__(VS_CLUSTER, 1, 1) __launch_bounds__(VS_THREADS) visible_sort_kernel(
@@ -54,9 +62,12 @@ __global__ void __cluster_dims__(VS_CLUSTER, 1, 1) __launch_bounds__(VS_THREADS)
     uint32_t* __restrict__ sorted_offsets) {
   pdl_enter();
   cg::cluster_group cluster = cg::this_cluster();
-  __shared__ uint32_t s_hist[256];                 // digit counts of my part of the segment (read by the other CTAs)
+  // digit counts of MY part of the segment, three buffers in rotation: pass p reads [p % 3] (all CTAs, remotely), fills
+  // [(p + 1) % 3] for the next pass (remote reductions of whoever writes into my part) and clears [(p + 2) % 3], which
+  // was last read before the previous cluster barrier and is next written after the coming one
+  __shared__ uint32_t s_hist[3][256];
   __shared__ uint32_t s_base[256];                 // running destination of my next key of every digit
-  __shared__ uint32_t s_warp_hist[VS_WARPS][256];
+  __shared__ uint16_t s_warp_hist[VS_WARPS][256];  // per-warp digit counts of the current sub-tile (<= 128 each)
   __shared__ uint32_t s_scan[VS_WARPS];
   __shared__ uint32_t s_total;
 
@@ -64,9 +75,22 @@ __global__ void __cluster_dims__(VS_CLUSTER, 1, 1) __launch_bounds__(VS_THREADS)
   const uint32_t rank = cluster.block_rank();
   const int v = blockIdx.y;
   const uint32_t seg_b = view_start[v], n = view_start[v + 1] - seg_b;
-  const uint32_t per = (n + VS_CLUSTER - 1) / VS_CLUSTER;
+  const uint32_t per = max(1u, (n + VS_CLUSTER - 1) / VS_CLUSTER);
   const uint32_t cb = seg_b + min(n, rank * per), ce = seg_b + min(n, (rank + 1) * per);
   const uint32_t lt_mask = (1u << lane) - 1;
+
+  // histogram of the first digit place over my part
+  if (tid < 256) { s_hist[0][tid] = 0; s_hist[1][tid] = 0; s_hist[2][tid] = 0; }
+  __syncthreads();
+  for (uint32_t base = cb; base < ce; base += VS_THREADS) {  // (uniform trip count: the match below is warp-wide)
+    const uint32_t i = base + tid;
+    const bool valid = i < ce;
+    const uint32_t d = valid ? ((uint32_t)keys0[i] & 255u) : 0x100u + lane;
+    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+    if (valid && (peers & lt_mask) == 0) atomicAdd(&s_hist[0][d], __popc(peers));
+  }
+  __syncthreads();
+  cluster.sync();
 
   for (int pass = 0; pass < 4; pass++) {
     const uint64_t* src_k = (pass & 1) ? keys1 : keys0;
@@ -74,57 +98,62 @@ __global__ void __cluster_dims__(VS_CLUSTER, 1, 1) __launch_bounds__(VS_THREADS)
     uint64_t* dst_k = (pass & 1) ? keys0 : keys1;
     uint32_t* dst_v = (pass & 1) ? vals0 : vals1;
     const int shift = 8 * pass;
-    // (1) digit counts of my part
-    s_hist[tid] = 0;
-    __syncthreads();
-    for (uint32_t i = cb + tid; i < ce; i += VS_THREADS) atomicAdd(&s_hist[(uint32_t)(src_k[i] >> shift) & 255u], 1u);
-    __syncthreads();
-    cluster.sync();
-    // (2) thread d: keys with digit d in the whole segment, and in the parts before mine
+    uint32_t* hist_now = s_hist[pass % 3];
+    uint32_t* hist_next = s_hist[(pass + 1) % 3];
+    if (tid < 256) s_hist[(pass + 2) % 3][tid] = 0;
+    // (1) thread d < 256: keys with digit d in the whole segment, and in the parts before mine
     uint32_t total = 0, before = 0;
+    if (tid < 256) {
 #pragma unroll
-    for (uint32_t r = 0; r < VS_CLUSTER; r++) {
-      const uint32_t c = *cluster.map_shared_rank(&s_hist[tid], r);
-      total += c;
-      before += r < rank ? c : 0u;
+      for (uint32_t r = 0; r < VS_CLUSTER; r++) {
+        const uint32_t c = *cluster.map_shared_rank(&hist_now[tid], r);
+        total += c;
+        before += r < rank ? c : 0u;
+      }
     }
     const uint32_t excl = vs_exclusive_scan_256(total, s_scan);
-    s_base[tid] = seg_b + excl + before;
-    // (3) stable ranks + scatter, one sub-tile of 4096 keys at a time
+    if (tid < 256) s_base[tid] = seg_b + excl + before;
+    // (2) stable ranks + scatter, one sub-tile of 4096 keys at a time
     for (uint32_t sub = cb; sub < ce; sub += VS_SUBTILE) {
       const uint32_t n_valid = min((uint32_t)VS_SUBTILE, ce - sub);
-#pragma unroll
-      for (int w = 0; w < VS_WARPS; w++) s_warp_hist[w][tid] = 0;
-      __syncthreads();  // (also orders s_base of the previous sub-tile / of step (2))
+      for (int e = tid; e < VS_WARPS * 128; e += VS_THREADS) reinterpret_cast<uint32_t*>(s_warp_hist)[e] = 0u;
       uint64_t key[VS_ITEMS];
-      uint32_t rk[VS_ITEMS];
-      uint32_t* my_hist = s_warp_hist[warp];
+      uint32_t val[VS_ITEMS], peers[VS_ITEMS], rk[VS_ITEMS];
+      uint16_t* my_hist = s_warp_hist[warp];
       const uint32_t warp_base = warp * (32 * VS_ITEMS);
 #pragma unroll
       for (int i = 0; i < VS_ITEMS; i++) {
         const uint32_t loc = warp_base + i * 32 + lane;  // index order inside the warp: the ranking below is stable
-        key[i] = loc < n_valid ? src_k[sub + loc] : 0ull;
+        const bool valid = loc < n_valid;
+        key[i] = valid ? src_k[sub + loc] : 0ull;
+        val[i] = valid ? src_v[sub + loc] : 0u;
       }
 #pragma unroll
+      for (int i = 0; i < VS_ITEMS; i++) {  // the peer masks are independent of each other: issue them together
+        const bool valid = warp_base + i * 32 + lane < n_valid;
+        peers[i] = __match_any_sync(0xffffffffu, valid ? ((uint32_t)(key[i] >> shift) & 255u) : 0x100u + lane);
+      }
+      __syncthreads();  // s_warp_hist is zero; s_base of the previous sub-tile / of step (1) is in place
+#pragma unroll
       for (int i = 0; i < VS_ITEMS; i++) {
-        const uint32_t loc = warp_base + i * 32 + lane;
-        const bool valid = loc < n_valid;
+        const bool valid = warp_base + i * 32 + lane < n_valid;
         const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
-        const uint32_t peers = __match_any_sync(0xffffffffu, valid ? d : 0x100u + lane);
         uint32_t b4 = 0;
         if (valid) b4 = my_hist[d];
         __syncwarp();
-        if (valid && (peers & lt_mask) == 0) my_hist[d] = b4 + __popc(peers);
+        if (valid && (peers[i] & lt_mask) == 0) my_hist[d] = (uint16_t)(b4 + __popc(peers[i]));
         __syncwarp();
-        rk[i] = b4 + __popc(peers & lt_mask);
+        rk[i] = b4 + __popc(peers[i] & lt_mask);
       }
       __syncthreads();
       uint32_t tile_count = 0;
-#pragma unroll
-      for (int w = 0; w < VS_WARPS; w++) {  // thread d: exclusive prefix over the warps
-        const uint32_t c = s_warp_hist[w][tid];
-        s_warp_hist[w][tid] = tile_count;
-        tile_count += c;
+      if (tid < 256) {
+#pragma unroll 8
+        for (int w = 0; w < VS_WARPS; w++) {  // thread d: exclusive prefix over the warps
+          const uint32_t c = s_warp_hist[w][tid];
+          s_warp_hist[w][tid] = (uint16_t)tile_count;
+          tile_count += c;
+        }
       }
       __syncthreads();
 #pragma unroll
@@ -134,14 +163,18 @@ __global__ void __cluster_dims__(VS_CLUSTER, 1, 1) __launch_bounds__(VS_THREADS)
           const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
           const uint32_t pos = s_base[d] + my_hist[d] + rk[i];
           dst_k[pos] = key[i];
-          dst_v[pos] = src_v[sub + loc];
+          dst_v[pos] = val[i];
+          if (pass < 3) {  // (3) the next pass's digit of this key, counted where the key now lives
+            const uint32_t owner = min((pos - seg_b) / per, (uint32_t)VS_CLUSTER - 1);
+            dsmem_add_u32(cluster.map_shared_rank(&hist_next[(uint32_t)(key[i] >> (shift + 8)) & 255u], owner), 1u);
+          }
         }
       }
       __syncthreads();
-      s_base[tid] += tile_count;
+      if (tid < 256) s_base[tid] += tile_count;
     }
     __threadfence();
-    cluster.sync();  // the pass is complete and visible to the whole cluster; s_hist may be reused
+    cluster.sync();  // the pass and the next histograms are complete and visible to the whole cluster
   }
 
   // ---- epilogue: inclusive scan of tiles_touched over the sorted order (four passes end in keys0 / vals0) ----
@@ -165,27 +198,27 @@ __global__ void __cluster_dims__(VS_CLUSTER, 1, 1) __launch_bounds__(VS_THREADS)
   cluster.sync();
   uint32_t run = v ? offsets[(size_t)v * P - 1] : 0u;  // pairs of the views before mine (preprocess's scan)
   for (uint32_t r = 0; r < rank; r++) run += *cluster.map_shared_rank(&s_total, r);
-  for (uint32_t sub = cb; sub < ce; sub += VS_THREADS * 4) {
-    uint32_t x[4], sum = 0;
+  for (uint32_t sub = cb; sub < ce; sub += VS_THREADS) {  // one key per thread, a CTA-wide scan per 1024 keys
+    const uint32_t j = sub + tid;
+    const uint32_t x = j < ce ? sorted_offsets[j] : 0u;
+    uint32_t incl = x;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const uint32_t j = sub + tid * 4 + k;
-      x[k] = j < ce ? sorted_offsets[j] : 0u;
-      sum += x[k];
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
     }
-    const uint32_t excl = vs_exclusive_scan_256(sum, s_scan);
-    uint32_t acc = run + excl;
-#pragma unroll
-    for (int k = 0; k < 4; k++) {
-      const uint32_t j = sub + tid * 4 + k;
-      acc += x[k];
-      if (j < ce) sorted_offsets[j] = acc;
+    __syncthreads();
+    if (lane == 31) s_scan[warp] = incl;
+    __syncthreads();
+    uint32_t off = 0, tot = 0;
+#pragma unroll 8
+    for (int w = 0; w < VS_WARPS; w++) {
+      const uint32_t c = s_scan[w];
+      off += w < warp ? c : 0u;
+      tot += c;
     }
-    // total of this sub-tile: the last thread's inclusive value
-    __syncthreads();
-    if (tid == VS_THREADS - 1) s_scan[0] = excl + sum;
-    __syncthreads();
-    run += s_scan[0];
+    if (j < ce) sorted_offsets[j] = run + off + incl;
+    run += tot;
   }
   cluster.sync();  // no CTA leaves while a peer may still read its shared memory
 }

@@ -12,7 +12,7 @@ from tests import util
 from tests.golden.make_golden import scene
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz"))
-                if not os.path.basename(p).startswith(("heads_", "bevpool_", "voxelcolor_")))
+                if not os.path.basename(p).startswith(("heads_", "bevpool_", "voxelcolor_", "hoa_")))
 GOLDEN_HEADS = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "heads_*.npz")))
 
 
