@@ -222,6 +222,24 @@ int ocrf_hoa_lift_backward(void* stream, int32_t B, int32_t dim, int32_t H, int3
                            const float* alpha, const float* params, const float* keep, const float* g_out,
                            float* g_opacity, float* g_alpha, float* g_params, float* workspace);
 
+/* Stage 5b: OpacityVoxelToBEVConverter + HeightAttention (view_transformer_ocrf.py:421-518, called at :1196):
+ * x [B,13,S,S] (the lifted opacity), position [1 or B,4,S,S] -> out [B,1,S,S] (S % 4 == 0).
+ * params: the module's OCRF_HOA_CONVERTER_PARAMS parameters concatenated in named_parameters() order.
+ * train != 0: batch-norm batch statistics (biased variance); batch_stats (may be NULL) receives, per block and channel,
+ *   [5][16][2] = (sum, sum of squares) over B*h*w, from which the caller updates its running statistics;
+ * train == 0: running_mean / running_var [5][16] (block-major, padded to 16 channels).
+ * workspace: ocrf_hoa_converter_workspace_floats(B, S) floats; the backward needs the workspace of ITS forward, untouched.
+ * Backward writes g_x [B,13,S,S] and g_position, and ACCUMULATES g_params (zero it first). */
+#define OCRF_HOA_CONVERTER_PARAMS 1847
+size_t ocrf_hoa_converter_workspace_floats(int32_t B, int32_t S);
+int ocrf_hoa_converter_forward(void* stream, int32_t B, int32_t S, int32_t train, const float* x, const float* position,
+                               int32_t position_batched, const float* params, const float* running_mean,
+                               const float* running_var, float* out, float* batch_stats, float* workspace);
+int ocrf_hoa_converter_backward(void* stream, int32_t B, int32_t S, int32_t train, const float* x, const float* position,
+                                int32_t position_batched, const float* params, const float* running_mean,
+                                const float* running_var, const float* g_out, float* g_x, float* g_position,
+                                float* g_params, float* workspace);
+
 /* Stage 0 (scope row a12, "next" f-1): OcRF Gaussian construction, the four MLP heads of
  * view_transformer_ocrf.py:272-320 evaluated at :1130-1133, in one pass over the voxel features.
  * feat [n,F] (F <= 125), rgb [n,3].  Packed parameters (input-major first layer):

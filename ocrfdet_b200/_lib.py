@@ -25,6 +25,7 @@ EXPORTS = [
     "ocrf_sort_pairs", "ocrf_opacity_mask_forward", "ocrf_opacity_mask_backward",
     "ocrf_gaussian_heads_forward", "ocrf_gaussian_heads_backward", "ocrf_gaussian_heads_backward_workspace_bytes", "ocrf_clear_gradients",
     "ocrf_hoa_lift_workspace_floats", "ocrf_hoa_lift_forward", "ocrf_hoa_lift_backward",
+    "ocrf_hoa_converter_workspace_floats", "ocrf_hoa_converter_forward", "ocrf_hoa_converter_backward",
     "ocrf_color_voxels", "ocrf_retain_valid_pixels", "ocrf_bev_pool_forward", "ocrf_bev_pool_backward_workspace_bytes", "ocrf_bev_pool_backward",
 ]
 
@@ -93,6 +94,10 @@ def lib():
     L.ocrf_hoa_lift_workspace_floats.argtypes = [i32, i32, i32, i32]
     L.ocrf_hoa_lift_forward.argtypes = [vp, i32, i32, i32, i32] + [vp] * 6
     L.ocrf_hoa_lift_backward.argtypes = [vp, i32, i32, i32, i32] + [vp] * 9
+    L.ocrf_hoa_converter_workspace_floats.restype = C.c_size_t
+    L.ocrf_hoa_converter_workspace_floats.argtypes = [i32, i32]
+    L.ocrf_hoa_converter_forward.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp]
+    L.ocrf_hoa_converter_backward.argtypes = [vp, i32, i32, i32, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     L.ocrf_color_voxels.argtypes = [vp, i32, i32, C.c_int64, i32, i32, i32, vp, vp, vp, f32, vp, vp]
     L.ocrf_retain_valid_pixels.argtypes = [vp, i32, C.c_int64, i32, i32, i32, vp, vp, vp, f32, vp]
     L.ocrf_bev_pool_forward.argtypes = [vp, i32, i32] + [vp] * 8

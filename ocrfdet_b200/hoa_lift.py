@@ -175,3 +175,123 @@ def opacity_alpha_lift(opacity, alpha_lidar, attention, keep=None):
     if keep is not None:
         keep = keep.float().contiguous()
     return _LiftFn.apply(opacity, alpha_lidar, attention.packed, keep)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Stage 5b: OpacityVoxelToBEVConverter (+ HeightAttention), view_transformer_ocrf.py:421-518
+# ---------------------------------------------------------------------------------------------------------------------
+BLOCKS = (("encoder1", 13, 4), ("encoder2", 4, 8), ("bottleneck", 8, 16), ("decoder2", 16, 8), ("decoder1", 8, 4))
+_GATE_OF = {"encoder1": "ca1", "encoder2": "ca2", "bottleneck": "ca_bottleneck", "decoder2": "ca_dec2", "decoder1": "ca_dec1"}
+_UPCONV_BEFORE = {"decoder2": ("upconv2", 16, 8), "decoder1": ("upconv1", 8, 4)}
+
+
+def _converter_modules():
+    """The reference module tree, layer by layer, in named_parameters() order: [(prefix, nn.Module)]."""
+    mods = []
+    for name, cin, cout in BLOCKS:
+        if name in _UPCONV_BEFORE:
+            up, a, b = _UPCONV_BEFORE[name]
+            mods.append((up, nn.ConvTranspose2d(a, b, kernel_size=2, stride=2)))
+        mods.append((name + ".0", nn.Conv2d(cin, cin, kernel_size=3, padding=1, groups=cin)))
+        mods.append((name + ".1", nn.Conv2d(cin, cout, kernel_size=1)))
+        mods.append((name + ".2", nn.BatchNorm2d(cout)))
+        cs = cout // 4
+        for s in range(1, 5):
+            mods.append(("%s.conv%d.0" % (_GATE_OF[name], s), nn.Conv2d(cs, cs, 1, bias=False)))
+            mods.append(("%s.conv%d.2" % (_GATE_OF[name], s), nn.Conv2d(cs, cs, 1, bias=False)))
+    mods.append(("output_conv", nn.Conv2d(4, 1, kernel_size=1)))
+    return mods
+
+
+def _converter_layout_and_init():
+    layout, init = OrderedDict(), OrderedDict()
+    for prefix, m in _converter_modules():
+        for n, p in m.named_parameters():
+            layout[prefix + "." + n] = tuple(p.shape)
+            init[prefix + "." + n] = p.data
+    return layout, init
+
+
+CONVERTER_PARAMS, _ = _converter_layout_and_init()
+CONVERTER_TOTAL = 1847
+BN_MOMENTUM = 0.1
+
+
+class _ConverterFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, position, packed, run_mean, run_var, train):
+        L = _lib.lib()
+        if not (x.is_cuda and position.is_cuda and packed.is_cuda):
+            raise _lib.OcrfError("OpacityVoxelToBEVConverter: tensors must live on a CUDA device (there is no CPU path)")
+        x, position, packed = x.float().contiguous(), position.float().contiguous(), packed.float().contiguous()
+        B, C, S, S2 = x.shape
+        if C != 13 or S != S2 or S % 4 or position.shape[1:] != (4, S, S) or position.shape[0] not in (1, B):
+            raise _lib.OcrfError("OpacityVoxelToBEVConverter: x must be [B,13,S,S] (S % 4 == 0), position [1 or B,4,S,S]")
+        pos_batched = int(position.shape[0] == B and B > 1)
+        ws = torch.empty(L.ocrf_hoa_converter_workspace_floats(B, S), dtype=torch.float32, device=x.device)
+        out = torch.empty((B, 1, S, S), dtype=torch.float32, device=x.device)
+        stats = torch.empty((5, 16, 2), dtype=torch.float32, device=x.device) if train else None
+        _lib.check(L.ocrf_hoa_converter_forward(_lib.current_stream(), B, S, int(train), _lib.ptr(x), _lib.ptr(position),
+                                                pos_batched, _lib.ptr(packed), _lib.ptr(run_mean), _lib.ptr(run_var),
+                                                _lib.ptr(out), _lib.ptr(stats), _lib.ptr(ws)), "ocrf_hoa_converter_forward")
+        ctx.save_for_backward(x, position, packed, run_mean, run_var, ws)
+        ctx.train, ctx.pos_batched = bool(train), pos_batched
+        ctx.mark_non_differentiable(*([stats] if stats is not None else []))
+        return (out, stats) if stats is not None else (out, None)
+
+    @staticmethod
+    def backward(ctx, g_out, _g_stats):
+        L = _lib.lib()
+        x, position, packed, run_mean, run_var, ws = ctx.saved_tensors
+        B, _, S, _ = x.shape
+        g_out = g_out.float().contiguous()
+        g_x, g_pos = torch.empty_like(x), torch.empty_like(position)
+        g_packed = torch.zeros_like(packed)
+        _lib.check(L.ocrf_hoa_converter_backward(_lib.current_stream(), B, S, int(ctx.train), _lib.ptr(x),
+                                                 _lib.ptr(position), ctx.pos_batched, _lib.ptr(packed), _lib.ptr(run_mean),
+                                                 _lib.ptr(run_var), _lib.ptr(g_out), _lib.ptr(g_x), _lib.ptr(g_pos),
+                                                 _lib.ptr(g_packed), _lib.ptr(ws)), "ocrf_hoa_converter_backward")
+        return g_x, g_pos, g_packed, None, None, None
+
+
+class OpacityVoxelToBEVConverter(_PackedModule):
+    """Drop-in for the reference class (view_transformer_ocrf.py:463-518): `forward(x, position)` with the lifted
+    opacity [B,13,S,S] and the learned BEV position encoding [1 or B,4,S,S] -> BEV opacity logit [B,1,S,S].
+    Same state_dict keys (parameters and batch-norm buffers), same default initialisation; batch norm follows
+    `self.training` (batch statistics + running-statistics update, or running statistics)."""
+    LAYOUT = CONVERTER_PARAMS
+
+    def __init__(self, input_channel=13):
+        super().__init__()
+        if input_channel != 13:
+            raise ValueError("the fused converter implements OcRFDet's 13 height planes")
+        _, init = _converter_layout_and_init()
+        self.packed = nn.Parameter(pack_parameters(init, CONVERTER_PARAMS))
+        for name, _cin, cout in BLOCKS:  # buffer names: "__" stands for "." (state_dict keys are the reference's)
+            self.register_buffer("%s__2__running_mean" % name, torch.zeros(cout))
+            self.register_buffer("%s__2__running_var" % name, torch.ones(cout))
+            self.register_buffer("%s__2__num_batches_tracked" % name, torch.tensor(0, dtype=torch.long))
+
+    def _running(self):
+        mean = torch.zeros((5, 16), dtype=torch.float32, device=self.packed.device)
+        var = torch.ones((5, 16), dtype=torch.float32, device=self.packed.device)
+        for i, (name, _cin, cout) in enumerate(BLOCKS):
+            mean[i, :cout] = getattr(self, "%s__2__running_mean" % name)
+            var[i, :cout] = getattr(self, "%s__2__running_var" % name)
+        return mean, var
+
+    def forward(self, x, position):
+        mean, var = self._running()
+        out, stats = _ConverterFn.apply(x, position, self.packed, mean, var, self.training)
+        if self.training:
+            with torch.no_grad():  # nn.BatchNorm2d: momentum 0.1, running_var from the unbiased batch variance
+                B, _, S, _ = x.shape
+                for i, (name, _cin, cout) in enumerate(BLOCKS):
+                    shift = (0, 1, 2, 1, 0)[i]
+                    n = float(B * (S >> shift) * (S >> shift))
+                    m = stats[i, :cout, 0] / n
+                    v = (stats[i, :cout, 1] / n - m * m).clamp_min(0.0) * (n / max(n - 1.0, 1.0))
+                    getattr(self, "%s__2__running_mean" % name).mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * m)
+                    getattr(self, "%s__2__running_var" % name).mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * v)
+                    getattr(self, "%s__2__num_batches_tracked" % name).add_(1)
+        return out

@@ -97,3 +97,66 @@ def test_lift_full_batch_against_torch_formulation():
     for b in (0, 3, 7):
         one = HL.opacity_alpha_lift(op[b:b + 1], al[b:b + 1], attn)
         assert torch.equal(one[0], full[b])
+
+
+def _converter_from(g):
+    m = HL.OpacityVoxelToBEVConverter(input_channel=13)
+    sd = {}
+    for k in g.files:
+        if k.startswith("p."):
+            sd[k[2:]] = torch.from_numpy(np.asarray(g[k]))
+        elif k.startswith("b0."):
+            sd[k[3:]] = torch.from_numpy(np.asarray(g[k]))
+    m.load_state_dict(sd)
+    return m.cuda()
+
+
+@pytest.mark.parametrize("name", ["hoa_converter_train_b2", "hoa_converter_eval_b1"])
+def test_converter_against_reference_golden_and_oracle(name):
+    g = np.load(os.path.join(GOLD, name + ".npz"))
+    io = hoa_inputs(int(g["seed"]), int(g["B"]), S=int(g["S"]))
+    params = {k[2:]: g[k] for k in g.files if k.startswith("p.")}
+    buffers = {k[3:]: g[k] for k in g.files if k.startswith("b0.")}
+    train = bool(int(g["train"]))
+    conv = _converter_from(g).train(train)
+    x_np = io["opacity"] + np.float32(0.25) * io["alpha"]
+    x = torch.from_numpy(x_np).cuda().requires_grad_(True)
+    pos = torch.from_numpy(io["position"]).cuda().requires_grad_(True)
+    out = conv(x, pos)
+    want, cache, stats = hoa.converter_forward(params, x_np, io["position"], train=train, buffers=buffers)
+    _close(out, want, 1e-5, "BEV opacity logit vs oracle")
+    _close(out, g["out"], 2e-5, "BEV opacity logit vs reference modules")
+    if train:  # running statistics were updated like nn.BatchNorm2d does
+        sd = conv.state_dict()
+        for k in ("encoder1.2.running_mean", "bottleneck.2.running_var", "decoder1.2.running_var"):
+            _close(sd[k], g["b1." + k], 1e-4, k)
+        assert int(sd["decoder2.2.num_batches_tracked"]) == int(g["b1.decoder2.2.num_batches_tracked"])
+    out.backward(torch.from_numpy(io["g_bev"]).cuda())
+    g_x, g_pos, G = hoa.converter_backward(params, cache, io["g_bev"])
+    _close(x.grad, g_x, 1e-4, "d/d x vs oracle")
+    _close(x.grad[..., ::STRIDE, ::STRIDE], g["g_x_sub"], 1e-4, "d/d x vs reference modules")
+    _close(pos.grad, g_pos, 1e-4, "d/d position vs oracle")
+    got = conv.reference_parameters(grads=True)
+    floor = 1e-2 * max(np.abs(g["g." + k]).max() for k in params)
+    for k in params:
+        _close(got[k], G[k], 3e-4, "d/d %s vs oracle" % k, floor)
+        _close(got[k], g["g." + k], 5e-4, "d/d %s vs reference modules" % k, floor)
+
+
+def test_converter_batch_of_eight_and_batched_position():
+    """The training shape (8 samples, 128 x 128): eval mode is sample-independent, so a batch equals its samples one by
+    one; a per-sample position tensor [B,4,S,S] gives per-sample position gradients."""
+    g = np.load(os.path.join(GOLD, "hoa_converter_eval_b1.npz"))
+    conv = _converter_from(g).eval()
+    io = hoa_inputs(21, 8, S=128)
+    x = torch.from_numpy(io["opacity"]).cuda()
+    pos = torch.from_numpy(io["position"]).cuda()
+    full = conv(x, pos)
+    for b in (0, 5):
+        assert torch.allclose(conv(x[b:b + 1], pos)[0], full[b], rtol=0, atol=1e-6)
+    posb = pos.expand(8, -1, -1, -1).contiguous().requires_grad_(True)
+    pos1 = pos.clone().requires_grad_(True)
+    gb = torch.from_numpy(io["g_bev"]).cuda()
+    conv(x, posb).backward(gb)
+    conv(x, pos1).backward(gb)
+    _close(posb.grad.sum(0, keepdim=True), pos1.grad.cpu().numpy(), 1e-5, "position gradient, batched vs shared")
