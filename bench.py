@@ -47,12 +47,107 @@ W, H, P, VIEWS, C = 704, 256, 100_000, 6, 3
 METRIC = "rendered camera views/sec (6x256x704 fwd+bwd)"
 
 
+# BASELINE.json configs beside the metric's own (config 2): samples x views, image, Gaussians per sample, channels,
+# voxel-grid refinement, samples per launch sequence
+WORKLOADS = {
+    "config2": None,
+    "config3": dict(S=8, views=6, W=704, H=256, P=100_000, C=3, bev=128, chunk=None,
+                    what="BASELINE config 3 on ONE GPU: 8 samples x 6 views 256x704, 100k Gaussians each, one call"),
+    "config4": dict(S=2, views=6, W=704, H=256, P=100_000, C=80, bev=128, chunk=None,
+                    what="BASELINE config 4: 2 frames x 6 views 256x704, 80-channel features + depth + opacity, 100k Gaussians"),
+    "config5": dict(S=8, views=6, W=1408, H=512, P=1_000_000, C=3, bev=277, chunk=1,
+                    what="BASELINE config 5: 8 samples x 6 views 512x1408, 1M Gaussians each, one sample per launch "
+                         "sequence (sample_chunk=1)"),
+}
+
+
+def run_workload(args, device):
+    """The other BASELINE configs on one GPU: forward + backward, CUDA-event timed, L2 flushed before each step."""
+    from ocrfdet_b200 import rasterizer as R
+    from ocrfdet_b200.scenes import ring_scene
+    w = WORKLOADS[args.workload]
+    S, V, C_ = w["S"], w["S"] * w["views"], w["C"]
+    gs, cams_all = [], []
+    for s_ in range(S):
+        g, cams = ring_scene(P=w["P"], seed=4321 + s_, width=w["W"], height=w["H"], channels=C_, n_views=w["views"],
+                             bev=w["bev"])
+        gs.append(g)
+        cams_all += cams
+    names = ("means3D", "scales", "rotations", "opacities", "colors")
+    dev = {k: torch.from_numpy(np.stack([g[k] for g in gs])).to(device).requires_grad_(True) for k in names}
+    cam_t = R.pack_camera_dicts(cams_all, device)
+    bg = torch.zeros(C_, device=device)
+    gen = torch.Generator(device=device).manual_seed(7)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)
+    cap = {"n": None}
+    stats = {}
+
+    def step(collect=False):
+        for k in names:
+            dev[k].grad = None
+        color, radii, depth, opac = R.render_batch(dev["means3D"], dev["opacities"], cam_t, w["H"], w["W"], bg,
+                                                   colors_precomp=dev["colors"], scales=dev["scales"],
+                                                   rotations=dev["rotations"], pair_capacity=cap["n"],
+                                                   sample_chunk=w["chunk"])
+        if collect:
+            stats["P_vis"] = int((radii > 0).sum())
+        # upstream gradients generated in place of a loss (not timed separately: two fills per step)
+        gcol = torch.empty_like(color).normal_(generator=gen)
+        gop = torch.empty_like(opac).normal_(generator=gen)
+        torch.autograd.backward([color, opac], [gcol, gop])
+
+    steps = min(args.steps, 10 if args.workload == "config5" else args.steps)
+    for _ in range(max(3, min(args.warmup, 3))):
+        step()
+    torch.cuda.synchronize()
+    R.KEEP_STATE = True
+    step(collect=True)
+    if w["chunk"] is None:
+        st = R.last_state()
+        stats["N_dup"] = int(st["num_pairs"])
+        cap["n"] = int(stats["N_dup"] * 1.3) + 4096  # sync-free sizing, like the headline workload
+    R.KEEP_STATE = False
+    R._LAST_STATE = None
+    step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(torch.cuda.current_device())
+    sampler.start()
+    torch.cuda.synchronize()
+    sampler.sm, sampler.bits = [], 0
+    evs = []
+    for _ in range(steps):
+        flush.fill_(1)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        step()
+        e1.record()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    R.check_overflow()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    mean_ms = sum(ms) / len(ms)
+    return {"metric": "rendered camera views/sec (fwd+bwd), %s" % args.workload, "value": V / (mean_ms / 1e3),
+            "unit": "views/s", "n_gpus": 1, "steps": steps, "warmup": 3, "ms_per_step": mean_ms,
+            "ms_per_step_median": ms[len(ms) // 2], "ms_per_render": mean_ms / V, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["what"], "views_per_step": V, "gaussians_per_sample": w["P"], "image": [w["H"], w["W"]],
+                       "channels": C_, "l2": "flushed (256 MB write) before each timed step",
+                       "sizing": "exact (one host read-back per launch sequence)" if cap["n"] is None
+                       else "sync-free: pair capacity %d" % cap["n"]},
+            "clocks": clocks, "workload_stats": stats, "peak_memory_GB": torch.cuda.max_memory_allocated() / 1e9,
+            "impl": "ours"}
+
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="config2", choices=sorted(WORKLOADS),
+                    help="config2 = the metric's workload (default; the only one with the full contract line); the others "
+                         "are BASELINE.json's remaining configs on ONE GPU, reported with the same timing hygiene")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="run a few untimed steps and exit (for ncu)")
     args = ap.parse_args()
@@ -625,6 +720,11 @@ def main():
         out = run_reference(args, rank, world, device)
         if out is not None:
             print(json.dumps(out))
+        return
+    if args.workload != "config2":
+        if world > 1:
+            raise SystemExit("--workload %s is a single-GPU measurement" % args.workload)
+        print(json.dumps(run_workload(args, device)))
         return
     if world > 1:
         dist.init_process_group("nccl", device_id=device)

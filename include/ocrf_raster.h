@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define OCRF_ABI_VERSION 3
+#define OCRF_ABI_VERSION 4
 
 #define OCRF_EINVAL (-1)    /* bad argument (null pointer, non-positive size, unsupported channel count) */
 #define OCRF_ECAPACITY (-2) /* workspace too small for the request */
@@ -97,6 +97,8 @@ typedef struct OcrfBinLayout {
   size_t split_counts;  /* depth-first: scanned tiles_touched; multi-split: uint32 [2][V][chunks][tiles] chunk x tile counts */
   size_t split_tiles;   /* depth-first: look-back state; multi-split: uint32 [3][V*tiles] totals (full, kept), offsets */
   size_t split_words;   /* capacity of split_counts in 32-bit words */
+  size_t split_total;   /* bytes the default (multi-split) mode of ocrf_bin_forward touches: records, keys (its per-pair
+                           items), split_counts, split_tiles -- laid out first; `total` covers every mode */
 } OcrfBinLayout;
 
 typedef struct OcrfImageLayout {

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libocrf_raster.so")
 OCRF_CAM_STRIDE = 40
 OCRF_RECORD_BYTES = 48
 OCRF_GGRAD_STRIDE = 6
-ABI_VERSION = 3
+ABI_VERSION = 4
 OCRF_EINVAL = -1
 OCRF_ECAPACITY = -2
 OCRF_BIN_PAIR_SORT = 1
@@ -44,7 +44,7 @@ class OcrfGeomLayout(C.Structure):
 class OcrfBinLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in ("total", "keys", "point_list", "keys_tmp", "vals_tmp", "keys_unsorted",
                                           "vals_unsorted", "records", "histogram", "sort_status", "split_counts",
-                                          "split_tiles", "split_words")]
+                                          "split_tiles", "split_words", "split_total")]
 
 
 class OcrfImageLayout(C.Structure):

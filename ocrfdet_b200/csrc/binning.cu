@@ -341,20 +341,13 @@ extern "C" int ocrf_bin_layout(const OcrfShape* sh, uint64_t num_pairs, OcrfBinL
   if (num_pairs >= (1ull << 30)) return OCRF_ECAPACITY;
   const size_t n = num_pairs ? num_pairs : 1;
   const int passes = (ocrf_sort_end_bit(sh) + 7) / 8;
+  // What the default (multi-split) binning touches comes FIRST: the records, the per-pair (tile, Gaussian) items (in the
+  // `keys` array), the chunk x tile count tables and the tile arrays end at `split_total`; a caller that uses only that
+  // mode may allocate just that much (56 instead of 72 bytes per pair and no sort workspace).  The key / point lists
+  // of the depth-first and pair-sort modes and the sort workspace follow.
   size_t off = 0;
+  out->records = off;    off = align128(off + n * OCRF_RECORD_BYTES);
   out->keys = off;       off = align128(off + n * 8);
-  out->keys_tmp = off;   off = align128(off + n * 8);
-  out->point_list = off; off = align128(off + n * 4);
-  out->vals_tmp = off;   off = align128(off + n * 4);
-  // `passes` ping-pongs must end in (keys, point_list): start in tmp when odd, in keys when even
-  out->keys_unsorted = (passes & 1) ? out->keys_tmp : out->keys;
-  out->vals_unsorted = (passes & 1) ? out->vals_tmp : out->point_list;
-  out->records = off;
-  off = align128(off + n * OCRF_RECORD_BYTES);
-  out->histogram = off;  // start of the sort workspace
-  const SortWs w = sort_ws_layout(n);
-  out->sort_status = off + w.status;
-  off = align128(off + w.total + 128);
   const size_t nvp = (size_t)sh->V * (sh->P > 0 ? sh->P : 1);
   const size_t tiles_v = (size_t)tiles_x(*sh) * tiles_y(*sh);
   const uint32_t Q = multisplit_chunk_pairs(n);
@@ -365,6 +358,17 @@ extern "C" int ocrf_bin_layout(const OcrfShape* sh, uint64_t num_pairs, OcrfBinL
   off = align128(off + (nvp + table_words) * 4);
   out->split_tiles = off;   // look-back state + ticket of that scan | [3][V*tiles] tile totals / offsets
   off = align128(off + align128(((nvp + 1023) / 1024 + 1) * 8 + 128) + 3 * (size_t)sh->V * tiles_v * 4);
+  out->split_total = off + 128;
+  out->keys_tmp = off;   off = align128(off + n * 8);
+  out->point_list = off; off = align128(off + n * 4);
+  out->vals_tmp = off;   off = align128(off + n * 4);
+  // `passes` ping-pongs must end in (keys, point_list): start in tmp when odd, in keys when even
+  out->keys_unsorted = (passes & 1) ? out->keys_tmp : out->keys;
+  out->vals_unsorted = (passes & 1) ? out->vals_tmp : out->point_list;
+  out->histogram = off;  // start of the sort workspace
+  const SortWs w = sort_ws_layout(n);
+  out->sort_status = off + w.status;
+  off = align128(off + w.total + 128);
   out->total = off + 128;
   return 0;
 }

@@ -211,7 +211,9 @@ class _RasterizeBatch(torch.autograd.Function):
             num_pairs = None
             capacity = max(int(capacity), 1)
         binl = _Workspaces.bin_layout(shape, capacity)
-        binning = torch.empty(binl.total, dtype=torch.uint8, device=dev)
+        # the default multi-split mode touches only the first `split_total` bytes of the layout (56 B per pair)
+        split_mode = cfg.get("binning") not in ("pairsort", "depthfirst") and ((W + 15) // 16) * ((H + 15) // 16) <= 4096
+        binning = torch.empty(binl.split_total if split_mode else binl.total, dtype=torch.uint8, device=dev)
         check(L.ocrf_bin_forward(stream, C.byref(shape), C.c_uint64(capacity), ptr(radii), ptr(colors), int(use_sh),
                                  C.c_uint32({"pairsort": _lib.OCRF_BIN_PAIR_SORT, "depthfirst": _lib.OCRF_BIN_DEPTH_FIRST}
                                             .get(cfg.get("binning"), 0)),
@@ -373,7 +375,7 @@ def last_state(reference_lists=False):
         out["point_list"] = view(binning, b.point_list, N, torch.int32, N)
     if reference_lists and st["binning_mode"] != "pairsort":
         L = _lib.lib()
-        bin2 = torch.empty_like(binning)
+        bin2 = torch.empty(b.total, dtype=torch.uint8, device=binning.device)
         img2 = torch.empty_like(image)
         check(L.ocrf_bin_forward(current_stream(), C.byref(shape), C.c_uint64(st["capacity"]), ptr(st["radii"]),
                                  ptr(st["colors"]), int(st["use_sh"]), C.c_uint32(_lib.OCRF_BIN_PAIR_SORT), ptr(geom),
@@ -388,8 +390,8 @@ def last_state(reference_lists=False):
 
 def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors_precomp=None, shs=None, scales=None,
                  rotations=None, cov3D_precomp=None, means2D=None, scale_modifier=1.0, sh_degree=0, prefiltered=False,
-                 pair_capacity: Optional[int] = None, binning: Optional[str] = None, colors_ready=None,
-                 debug: bool = False):
+                 pair_capacity=None, binning: Optional[str] = None, colors_ready=None, debug: bool = False,
+                 sample_chunk: Optional[int] = None):
     """Render V = cams.shape[0] views of S = means3D.shape[0] samples in one launch sequence.
 
     means3D [S,P,3]; opacities [S,P,1]; colors_precomp [S,P,C] or shs [S,P,M,3]; scales [S,P,3] and
@@ -406,6 +408,10 @@ def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors
     `pair_capacity`: if given, the binning workspace is sized for that many (tile, Gaussian) pairs
     and NO host synchronisation happens (CUDA-graph friendly); an overflow renders background and
     raises at the next entry into the path (`render_batch`, the backward) or `check_overflow()`, whichever comes first.
+    `sample_chunk`: render at most that many samples per launch sequence (their views stay together), one after the
+    other, and concatenate: bounds the transient workspaces -- the binning workspace is 56 bytes per (tile, Gaussian)
+    pair -- for shapes like BASELINE config 5 (8 samples x 6 views at 512x1408 with a million Gaussians each: 134 M
+    pairs per sample).  Every chunk is its own autograd node; `pair_capacity` may then be a sequence, one per chunk.
     `debug`: the reference's debug mode (PKG:83-90,132-139; CR/auxiliary.h:166-173): synchronise and check for CUDA
     errors after every stage, and on any failure save the CPU copy of the arguments as `snapshot_fw.dump` /
     `snapshot_bw.dump` before re-raising.
@@ -414,6 +420,22 @@ def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors
     if means3D.dim() != 3 or means3D.shape[-1] != 3:
         raise Exception("means3D must have dimensions (samples, num_points, 3)")
     S, P = means3D.shape[0], means3D.shape[1]
+    if sample_chunk is not None and 0 < sample_chunk < S and cams.dim() == 2 and cams.shape[0] % S == 0:
+        vps = cams.shape[0] // S
+        cut = lambda t, a, b: None if t is None else t[a:b]  # noqa: E731
+        outs = []
+        for i, s0 in enumerate(range(0, S, sample_chunk)):
+            s1 = min(S, s0 + sample_chunk)
+            cap = pair_capacity[i] if isinstance(pair_capacity, (list, tuple)) else pair_capacity
+            outs.append(render_batch(
+                means3D[s0:s1], opacities[s0:s1], cams[s0 * vps:s1 * vps], image_height, image_width, bg,
+                colors_precomp=cut(colors_precomp, s0, s1), shs=cut(shs, s0, s1), scales=cut(scales, s0, s1),
+                rotations=cut(rotations, s0, s1), cov3D_precomp=cut(cov3D_precomp, s0, s1),
+                means2D=cut(means2D, s0 * vps, s1 * vps), scale_modifier=scale_modifier, sh_degree=sh_degree,
+                prefiltered=prefiltered, pair_capacity=cap, binning=binning, colors_ready=colors_ready, debug=debug))
+        return tuple(torch.cat(parts, 0) for parts in zip(*outs))
+    if isinstance(pair_capacity, (list, tuple)):
+        pair_capacity = pair_capacity[0]
     if cams.dim() != 2 or cams.shape[1] != _lib.OCRF_CAM_STRIDE:
         raise Exception("cams must have dimensions (views, %d): build it with pack_cameras" % _lib.OCRF_CAM_STRIDE)
     V = cams.shape[0]

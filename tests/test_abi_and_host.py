@@ -39,9 +39,12 @@ def test_layout_queries_and_argument_errors_without_gpu():
     assert L.ocrf_bin_layout(C.byref(sh), 4_000_000, C.byref(b)) == 0
     assert L.ocrf_image_layout(C.byref(sh), C.byref(im)) == 0
     for lay in (g, b, im):
-        offs = [getattr(lay, f) for f, _ in lay._fields_ if f != "total"]
+        offs = [getattr(lay, f) for f, _ in lay._fields_ if f not in ("total", "split_words", "split_total")]
         assert all(o % 128 == 0 for o in offs) and lay.total > max(offs)
-    assert g.conic_opacity - g.xy >= 6 * 100000 * 8 and b.records - b.vals_tmp >= 4_000_000 * 4
+    assert g.conic_opacity - g.xy >= 6 * 100000 * 8 and b.keys - b.records >= 4_000_000 * 48
+    # what the default multi-split mode touches is laid out first: 56 bytes per pair + tables, well below the full 72
+    assert b.records == 0 and b.keys < b.split_counts < b.split_tiles < b.split_total <= b.keys_tmp + 128 < b.total
+    assert b.split_total < 4_000_000 * 66 and b.total > 4_000_000 * 72   # (56 B per pair + the count tables)
     # 6 views x 704 tiles = 4224 -> 13 bits -> 45-bit keys; one view -> the reference's 42
     assert L.ocrf_sort_end_bit(C.byref(sh)) == 45
     assert L.ocrf_sort_end_bit(C.byref(_lib.OcrfShape(1, 10, 1, 1, 704, 256, 3, 0, 0))) == 42
