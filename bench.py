@@ -305,10 +305,10 @@ def run_ours(args, rank, world, device):
         tile_passes = (end_bit - 32 + 7) // 8
         launches_per_step = 1 + (1 + vis_passes) + 2 + (1 + tile_passes) + 1 + 4
     else:
-        # default multi-split: preprocess | on-chip cluster sort of the visible Gaussians (+ scan) | count, scan chunks,
-        # scan tiles, scatter | fwd | clear grads | bwd | preprocess bwd
+        # default multi-split: preprocess | on-chip cluster sort of the visible Gaussians (+ scan) | count, scan (chunks
+        # and tiles), scatter | fwd | clear grads | bwd | preprocess bwd
         onchip = not os.environ.get("OCRF_VIS_SORT", "").startswith("g")
-        launches_per_step = 1 + (1 if onchip else (1 + vis_passes) + 1) + 4 + 4
+        launches_per_step = 1 + (1 if onchip else (1 + vis_passes) + 1) + 3 + 4
 
     # ---- device-resident throughput ----
     sampler = ClockSampler(torch.cuda.current_device())

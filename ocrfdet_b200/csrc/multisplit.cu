@@ -75,12 +75,14 @@ __global__ void __launch_bounds__(MS_THREADS) ms_count_kernel(
     const uint32_t* __restrict__ view_start, const uint32_t* __restrict__ sorted_offsets,
     const uint32_t* __restrict__ vis_vals, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
     const float4* __restrict__ conic_opacity, uint32_t* __restrict__ cnt_full, uint32_t* __restrict__ cnt_kept,
-    uint2* __restrict__ items) {
+    uint2* __restrict__ items, uint32_t* __restrict__ chain_words, int n_chain_words) {
   pdl_enter();
   extern __shared__ uint32_t s_dyn[];  // [2][tiles] counters, then [MS_ROUND/2] packed u16 Gaussian offsets
   __shared__ uint32_t s_jf, s_jl;
   __shared__ uint32_t s_wtot[MS_WARPS];
   const int v = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (c == 0 && v == 0)  // look-back state + ticket of the scan kernel that follows (no memset node in the chain)
+    for (int i = tid; i < n_chain_words; i += MS_THREADS) chain_words[i] = 0u;
   if ((uint64_t)header[HDR_NUM_PAIRS] > n_cap) {
     if (c == 0 && v == 0 && tid == 0) atomicOr(&header[HDR_ERROR], ERR_PAIR_OVERFLOW);
     return;
@@ -175,133 +177,89 @@ __global__ void __launch_bounds__(MS_THREADS) ms_count_kernel(
   }
 }
 
-// (B1) exclusive scan over the chunks of every tile (in place) + tile totals, for both tables.
-// One WARP per tile: the lanes take 32 consecutive chunks, so a tile's column is read in
-// ceil(chunks/32) parallel round trips instead of one dependent load per chunk.
-__global__ void __launch_bounds__(256) ms_scan_chunks_kernel(OcrfShape sh, int chunks_max, uint32_t Q, uint64_t n_cap,
-                                                             const uint32_t* __restrict__ header,
-                                                             const uint32_t* __restrict__ view_start,
-                                                             const uint32_t* __restrict__ sorted_offsets,
-                                                             uint32_t* __restrict__ cnt_full,
-                                                             uint32_t* __restrict__ cnt_kept,
-                                                             uint32_t* __restrict__ tot_full,
-                                                             uint32_t* __restrict__ tot_kept) {
+// (B) exclusive scan over the chunks of every tile (in place, both tables) AND the exclusive scan of the tile totals
+// over the whole batch -> tile offsets and both range tables, in ONE kernel: a CTA owns eight consecutive tiles of a
+// view (one warp per tile: the lanes take 32 consecutive chunks, so a tile's column is read in ceil(chunks/32) parallel
+// round trips), and the CTAs are chained by a decoupled look-back over their eight-tile totals (ticketed, so a CTA only
+// ever waits for CTAs that already run).  Round 1 ran the tile scan as a separate single-CTA kernel (11 us of launch
+// and latency for 4 224 numbers).  The look-back words live in `chain` (zeroed by ms_count_kernel).
+__global__ void __launch_bounds__(256) ms_scan_kernel(OcrfShape sh, int chunks_max, uint32_t Q, uint64_t n_cap,
+                                                      const uint32_t* __restrict__ header,
+                                                      const uint32_t* __restrict__ view_start,
+                                                      const uint32_t* __restrict__ sorted_offsets,
+                                                      uint32_t* __restrict__ cnt_full, uint32_t* __restrict__ cnt_kept,
+                                                      unsigned long long* __restrict__ chain, uint32_t* __restrict__ ticket,
+                                                      uint32_t* __restrict__ tile_offset, uint2* __restrict__ ranges,
+                                                      uint2* __restrict__ ranges_render, uint32_t* __restrict__ sticky) {
   pdl_enter();
-  const int v = blockIdx.y;
+  __shared__ uint32_t s_bid, s_prefix;
+  __shared__ uint32_t s_full[8], s_kept[8];
   const int tiles = ceil_div(sh.W, TILE) * ceil_div(sh.H, TILE);
-  const int lane = threadIdx.x & 31;
-  const int t = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-  if (t >= tiles) return;
-  // capacity overflow: ms_count_kernel left the tables unwritten and the real pair count is not bounded by the
-  // table extent -- touch nothing (ms_scan_tiles_kernel zeroes the range tables)
-  if ((uint64_t)header[HDR_NUM_PAIRS] > n_cap) return;
-  uint32_t pb, pe;
-  ms_view_pairs(v, view_start, sorted_offsets, pb, pe);
-  const int nchunks = min(chunks_max, (int)(((uint64_t)(pe - pb) + Q - 1) / Q));
-  uint32_t* cf = cnt_full + (size_t)v * chunks_max * tiles + t;
-  uint32_t* ck = cnt_kept + (size_t)v * chunks_max * tiles + t;
-  uint32_t rf = 0, rk = 0;
-  constexpr int BATCH = 8;  // rounds of 32 chunks whose loads are all issued before the first in-place store
-  for (int cb = 0; cb < nchunks; cb += 32 * BATCH) {
-    uint32_t xf[BATCH], xk[BATCH];
-#pragma unroll
-    for (int r = 0; r < BATCH; r++) {
-      const int c = cb + r * 32 + lane;
-      xf[r] = c < nchunks ? cf[(size_t)c * tiles] : 0u;
-      xk[r] = c < nchunks ? ck[(size_t)c * tiles] : 0u;
-    }
-#pragma unroll
-    for (int r = 0; r < BATCH; r++) {
-      const int c = cb + r * 32 + lane;
-      if (cb + r * 32 >= nchunks) break;  // warp-uniform
-      uint32_t inf = xf[r], ink = xk[r];
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t yf = __shfl_up_sync(0xffffffffu, inf, d), yk = __shfl_up_sync(0xffffffffu, ink, d);
-        if (lane >= d) { inf += yf; ink += yk; }
-      }
-      if (c < nchunks) {
-        cf[(size_t)c * tiles] = rf + inf - xf[r];
-        ck[(size_t)c * tiles] = rk + ink - xk[r];
-      }
-      rf += __shfl_sync(0xffffffffu, inf, 31);
-      rk += __shfl_sync(0xffffffffu, ink, 31);
-    }
-  }
-  if (lane == 0) {
-    tot_full[(size_t)v * tiles + t] = rf;
-    tot_kept[(size_t)v * tiles + t] = rk;
-  }
-}
-
-// (B2) exclusive scan of the full tile totals over the batch -> tile offsets and both range tables
-__global__ void __launch_bounds__(1024) ms_scan_tiles_kernel(int n_tiles, const uint32_t* __restrict__ header,
-                                                             uint64_t n_cap, const uint32_t* __restrict__ tot_full,
-                                                             const uint32_t* __restrict__ tot_kept,
-                                                             uint32_t* __restrict__ tile_offset,
-                                                             uint2* __restrict__ ranges,
-                                                             uint2* __restrict__ ranges_render,
-                                                             uint32_t* __restrict__ sticky) {
-  pdl_enter();
-  __shared__ uint32_t s_warp[32];
-  __shared__ uint32_t s_carry, s_total;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (sticky != nullptr && tid == 0) publish_status(header, n_cap, sticky);
-  if ((uint64_t)header[HDR_NUM_PAIRS] > n_cap) {  // capacity overflow: nothing was binned, render background only
-    for (int i = tid; i < n_tiles; i += 1024) {
-      ranges[i] = make_uint2(0u, 0u);
-      ranges_render[i] = make_uint2(0u, 0u);
-    }
-    return;
-  }
-  if (tid == 0) s_carry = 0;
+  const int groups = ceil_div(tiles, 8);  // CTAs per view
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) s_bid = atomicAdd(ticket, 1u);
   __syncthreads();
-  constexpr int PER = 8;  // consecutive tiles per thread: one load round trip and one CTA scan per 8192 tiles
-  for (int base = 0; base < n_tiles; base += 1024 * PER) {
-    const int i0 = base + tid * PER;
-    uint32_t x[PER], kept[PER], sum = 0;
+  const int bid = (int)s_bid;
+  const int v = bid / groups;
+  const int t = (bid - v * groups) * 8 + warp;
+  const bool overflow = (uint64_t)header[HDR_NUM_PAIRS] > n_cap;
+  if (sticky != nullptr && bid == 0 && threadIdx.x == 0) publish_status(header, n_cap, sticky);
+  uint32_t rf = 0, rk = 0;
+  // (capacity overflow: ms_count_kernel left the tables unwritten and the real pair count is not bounded by the table
+  // extent -- touch nothing, every range reads (0, 0) and only the background is rendered)
+  if (t < tiles && !overflow) {
+    uint32_t pb, pe;
+    ms_view_pairs(v, view_start, sorted_offsets, pb, pe);
+    const int nchunks = min(chunks_max, (int)(((uint64_t)(pe - pb) + Q - 1) / Q));
+    uint32_t* cf = cnt_full + (size_t)v * chunks_max * tiles + t;
+    uint32_t* ck = cnt_kept + (size_t)v * chunks_max * tiles + t;
+    constexpr int BATCH = 8;  // rounds of 32 chunks whose loads are all issued before the first in-place store
+    for (int cb = 0; cb < nchunks; cb += 32 * BATCH) {
+      uint32_t xf[BATCH], xk[BATCH];
 #pragma unroll
-    for (int k = 0; k < PER; k++) {
-      x[k] = i0 + k < n_tiles ? tot_full[i0 + k] : 0u;
-      kept[k] = i0 + k < n_tiles ? tot_kept[i0 + k] : 0u;
-      sum += x[k];
-    }
-    uint32_t incl = sum;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-      if (lane >= d) incl += y;
-    }
-    if (lane == 31) s_warp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {  // scan of the 32 warp totals
-      const uint32_t w = s_warp[lane];
-      uint32_t wi = w;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, wi, d);
-        if (lane >= d) wi += y;
+      for (int r = 0; r < BATCH; r++) {
+        const int c = cb + r * 32 + lane;
+        xf[r] = c < nchunks ? cf[(size_t)c * tiles] : 0u;
+        xk[r] = c < nchunks ? ck[(size_t)c * tiles] : 0u;
       }
-      s_warp[lane] = wi - w;
-      if (lane == 31) s_total = wi;
-    }
-    __syncthreads();
-    uint32_t run = s_carry + s_warp[warp] + incl - sum;
 #pragma unroll
-    for (int k = 0; k < PER; k++) {
-      if (i0 + k < n_tiles) {
-        tile_offset[i0 + k] = run;
-        ranges[i0 + k] = x[k] ? make_uint2(run, run + x[k]) : make_uint2(0u, 0u);  // empty tiles read (0,0) like the reference
-        ranges_render[i0 + k] = make_uint2(run, run + kept[k]);
+      for (int r = 0; r < BATCH; r++) {
+        const int c = cb + r * 32 + lane;
+        if (cb + r * 32 >= nchunks) break;  // warp-uniform
+        uint32_t inf = xf[r], ink = xk[r];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t yf = __shfl_up_sync(0xffffffffu, inf, d), yk = __shfl_up_sync(0xffffffffu, ink, d);
+          if (lane >= d) { inf += yf; ink += yk; }
+        }
+        if (c < nchunks) {
+          cf[(size_t)c * tiles] = rf + inf - xf[r];
+          ck[(size_t)c * tiles] = rk + ink - xk[r];
+        }
+        rf += __shfl_sync(0xffffffffu, inf, 31);
+        rk += __shfl_sync(0xffffffffu, ink, 31);
       }
-      run += x[k];
     }
-    __syncthreads();
-    if (tid == 0) s_carry += s_total;
-    __syncthreads();
+  }
+  if (lane == 0) { s_full[warp] = rf; s_kept[warp] = rk; }
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) total += s_full[w];
+    const unsigned long long excl = lookback_warp(chain, bid, total);
+    if (lane == 0) s_prefix = (uint32_t)excl;
+  }
+  __syncthreads();
+  if (lane == 0 && t < tiles) {
+    uint32_t run = s_prefix;
+    for (int w = 0; w < warp; w++) run += s_full[w];
+    const size_t vt = (size_t)v * tiles + t;
+    tile_offset[vt] = run;
+    ranges[vt] = rf ? make_uint2(run, run + rf) : make_uint2(0u, 0u);  // empty tiles read (0,0) like the reference
+    ranges_render[vt] = overflow ? make_uint2(0u, 0u) : make_uint2(run, run + rk);
   }
 }
-
 
 // (C) stable ranks per tile + direct record writes.  grid (chunks_max, V).
 __global__ void __launch_bounds__(MS_THREADS) ms_scatter_kernel(
@@ -447,9 +405,13 @@ int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity,
   if ((size_t)2 * sh->V * chunks_max * tiles_v > table_words) return OCRF_ECAPACITY;
   uint32_t* cnt_full = tables;
   uint32_t* cnt_kept = tables + (size_t)sh->V * chunks_max * tiles_v;
-  uint32_t* tot_full = tile_arrays;
-  uint32_t* tot_kept = tot_full + (size_t)sh->V * tiles_v;
-  uint32_t* tile_offset = tot_kept + (size_t)sh->V * tiles_v;
+  // tile arrays: [0, V*tiles) the look-back words of the scan (uint64 per CTA = per eight tiles, then its ticket),
+  // [2*V*tiles, 3*V*tiles) the tile offsets
+  const int scan_blocks = sh->V * ceil_div(tiles_v, 8);
+  unsigned long long* chain = reinterpret_cast<unsigned long long*>(tile_arrays);
+  uint32_t* scan_ticket = tile_arrays + 2 * (size_t)scan_blocks + 2;
+  const int n_chain_words = 2 * scan_blocks + 4;
+  uint32_t* tile_offset = tile_arrays + 2 * (size_t)sh->V * tiles_v;
   const size_t smem_a = (size_t)2 * tiles_v * 4 + MS_ROUND * 2;
   const size_t smem_c = (size_t)2 * tiles_v * 4 + (size_t)MS_WARPS * tiles_v * 4 + (size_t)2 * tiles_v * 2;
   static unsigned long long attr_a = 0, attr_c = 0;  // per-device bit masks
@@ -467,13 +429,10 @@ int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity,
 #endif
   for (int rep = 0; rep < OCRF_DIAG_REP(0); rep++)
   OCRF_LAUNCH(ms_count_kernel, dim3(grid), dim3(MS_THREADS), smem_a, st, *sh, chunks_max, Q, pair_capacity, header, view_start, sorted_offsets,
-                                                    vis_vals, radii, xy, conic_opacity, cnt_full, cnt_kept, items);
-  OCRF_LAUNCH(ms_scan_chunks_kernel, dim3(ceil_div(tiles_v, 8), sh->V), dim3(256), 0, st, *sh, chunks_max, Q, pair_capacity,
-                                                                             header, view_start, sorted_offsets, cnt_full, cnt_kept, tot_full,
-                                                                             tot_kept);
-  for (int rep = 0; rep < OCRF_DIAG_REP(1); rep++)
-  OCRF_LAUNCH(ms_scan_tiles_kernel, dim3(1), dim3(1024), 0, st, sh->V * tiles_v, header, pair_capacity, tot_full, tot_kept, tile_offset, ranges,
-                                           ranges_render, sticky);
+                                                    vis_vals, radii, xy, conic_opacity, cnt_full, cnt_kept, items,
+                                                    tile_arrays, n_chain_words);
+  OCRF_LAUNCH(ms_scan_kernel, dim3(scan_blocks), dim3(256), 0, st, *sh, chunks_max, Q, pair_capacity, header, view_start,
+              sorted_offsets, cnt_full, cnt_kept, chain, scan_ticket, tile_offset, ranges, ranges_render, sticky);
   for (int rep = 0; rep < OCRF_DIAG_REP(2); rep++)
   OCRF_LAUNCH(ms_scatter_kernel, dim3(grid), dim3(MS_THREADS), smem_c, st, *sh, chunks_max, Q, pair_capacity, use_sh, sh->C == 3, header,
                                                       view_start, sorted_offsets, items, xy, conic_opacity, depths, rgb,

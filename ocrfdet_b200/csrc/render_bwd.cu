@@ -613,15 +613,15 @@ __global__ void __launch_bounds__(TILE_PIX, 1) render_backward_generic_kernel(
       my_w[(j & (BWDG_FB - 1)) * BWDG_WP] = w;  // column `lane` of the warp's w^T tile (0 for a pixel that did not blend)
       if (__any_sync(0xffffffffu, ok)) {
         const float* fj = s_feat + j * CP;
-        float dsum = 0.f;  // g . colour of this Gaussian
+        // g . colour of this Gaussian: two channels per FFMA2, two independent accumulator pairs
+        float2 d01 = make_float2(0.f, 0.f), d23 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int k = 0; k < CP; k += 4) {
           const float4 c = *reinterpret_cast<const float4*>(fj + k);
-          dsum = fmaf(c.x, g[k], dsum);
-          dsum = fmaf(c.y, g[k + 1], dsum);
-          dsum = fmaf(c.z, g[k + 2], dsum);
-          dsum = fmaf(c.w, g[k + 3], dsum);
+          d01 = ffma2(make_float2(c.x, c.y), make_float2(g[k], g[k + 1]), d01);
+          d23 = ffma2(make_float2(c.z, c.w), make_float2(g[k + 2], g[k + 3]), d23);
         }
+        const float dsum = (d01.x + d01.y) + (d23.x + d23.y);
         const float dot = dsum - S;
         S = fmaf(al, dot, S);  // lanes that did not blend have al = 0
         float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};

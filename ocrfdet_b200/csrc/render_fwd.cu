@@ -524,11 +524,13 @@ __global__ void __launch_bounds__(TILE_PIX, CP <= 80 ? 2 : 1) render_forward_wid
       const bool stop = ok && test_T < 0.0001f;
       const float w = blend ? alpha * T : 0.f;
       const float* fj = s_feat + j * CP;
+      const float2 w2 = bcast2(w);
 #pragma unroll
-      for (int k = 0; k < CP; k += 4) {
+      for (int k = 0; k < CP; k += 4) {  // two channels per FFMA2: the feature pair comes packed out of the LDS.128
         const float4 f = *reinterpret_cast<const float4*>(fj + k);
-        acc[k] = fmaf(f.x, w, acc[k]); acc[k + 1] = fmaf(f.y, w, acc[k + 1]);
-        acc[k + 2] = fmaf(f.z, w, acc[k + 2]); acc[k + 3] = fmaf(f.w, w, acc[k + 3]);
+        const float2 a01 = ffma2(make_float2(f.x, f.y), w2, make_float2(acc[k], acc[k + 1]));
+        const float2 a23 = ffma2(make_float2(f.z, f.w), w2, make_float2(acc[k + 2], acc[k + 3]));
+        acc[k] = a01.x; acc[k + 1] = a01.y; acc[k + 2] = a23.x; acc[k + 3] = a23.y;
       }
       if (blend) {
         if (T > 0.5f && test_T < 0.5f) D = s_rec[j].depth;
