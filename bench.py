@@ -259,8 +259,13 @@ def run_ours(args, rank, world, device):
         for k in names:
             t[k].grad = None
         color, radii, depth, opac = render(t)
-        gathered = gather_opacity_maps(opac.detach(), world, VIEWS, stream=side) if world > 1 else opac
+        if world > 1:
+            fwd_done = torch.cuda.Event()
+            fwd_done.record()
+        # the backward is QUEUED first; the gather of the opacity maps (side stream, copy engines) waits only for the
+        # forward and runs beside it on the device
         torch.autograd.backward([color, opac], [gcol, gop])
+        gathered = gather_opacity_maps(opac.detach(), world, VIEWS, stream=side, after=fwd_done) if world > 1 else opac
         if side is not None:
             torch.cuda.current_stream().wait_stream(side)
         return gathered

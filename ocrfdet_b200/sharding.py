@@ -97,30 +97,38 @@ def _gather_raw(send, world, vmax, group, transport):
     return _nccl_all_gather(send, world, vmax, group)
 
 
+def _gather_forward(local_maps, counts, group, stream, transport, after):
+    world = dist.get_world_size(group)
+    vmax = max(counts)
+    send = local_maps.detach()
+    if send.shape[0] != vmax:
+        pad = send.new_zeros((vmax,) + tuple(send.shape[1:]))
+        pad[:send.shape[0]] = send
+        send = pad
+    send = send.contiguous()
+    side = stream is not None and send.is_cuda
+    if side:
+        if after is not None:
+            stream.wait_event(after)
+        else:
+            stream.wait_stream(torch.cuda.current_stream())
+        send.record_stream(stream)
+    with torch.cuda.stream(stream) if side else _null():
+        out = _gather_raw(send, world, vmax, group, transport)
+        if all(c == vmax for c in counts):
+            out = out.view((world * vmax,) + tuple(send.shape[1:]))
+        else:
+            out = torch.cat([out[r, :counts[r]] for r in range(world)], 0)
+    if side:
+        out.record_stream(torch.cuda.current_stream())  # produced on `stream`, consumed on the caller's stream
+    return out
+
+
 class _GatherMaps(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, local_maps, counts, group, stream, transport, grad_mode):
-        world, rank = dist.get_world_size(group), dist.get_rank(group)
-        vmax = max(counts)
-        send = local_maps.detach()
-        if send.shape[0] != vmax:
-            pad = send.new_zeros((vmax,) + tuple(send.shape[1:]))
-            pad[:send.shape[0]] = send
-            send = pad
-        send = send.contiguous()
-        side = stream is not None and send.is_cuda
-        if side:
-            stream.wait_stream(torch.cuda.current_stream())
-            send.record_stream(stream)
-        with torch.cuda.stream(stream) if side else _null():
-            out = _gather_raw(send, world, vmax, group, transport)
-            if all(c == vmax for c in counts):
-                out = out.view((world * vmax,) + tuple(send.shape[1:]))
-            else:
-                out = torch.cat([out[r, :counts[r]] for r in range(world)], 0)
-        if side:
-            out.record_stream(torch.cuda.current_stream())  # produced on `stream`, consumed on the caller's stream
-        ctx.meta = (counts, rank, world, group, grad_mode, vmax)
+    def forward(ctx, local_maps, counts, group, stream, transport, grad_mode, after):
+        out = _gather_forward(local_maps, counts, group, stream, transport, after)
+        ctx.meta = (counts, dist.get_rank(group), dist.get_world_size(group), group, grad_mode, max(counts))
         return out
 
     @staticmethod
@@ -128,7 +136,7 @@ class _GatherMaps(torch.autograd.Function):
         counts, rank, world, group, grad_mode, vmax = ctx.meta
         begin = sum(counts[:rank])
         if grad_mode == "local":
-            return g[begin:begin + counts[rank]], None, None, None, None, None
+            return g[begin:begin + counts[rank]], None, None, None, None, None, None
         # grad == "sum": every rank's consumer produced a gradient for my maps
         padded = g.new_zeros((world, vmax) + tuple(g.shape[1:]))
         off = 0
@@ -137,7 +145,7 @@ class _GatherMaps(torch.autograd.Function):
             off += counts[r]
         mine = g.new_empty((vmax,) + tuple(g.shape[1:]))
         dist.reduce_scatter_tensor(mine, padded.view((world * vmax,) + tuple(g.shape[1:])), group=group)
-        return mine[:counts[rank]], None, None, None, None, None
+        return mine[:counts[rank]], None, None, None, None, None, None
 
 
 class _null:
@@ -148,13 +156,19 @@ class _null:
         return False
 
 
+_COUNTS = {}
+
+
 def gather_opacity_maps(local_maps: torch.Tensor, num_samples: int, views_per_sample: int, group=None,
-                        stream: "torch.cuda.Stream" = None, transport: str = None, grad: str = "local") -> torch.Tensor:
+                        stream: "torch.cuda.Stream" = None, transport: str = None, grad: str = "local",
+                        after: "torch.cuda.Event" = None) -> torch.Tensor:
     """All-gather per-view opacity maps [V_local,1,H,W] into [num_samples*views_per_sample,1,H,W]
     (global sample-major order).  Works for uneven shards (pads to the largest shard).  Differentiable (see the
     module docstring for `grad`).
-    With `stream`, the transfer is enqueued there after the producer stream's current work and the
-    caller must `torch.cuda.current_stream().wait_stream(stream)` before consuming the result.
+    With `stream`, the transfer is enqueued there after the producer stream's current work -- or, with `after`, after
+    that event only, so a caller may queue the backward first and the gather behind it on the host while the device
+    still runs them side by side -- and the caller must `torch.cuda.current_stream().wait_stream(stream)` before
+    consuming the result.
     `transport`: "peer" (default on CUDA: copy-engine pushes over NVLink peer mappings; the result aliases a
     persistent symmetric buffer that the next gather of the same shape overwrites) or "nccl"; the environment
     variable OCRF_GATHER overrides the default."""
@@ -165,6 +179,11 @@ def gather_opacity_maps(local_maps: torch.Tensor, num_samples: int, views_per_sa
     if transport is None:
         transport = os.environ.get("OCRF_GATHER", "peer")
     world = dist.get_world_size(group)
-    counts = [(shard_samples(num_samples, world, r)[1] - shard_samples(num_samples, world, r)[0]) * views_per_sample
-              for r in range(world)]
-    return _GatherMaps.apply(local_maps, counts, group, stream, transport, grad)
+    key = (num_samples, views_per_sample, world)
+    counts = _COUNTS.get(key)
+    if counts is None:
+        counts = _COUNTS[key] = [(shard_samples(num_samples, world, r)[1] - shard_samples(num_samples, world, r)[0])
+                                 * views_per_sample for r in range(world)]
+    if not (local_maps.requires_grad and torch.is_grad_enabled()):
+        return _gather_forward(local_maps, counts, group, stream, transport, after)  # nothing to differentiate
+    return _GatherMaps.apply(local_maps, counts, group, stream, transport, grad, after)
