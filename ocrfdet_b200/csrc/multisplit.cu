@@ -384,298 +384,6 @@ __global__ void __launch_bounds__(MS_THREADS) ms_scatter_kernel(
   }
 }
 
-// ------------------------------------------------------------------------------------------------------------------
-// Gaussian-centric traversal (default).  A pair-centric kernel (one thread per pair, above) has to find its Gaussian
-// (flag scan), decode its tile with an integer division, and -- in the scatter -- rank itself among the pairs of its
-// tile with a warp match and a dependent shared-memory update per pair.  But the pairs of ONE Gaussian hit DISTINCT
-// tiles, and the stream is ordered by Gaussian: if a warp walks its part of the stream Gaussian by Gaussian, with its
-// lanes on the tiles of that Gaussian's rectangle, the rank of a pair inside its tile is simply the running per-tile
-// counter at the moment the Gaussian is visited -- plain load / add / store, no match, no atomics, no per-pair items
-// (the only thing the second kernel needs from the first is the cull decision: one bit per pair).
-// A chunk round of 4096 pairs is cut into eight 512-pair parts, one per warp; a Gaussian whose pairs straddle a
-// boundary is visited by both warps, each for its own sub-range of the rectangle.
-// ------------------------------------------------------------------------------------------------------------------
-constexpr int GS_PART = MS_ROUND / MS_WARPS;  // pairs per warp per round
-
-struct GsView {
-  int gx, gy, W, H;
-};
-
-// Calls body(active, t, tx, ty, pair_index, first_of_gaussian_data...) for every pair of [wb, we), 32 pairs of one
-// Gaussian at a time.  s_off[i] = sorted_offsets[jf - 1 + i] (exclusive prefix of Gaussian jf + i), i in [0, n_g].
-// load_extra(g) -> float4 fetched by the lane that prefetches Gaussian g and handed to per_gaussian (depth + colour in
-// the record pass; unused elsewhere), so that no load sits between a Gaussian's broadcast and its first round.
-template <typename LoadExtra, typename PerGaussian, typename PerRound>
-__device__ __forceinline__ void gs_walk(uint32_t wb, uint32_t we, uint32_t jf, uint32_t n_g, const uint32_t* s_off,
-                                        const uint32_t* __restrict__ vis_vals, const int32_t* __restrict__ radii,
-                                        const float2* __restrict__ xy, const float4* __restrict__ conic_opacity,
-                                        const GsView& vw, LoadExtra load_extra, PerGaussian per_gaussian,
-                                        PerRound per_round) {
-  const int lane = threadIdx.x & 31;
-  if (wb >= we) return;
-  // first / last Gaussian of my part: the smallest i with s_off[i + 1] > target
-  uint32_t ia, ib;
-  {
-    uint32_t lo = 0, hi = n_g;
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid + 1] > wb) hi = mid; else lo = mid + 1; }
-    ia = lo;
-    lo = ia; hi = n_g;
-    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (s_off[mid + 1] > we - 1) hi = mid; else lo = mid + 1; }
-    ib = lo;
-  }
-  for (uint32_t ibase = ia; ibase <= ib; ibase += 32) {
-    // the next (up to) 32 Gaussians, one per lane: index, rectangle, geometry
-    const uint32_t i = ibase + lane;
-    const bool have = i <= ib;
-    uint32_t g = 0, excl = 0, n = 0;
-    float2 p = make_float2(0.f, 0.f);
-    float4 co = make_float4(0.f, 0.f, 0.f, 0.f), ex = make_float4(0.f, 0.f, 0.f, 0.f);
-    int x0 = 0, y0 = 0, w = 1;
-    if (have) {
-      g = vis_vals[jf + i];
-      ex = load_extra(g);
-      excl = s_off[i];
-      n = s_off[i + 1] - excl;
-      p = xy[g];
-      co = conic_opacity[g];
-      int x1, y1;
-      ms_tile_rect(p.x, p.y, radii[g], vw.gx, vw.gy, x0, y0, x1, y1);
-      w = max(x1 - x0, 1);
-    }
-    const int cnt = (int)min(32u, ib - ibase + 1);
-    for (int s = 0; s < cnt; s++) {
-      const uint32_t bg = __shfl_sync(0xffffffffu, g, s), bexcl = __shfl_sync(0xffffffffu, excl, s);
-      const uint32_t bn = __shfl_sync(0xffffffffu, n, s);
-      const float bpx = __shfl_sync(0xffffffffu, p.x, s), bpy = __shfl_sync(0xffffffffu, p.y, s);
-      const float4 bco = make_float4(__shfl_sync(0xffffffffu, co.x, s), __shfl_sync(0xffffffffu, co.y, s),
-                                     __shfl_sync(0xffffffffu, co.z, s), __shfl_sync(0xffffffffu, co.w, s));
-      const int bx0 = __shfl_sync(0xffffffffu, x0, s), by0 = __shfl_sync(0xffffffffu, y0, s);
-      const int bw = __shfl_sync(0xffffffffu, w, s);
-      const float4 bex = make_float4(__shfl_sync(0xffffffffu, ex.x, s), __shfl_sync(0xffffffffu, ex.y, s),
-                                     __shfl_sync(0xffffffffu, ex.z, s), __shfl_sync(0xffffffffu, ex.w, s));
-      // my part of this Gaussian's pairs: k in [k0, k1) of its row-major rectangle
-      const uint32_t k0 = max(bexcl, wb) - bexcl, k1 = min(bexcl + bn, we) - bexcl;
-      const float inv_w = 1.f / (float)bw;
-      per_gaussian(bg, make_float2(bpx, bpy), bco, bex);
-      for (uint32_t kb = k0; kb < k1; kb += 32) {
-        const uint32_t k = kb + lane;
-        const bool active = k < k1;
-        const int row = (int)(((float)k + 0.5f) * inv_w);  // exact: k < 2^20, w <= 2^7
-        const int ty = by0 + row, tx = bx0 + (int)k - row * bw;
-        per_round(active, ty * vw.gx + tx, tx, ty, bexcl + k, bg, make_float2(bpx, bpy), bco);
-      }
-    }
-  }
-}
-
-// (A') count.  grid (chunks_max, V).  Writes the chunk x tile count tables and one cull bit per pair.
-__global__ void __launch_bounds__(MS_THREADS) gs_count_kernel(
-    OcrfShape sh, int chunks_max, uint32_t Q, uint64_t n_cap, uint32_t* __restrict__ header,
-    const uint32_t* __restrict__ view_start, const uint32_t* __restrict__ sorted_offsets,
-    const uint32_t* __restrict__ vis_vals, const int32_t* __restrict__ radii, const float2* __restrict__ xy,
-    const float4* __restrict__ conic_opacity, uint32_t* __restrict__ cnt_full, uint32_t* __restrict__ cnt_kept,
-    uint32_t* __restrict__ keep_bits, uint32_t* __restrict__ chain_words, int n_chain_words) {
-  pdl_enter();
-  extern __shared__ uint32_t s_dyn[];  // [2][tiles] counters | [MS_ROUND + 2] Gaussian offsets | [MS_WARPS][17] cull bits
-  __shared__ uint32_t s_jf, s_jl;
-  const int v = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (c == 0 && v == 0)  // look-back state + ticket of the scan kernel that follows (no memset node in the chain)
-    for (int i = tid; i < n_chain_words; i += MS_THREADS) chain_words[i] = 0u;
-  if ((uint64_t)header[HDR_NUM_PAIRS] > n_cap) {
-    if (c == 0 && v == 0 && tid == 0) atomicOr(&header[HDR_ERROR], ERR_PAIR_OVERFLOW);
-    return;
-  }
-  uint32_t pb, pe;
-  ms_view_pairs(v, view_start, sorted_offsets, pb, pe);
-  const uint64_t cb64 = (uint64_t)pb + (uint64_t)c * Q;
-  if (cb64 >= pe) return;
-  const uint32_t cb = (uint32_t)cb64, ce = (uint32_t)min((uint64_t)pe, cb64 + Q);
-  GsView vw;
-  vw.gx = ceil_div(sh.W, TILE); vw.gy = ceil_div(sh.H, TILE); vw.W = sh.W; vw.H = sh.H;
-  const int tiles = vw.gx * vw.gy;
-  uint32_t* s_cnt = s_dyn;
-  uint32_t* s_off = s_dyn + 2 * tiles;
-  uint32_t* s_bits = s_off + MS_ROUND + 2 + warp * 17;
-  for (int t = tid; t < 2 * tiles; t += MS_THREADS) s_cnt[t] = 0;
-  const uint32_t jv0 = view_start[v], jv1 = view_start[v + 1];
-  uint32_t* bits_out = keep_bits + ((size_t)v * chunks_max + c) * (Q / 32);
-
-  for (uint32_t rb = cb; rb < ce; rb += MS_ROUND) {
-    const uint32_t n_items = min((uint32_t)MS_ROUND, ce - rb);
-    __syncthreads();
-    if (tid < 2) {  // Gaussian holding the first / last pair of the round: smallest j with sorted_offsets[j] > target
-      const uint32_t target = tid == 0 ? rb : rb + n_items - 1;
-      uint32_t lo = jv0, hi = jv1;
-      while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (sorted_offsets[mid] > target) hi = mid; else lo = mid + 1;
-      }
-      if (tid == 0) s_jf = lo; else s_jl = lo;
-    }
-    __syncthreads();
-    const uint32_t jf = s_jf, n_g = s_jl - jf + 1;  // n_g <= n_items
-    for (uint32_t i = tid; i <= n_g; i += MS_THREADS) s_off[i] = (jf + i) ? sorted_offsets[jf + i - 1] : 0u;
-    if (lane < 17) s_bits[lane] = 0u;
-    __syncthreads();
-    const uint32_t wb = rb + min(n_items, (uint32_t)(warp * GS_PART)), we = rb + min(n_items, (uint32_t)((warp + 1) * GS_PART));
-    gs_walk(wb, we, jf, n_g, s_off, vis_vals, radii, xy, conic_opacity, vw,
-            [](uint32_t) { return make_float4(0.f, 0.f, 0.f, 0.f); }, [](uint32_t, float2, float4, float4) {},
-            [&](bool active, int t, int tx, int ty, uint32_t pair, uint32_t, float2 p, float4 co) {
-              bool keep = false;
-              if (active) {
-                const float px0 = (float)(tx * TILE), px1 = (float)min(tx * TILE + TILE - 1, vw.W - 1);
-                const float py0 = (float)(ty * TILE), py1 = (float)min(ty * TILE + TILE - 1, vw.H - 1);
-                keep = ms_tile_can_contribute(p, co, px0, px1, py0, py1);
-                atomicAdd(&s_cnt[t], 1u);                 // (the tiles of one Gaussian are distinct: no conflicts)
-                if (keep) atomicAdd(&s_cnt[tiles + t], 1u);
-              }
-              const uint32_t bal = __ballot_sync(0xffffffffu, keep);
-              if (lane == 0 && bal) {  // bit (pair - wb) of my part's 512-bit mask; this round starts at pair - lane
-                const uint32_t pos = pair - wb;  // lane 0's pair
-                s_bits[pos >> 5] |= bal << (pos & 31);
-                if (pos & 31) s_bits[(pos >> 5) + 1] |= bal >> (32 - (pos & 31));
-              }
-            });
-    __syncwarp();
-    if (lane < GS_PART / 32 && wb < we) bits_out[(wb - cb) / 32 + lane] = s_bits[lane];
-  }
-  __syncthreads();
-  const size_t row = ((size_t)v * chunks_max + c) * tiles;
-  for (int t = tid; t < tiles; t += MS_THREADS) {
-    cnt_full[row + t] = s_cnt[t];
-    cnt_kept[row + t] = s_cnt[tiles + t];
-  }
-}
-
-// (C') ranks + record writes.  grid (chunks_max, V).
-__global__ void __launch_bounds__(MS_THREADS) gs_scatter_kernel(
-    OcrfShape sh, int chunks_max, uint32_t Q, uint64_t n_cap, int use_sh, int has_rgb,
-    const uint32_t* __restrict__ header, const uint32_t* __restrict__ view_start,
-    const uint32_t* __restrict__ sorted_offsets, const uint32_t* __restrict__ vis_vals,
-    const int32_t* __restrict__ radii, const uint32_t* __restrict__ keep_bits, const float2* __restrict__ xy,
-    const float4* __restrict__ conic_opacity, const float* __restrict__ depths, const float* __restrict__ rgb,
-    const float* __restrict__ colors, const uint32_t* __restrict__ cnt_full, const uint32_t* __restrict__ cnt_kept,
-    const uint32_t* __restrict__ tile_offset, Record* __restrict__ records) {
-  pdl_enter();
-  // [2][tiles] running bases (full: relative to the tile list, kept: record slot) | [MS_WARPS][tiles] per-warp counters
-  // (low half pairs, high half kept pairs) | [2][tiles] u16 round totals | [MS_ROUND + 2] Gaussian offsets |
-  // [MS_WARPS][17] cull bits
-  extern __shared__ uint32_t s_dyn[];
-  __shared__ uint32_t s_jf, s_jl;
-  const int v = blockIdx.y, c = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if ((uint64_t)header[HDR_NUM_PAIRS] > n_cap) return;
-  uint32_t pb, pe;
-  ms_view_pairs(v, view_start, sorted_offsets, pb, pe);
-  const uint64_t cb64 = (uint64_t)pb + (uint64_t)c * Q;
-  if (cb64 >= pe) return;
-  const uint32_t cb = (uint32_t)cb64, ce = (uint32_t)min((uint64_t)pe, cb64 + Q);
-  GsView vw;
-  vw.gx = ceil_div(sh.W, TILE); vw.gy = ceil_div(sh.H, TILE); vw.W = sh.W; vw.H = sh.H;
-  const int tiles = vw.gx * vw.gy;
-  uint32_t* s_base = s_dyn;
-  uint32_t* s_wc = s_dyn + 2 * tiles;
-  uint16_t* s_rt = reinterpret_cast<uint16_t*>(s_wc + (size_t)MS_WARPS * tiles);
-  uint32_t* s_off = s_wc + (size_t)MS_WARPS * tiles + tiles;  // (2 * tiles u16 = tiles words)
-  uint32_t* s_bits = s_off + MS_ROUND + 2 + warp * 17;
-  uint32_t* my_cnt = s_wc + (size_t)warp * tiles;
-  const size_t row = ((size_t)v * chunks_max + c) * tiles;
-  const uint32_t* toff = tile_offset + (size_t)v * tiles;
-  for (int t = tid; t < tiles; t += MS_THREADS) {
-    s_base[t] = cnt_full[row + t];
-    s_base[tiles + t] = toff[t] + cnt_kept[row + t];
-  }
-  const uint32_t jv0 = view_start[v], jv1 = view_start[v + 1];
-  const uint32_t* bits_in = keep_bits + ((size_t)v * chunks_max + c) * (Q / 32);
-  const size_t sample_base = (size_t)(v / sh.views_per_sample) * sh.P;
-  const uint32_t gv0 = (uint32_t)v * (uint32_t)sh.P;
-
-  for (uint32_t rb = cb; rb < ce; rb += MS_ROUND) {
-    const uint32_t n_items = min((uint32_t)MS_ROUND, ce - rb);
-    __syncthreads();
-    if (tid < 2) {
-      const uint32_t target = tid == 0 ? rb : rb + n_items - 1;
-      uint32_t lo = jv0, hi = jv1;
-      while (lo < hi) {
-        const uint32_t mid = (lo + hi) >> 1;
-        if (sorted_offsets[mid] > target) hi = mid; else lo = mid + 1;
-      }
-      if (tid == 0) s_jf = lo; else s_jl = lo;
-    }
-    for (int i = tid; i < MS_WARPS * tiles; i += MS_THREADS) s_wc[i] = 0;
-    __syncthreads();
-    const uint32_t jf = s_jf, n_g = s_jl - jf + 1;
-    for (uint32_t i = tid; i <= n_g; i += MS_THREADS) s_off[i] = (jf + i) ? sorted_offsets[jf + i - 1] : 0u;
-    const uint32_t wb = rb + min(n_items, (uint32_t)(warp * GS_PART)), we = rb + min(n_items, (uint32_t)((warp + 1) * GS_PART));
-    if (lane < 17) s_bits[lane] = (lane < GS_PART / 32 && wb < we) ? bits_in[(wb - cb) / 32 + lane] : 0u;
-    __syncthreads();
-    auto keep_of = [&](uint32_t pair) { const uint32_t pos = pair - wb; return (s_bits[pos >> 5] >> (pos & 31)) & 1u; };
-    // pass 1: this warp's pairs / kept pairs per tile
-    gs_walk(wb, we, jf, n_g, s_off, vis_vals, radii, xy, conic_opacity, vw,
-            [](uint32_t) { return make_float4(0.f, 0.f, 0.f, 0.f); }, [](uint32_t, float2, float4, float4) {},
-            [&](bool active, int t, int, int, uint32_t pair, uint32_t, float2, float4) {
-              if (active) my_cnt[t] += 1u + (keep_of(pair) << 16);  // distinct tiles within a round: no conflict
-              __syncwarp();
-            });
-    __syncthreads();
-    // per tile: exclusive prefix over the warps (stored back into the per-warp slots) and the round totals
-    for (int t = tid; t < tiles; t += MS_THREADS) {
-      uint32_t rf = 0, rk = 0;
-#pragma unroll
-      for (int w = 0; w < MS_WARPS; w++) {
-        uint32_t* f = s_wc + (size_t)w * tiles;
-        const uint32_t x = f[t];
-        f[t] = rf | (rk << 16);
-        rf += x & 0xffffu;
-        rk += x >> 16;
-      }
-      s_rt[t] = (uint16_t)rf;
-      s_rt[tiles + t] = (uint16_t)rk;
-    }
-    __syncthreads();
-    // pass 2: the running counter of a tile, when a Gaussian is visited, IS the rank of its pair in that tile
-    float4 h0 = make_float4(0.f, 0.f, 0.f, 0.f);
-    float qc = 0.f, op = 0.f, cr = 0.f, cg = 0.f, cbl = 0.f, dep = 0.f;
-    uint32_t id = 0;
-    gs_walk(wb, we, jf, n_g, s_off, vis_vals, radii, xy, conic_opacity, vw,
-            [&](uint32_t g) {  // depth + colour, fetched with the rest of the Gaussian
-              float4 e = make_float4(depths[g], 0.f, 0.f, 0.f);
-              if (has_rgb) {
-                const float* col = use_sh ? rgb + (size_t)g * 3 : colors + (sample_base + (g - gv0)) * 3;
-                e.y = __ldg(col); e.z = __ldg(col + 1); e.w = __ldg(col + 2);
-              }
-              return e;
-            },
-            [&](uint32_t g, float2 p, float4 co, float4 e) {  // the record fields every pair of this Gaussian shares
-              h0 = record_head(p, co);
-              qc = record_qc(co);
-              op = co.w;
-              id = g - gv0;
-              dep = e.x; cr = e.y; cg = e.z; cbl = e.w;
-            },
-            [&](bool active, int t, int, int, uint32_t pair, uint32_t, float2, float4) {
-              if (active) {
-                const uint32_t keep = keep_of(pair);
-                const uint32_t cur = my_cnt[t];
-                my_cnt[t] = cur + 1u + (keep << 16);
-                if (keep) {
-                  const uint32_t orig = s_base[t] + (cur & 0xffffu) + 1;  // 1-based position in the tile's full list
-                  const uint32_t dst = s_base[tiles + t] + (cur >> 16);    // record slot
-                  float4* out = reinterpret_cast<float4*>(records + dst);
-                  out[0] = h0;
-                  out[1] = make_float4(qc, op, __uint_as_float(orig), cr);
-                  out[2] = make_float4(cg, cbl, __uint_as_float(id), dep);
-                }
-              }
-              __syncwarp();
-            });
-    __syncthreads();
-    for (int t = tid; t < tiles; t += MS_THREADS) {  // advance the running bases past this round
-      s_base[t] += s_rt[t];
-      s_base[tiles + t] += s_rt[tiles + t];
-    }
-  }
-}
-
 }  // namespace ocrf
 
 using namespace ocrf;
@@ -704,29 +412,6 @@ int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity,
   uint32_t* scan_ticket = tile_arrays + 2 * (size_t)scan_blocks + 2;
   const int n_chain_words = 2 * scan_blocks + 4;
   uint32_t* tile_offset = tile_arrays + 2 * (size_t)sh->V * tiles_v;
-  static const bool gaussian_centric = !(getenv("OCRF_MS") != nullptr && getenv("OCRF_MS")[0] == 'p');  // p(airs): round 1
-  if (gaussian_centric) {
-    const size_t smem_ga = ((size_t)2 * tiles_v + MS_ROUND + 2 + MS_WARPS * 17) * 4;
-    const size_t smem_gc = ((size_t)2 * tiles_v + (size_t)MS_WARPS * tiles_v + tiles_v + MS_ROUND + 2 + MS_WARPS * 17) * 4;
-    if (smem_ga > 100 * 1024 || smem_gc > 200 * 1024) return OCRF_ECAPACITY;
-    static unsigned long long attr_ga = 0, attr_gc = 0;
-    cudaError_t ge = ensure_dynamic_smem(gs_count_kernel, 100 * 1024, attr_ga);
-    if (ge != cudaSuccess) return (int)ge;
-    ge = ensure_dynamic_smem(gs_scatter_kernel, 200 * 1024, attr_gc);
-    if (ge != cudaSuccess) return (int)ge;
-    const dim3 ggrid(chunks_max, sh->V);
-    uint32_t* keep_bits = reinterpret_cast<uint32_t*>(items);  // one bit per pair, (Q / 32) words per (view, chunk)
-    OCRF_LAUNCH(gs_count_kernel, dim3(ggrid), dim3(MS_THREADS), smem_ga, st, *sh, chunks_max, Q, pair_capacity, header,
-                view_start, sorted_offsets, vis_vals, radii, xy, conic_opacity, cnt_full, cnt_kept, keep_bits, tile_arrays,
-                n_chain_words);
-    OCRF_LAUNCH(ms_scan_kernel, dim3(scan_blocks), dim3(256), 0, st, *sh, chunks_max, Q, pair_capacity, header, view_start,
-                sorted_offsets, cnt_full, cnt_kept, chain, scan_ticket, tile_offset, ranges, ranges_render, sticky);
-    OCRF_LAUNCH(gs_scatter_kernel, dim3(ggrid), dim3(MS_THREADS), smem_gc, st, *sh, chunks_max, Q, pair_capacity, use_sh,
-                sh->C == 3, header, view_start, sorted_offsets, vis_vals, radii, keep_bits, xy, conic_opacity, depths, rgb,
-                colors, cnt_full, cnt_kept, tile_offset, records);
-    cudaError_t le = cudaGetLastError();
-    return le == cudaSuccess ? 0 : (int)le;
-  }
   const size_t smem_a = (size_t)2 * tiles_v * 4 + MS_ROUND * 2;
   const size_t smem_c = (size_t)2 * tiles_v * 4 + (size_t)MS_WARPS * tiles_v * 4 + (size_t)2 * tiles_v * 2;
   static unsigned long long attr_a = 0, attr_c = 0;  // per-device bit masks
