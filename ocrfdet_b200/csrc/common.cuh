@@ -181,6 +181,14 @@ inline uint32_t multisplit_chunk_pairs(uint64_t pair_capacity) {  // pairs per c
   return (uint32_t)((rounds < 1 ? 1 : rounds) * 4096);
 }
 
+// render_tc_fwd.cu / render_tc_bwd.cu: the many-channel blend on tcgen05 (32 < C <= 80, C % 4 == 0; OCRF_TC=0 disables)
+namespace tc {
+bool forward_tc_supported(int C);
+int launch_forward_tc(cudaStream_t st, dim3 grid, const OcrfShape* sh, const uint2* ranges, const Record* rec,
+                      const float* colors, const float* bg, float* fT, uint32_t* nc, uint32_t* mc, float* out_color,
+                      float* out_depth, float* out_opacity);
+}  // namespace tc
+
 // ---- PTX helpers: mbarrier + 1D bulk async copy (TMA unit, SASS UBLKCP) ----
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

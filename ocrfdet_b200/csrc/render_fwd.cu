@@ -609,7 +609,8 @@ extern "C" int ocrf_render_forward(void* stream, const OcrfShape* sh, uint64_t p
     (void)use_sh;
     const Record* rec = at<Record>(bin_ws, B.records);
     int rcw = 0;
-    if (sh->C <= 16) rcw = launch_forward_wide<16>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
+    if (tc::forward_tc_supported(sh->C)) rcw = tc::launch_forward_tc(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
+    else if (sh->C <= 16) rcw = launch_forward_wide<16>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
     else if (sh->C <= 32) rcw = launch_forward_wide<32>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
     else if (sh->C <= 48) rcw = launch_forward_wide<48>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
     else if (sh->C <= 64) rcw = launch_forward_wide<64>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
