@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libocrf_raster.so")
 SOURCES = ["api.cu", "preprocess.cu", "preprocess_bwd.cu", "binning.cu", "multisplit.cu", "visible_sort.cu", "radix_sort.cu", "render_fwd.cu",
-           "render_bwd.cu", "render_tc_fwd.cu", "opacity_lift.cu", "hoa_lift.cu", "hoa_converter.cu", "gaussian_heads.cu", "bev_pool.cu", "voxel_color.cu"]
+           "render_bwd.cu", "render_tc_fwd.cu", "render_tc_bwd.cu", "opacity_lift.cu", "hoa_lift.cu", "hoa_converter.cu", "gaussian_heads.cu", "bev_pool.cu", "voxel_color.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
               "-I" + os.path.join(ROOT, "include"), "-I" + CSRC]
 

@@ -187,6 +187,9 @@ bool forward_tc_supported(int C);
 int launch_forward_tc(cudaStream_t st, dim3 grid, const OcrfShape* sh, const uint2* ranges, const Record* rec,
                       const float* colors, const float* bg, float* fT, uint32_t* nc, uint32_t* mc, float* out_color,
                       float* out_depth, float* out_opacity);
+int launch_backward_tc(cudaStream_t st, dim3 grid, const OcrfShape* sh, const uint2* ranges, const Record* rec,
+                       const float* colors, const float* bg, const float* fT, const uint32_t* nc, const uint32_t* mc,
+                       const float* dL_dcolor, const float* dL_dopa, double* ggrad, float* dL_dcolors);
 }  // namespace tc
 
 // ---- PTX helpers: mbarrier + 1D bulk async copy (TMA unit, SASS UBLKCP) ----

@@ -13,51 +13,12 @@
 // The arithmetic follows SURVEY.md appendix A5 (T recovered by division, suffix colour recurrence,
 // background term, no clamp mask) plus the opacity-map term  +T_final/(1-alpha) * dL/dO.
 // Summation order differs from the reference's unordered atomics: gradients agree to ~1e-5 rel.
-#include "common.cuh"
+#include "blend_math.cuh"
 
 namespace ocrf {
 
 template <int PPT> struct BwdBatch { static constexpr int value = PPT == 1 ? 64 : 128; };  // records per stage
 constexpr int BWD_ACC = 12;  // floats per record accumulator row (9 used)
-
-__device__ __forceinline__ float ex2_approx_b(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// 1 / x for x in [0.01, 1] (x = 1 - alpha): one MUFU.RCP, no range fix-up code
-__device__ __forceinline__ float rcp_approx(float x) {
-  float y;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
-
-// Reduce-scatter of 8 values over the warp: afterwards lane L (any L) holds the warp total of value
-// index ((L>>4)&1)*4 + ((L>>3)&1)*2 + ((L>>2)&1).
-__device__ __forceinline__ float butterfly8(float (&v)[8], int lane) {
-  const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
-  float w[4];
-#pragma unroll
-  for (int i = 0; i < 4; i++) {
-    const float keep = h16 ? v[i + 4] : v[i];
-    const float send = h16 ? v[i] : v[i + 4];
-    w[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-  }
-  float u[2];
-#pragma unroll
-  for (int i = 0; i < 2; i++) {
-    const float keep = h8 ? w[i + 2] : w[i];
-    const float send = h8 ? w[i] : w[i + 2];
-    u[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-  }
-  const float keep = h4 ? u[1] : u[0];
-  const float send = h4 ? u[0] : u[1];
-  float r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-  r += __shfl_xor_sync(0xffffffffu, r, 2);
-  r += __shfl_xor_sync(0xffffffffu, r, 1);
-  return r;
-}
 
 template <int PPT>
 __global__ void __launch_bounds__(TILE_PIX / PPT) render_backward_c3_scalar_kernel(
@@ -495,26 +456,6 @@ __device__ __forceinline__ float butterfly16(const float* v, int lane) {
   return r;  // value index = h16*8 + h8*4 + h4*2 + h2
 }
 
-// ---- tensor-core helpers for the feature gradients of the generic-channel backward -------------------------------
-// dF[record][channel] = sum over the pixels of a tile of w[pixel][record] * g[pixel][channel] is a dense product.
-// Every warp multiplies ITS 32 pixels: A = w^T [16 records x 32 pixels] (staged through shared memory as the records
-// are walked), B = g [32 pixels x CP channels] (staged once per tile), C = a [16 x CP] partial that the eight warps
-// then add up.  mma.sync.m16n8k8 TF32 with the 3-term split (hi*hi + lo*hi + hi*lo) keeps fp32 accuracy: plain TF32
-// (10-bit mantissa) misses the 1e-4 gradient bar on sums of 256 mixed-sign terms.
-__device__ __forceinline__ uint32_t to_tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = to_tf32(x);
-  lo = to_tf32(x - __uint_as_float(hi));
-}
-__device__ __forceinline__ void mma_tf32_16x8x8(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
-}
 constexpr int BWDG_WP = 36;  // pitch of a record's 32 pixel weights (== 4 mod 32: conflict-free A fragments)
 
 template <int CP>
@@ -794,7 +735,10 @@ extern "C" int ocrf_render_backward(void* stream, const OcrfShape* sh, uint64_t 
 #define OCRF_BWDG(CPV)                                                                                              \
   rc2 = launch_backward_generic<CPV>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopacity_map, \
                                      ggrad, dL_dcolors)
-    if (sh->C <= 16) OCRF_BWDG(16);
+    static const bool tc_bwd = !(getenv("OCRF_TC_BWD") != nullptr && atoi(getenv("OCRF_TC_BWD")) == 0);
+    if (tc_bwd && tc::forward_tc_supported(sh->C))
+      rc2 = tc::launch_backward_tc(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopacity_map, ggrad, dL_dcolors);
+    else if (sh->C <= 16) OCRF_BWDG(16);
     else if (sh->C <= 32) OCRF_BWDG(32);
     else if (sh->C <= 48) OCRF_BWDG(48);
     else if (sh->C <= 64) OCRF_BWDG(64);

@@ -1,0 +1,396 @@
+// Stage 4 for many feature channels (32 < C <= 80, BASELINE config 4): the blend backward with its per-(pixel, record)
+// C-term dot product on the 5th-generation tensor cores.
+//
+// The reverse traversal of cuda_rasterizer/backward.cu:399-557 needs, per (pixel p, record j),
+//     dot[p][j] = sum_c dL/dpixel[p][c] * feature[j][c]
+// (render_backward_generic_kernel: C/2 FFMA2 + C/4 LDS.128 per pair, about half of its instructions).  For a tile that
+// is  D1[256 px][R records] = G[256][C] . F^T[C][R],  issued here as tcgen05.mma (kind::tf32, M = 128, N = 32, K = 8):
+//   A operand  G = dL/dpixel of the tile, RESIDENT in tensor memory for the whole tile: every thread stores its pixel's
+//              row once (g and g_lo = g - trunc_tf32(g): 2 x 2 x C columns)
+//   B operand  feature rows of 32 records, K-major in shared memory: a row IS a run of 16-byte chunks of the canonical
+//              core-matrix layout, so the loader warp lets cp.async put them in place and only derives the f_lo image
+//   D1         2 x (2 x 32) columns, double-buffered: the MMAs of block b + 1 run under the scalar work of block b;
+//              a worker reads its pixel's 32 dot products with two tcgen05.ld
+//   precision  3xTF32 (g.f + g_lo.f + g.f_lo), ~2^-21 relative per term: inside the 1e-4 gradient bar.
+// Everything after the dot product is render_backward_generic_kernel's scheme: scalar recurrence for the colour
+// accumulated behind, 8-value butterfly for the geometry gradients, per-warp 3xTF32 mma.sync product for the feature
+// gradients, one set of global reductions per record per tile.
+// Tensor memory: 4 C + 128 <= 448 columns -> one CTA per SM (8 worker warps + MMA warp + loader warp).
+#include "blend_math.cuh"
+#include "tc_common.cuh"
+
+namespace ocrf {
+namespace tc {
+
+constexpr int BR = 32;  // records per block == N of the tcgen05.mma
+constexpr int BWD_THREADS = TILE_PIX + 64;
+constexpr uint32_t BWD_TMEM_COLS = 512;
+constexpr int FB = 16;  // records per cross-warp reduction of the feature gradients
+constexpr int WP = 36;  // pitch of a record's 32 pixel weights (== 4 mod 32: conflict-free A fragments)
+constexpr int NWW = TILE_PIX / 32;
+
+template <int CP>
+struct BwdSmem {
+  static constexpr int KC = CP / 4;  // 16-byte chunks per feature row
+  static constexpr uint32_t LBO = 128;          // next 4 channels of the same 8 records
+  static constexpr uint32_t SBO = KC * 128;     // next 8 records
+  static constexpr uint32_t PART = (BR / 8) * SBO;
+  static constexpr int GP = CP + 8;             // g row pitch (== 8 mod 16: conflict-free B fragments)
+  alignas(128) unsigned char f[2][2][PART];     // [stage][raw | lo]
+  alignas(128) Record rec[2][BR];
+  alignas(16) float acc[NWW][BR][8];
+  alignas(16) float facc[NWW][FB][CP];
+  alignas(16) float g[NWW][32][GP];
+  alignas(16) float w[NWW][FB][WP];
+  alignas(8) uint64_t ready_f[2], free_f[2], ready_d[2], free_d[2];
+  uint32_t touched[NWW];
+  uint32_t tmem;
+};
+
+__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TILE_PIX) : "memory"); }
+
+template <int CP>
+__global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
+    int W, int H, int C, int P, int views_per_sample, const uint2* __restrict__ ranges /* culled lists */,
+    const Record* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
+    const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
+    const uint32_t* __restrict__ max_contrib, const float* __restrict__ dL_dpix, const float* __restrict__ dL_dopa,
+    double* __restrict__ ggrad, float* __restrict__ dL_dfeats) {
+  pdl_enter();
+  using SM = BwdSmem<CP>;
+  extern __shared__ __align__(128) unsigned char smem_raw_b[];
+  SM& sm = *reinterpret_cast<SM*>(smem_raw_b);
+  constexpr int GP = SM::GP;
+  constexpr uint32_t D_COL0 = 4 * CP;  // G occupies [0, 4 CP): per M-block g then g_lo
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tiles_x = gridDim.x, tiles_per_view = gridDim.x * gridDim.y;
+  const int view = blockIdx.z;
+  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  const size_t vt = (size_t)view * tiles_per_view + tile;
+  const int mc = (int)max_contrib[vt];
+  if (mc == 0) return;
+  const uint2 range = ranges[vt];
+  const int nb = (mc + BR - 1) / BR;
+  const int s_idx = view / views_per_sample;
+
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < 2; s++) {
+      mbar_init(&sm.ready_f[s], 1);
+      mbar_init(&sm.free_f[s], NWW);
+      mbar_init(&sm.ready_d[s], 1);
+      mbar_init(&sm.free_d[s], NWW);
+    }
+    mbar_fence_init();
+  }
+  if (warp == NWW) tmem_alloc<BWD_TMEM_COLS>(&sm.tmem);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tm = sm.tmem;
+
+  if (warp < NWW) {
+    // ------------------------------------------------ workers ------------------------------------------------
+    const float* fbase = feats + (size_t)s_idx * P * C;
+    (void)fbase;
+    float* gfbase = dL_dfeats + (size_t)s_idx * P * C;
+    const size_t HW = (size_t)H * W;
+    const int px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
+    const int py = blockIdx.y * TILE + (warp >> 1) * 4 + (lane >> 3);
+    const bool inside = px < W && py < H;
+    const size_t pix = (size_t)py * W + px;
+    const float fx = (float)px, fy = (float)py;
+    const float Tf = inside ? final_T[view * HW + pix] : 0.f;
+    const int nc = inside ? (int)n_contrib[view * HW + pix] : 0;
+    const int mb = warp >> 2;
+    const uint32_t lane_addr = tm + ((uint32_t)((warp & 3) * 32) << 16);
+    // this pixel's upstream gradient: to tensor memory (g, g_lo) and to the shared tile the mma.sync product reads
+    float bgdot = 0.f;
+    {
+      float* grow = &sm.g[warp][lane][0];
+#pragma unroll
+      for (int c0 = 0; c0 < CP; c0 += 16) {
+        uint32_t raw[16], lo[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const int k = c0 + i;
+          const float gv = (inside && k < C) ? dL_dpix[((size_t)view * C + k) * HW + pix] : 0.f;
+          bgdot += (k < C ? bg[k] : 0.f) * gv;
+          raw[i] = __float_as_uint(gv);
+          lo[i] = __float_as_uint(tf32_lo(gv));
+        }
+#pragma unroll
+        for (int i = 0; i < 16; i += 4)
+          *reinterpret_cast<float4*>(grow + c0 + i) = make_float4(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]),
+                                                                  __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+        tmem_st16(lane_addr + mb * 2 * CP + c0, raw);
+        tmem_st16(lane_addr + mb * 2 * CP + CP + c0, lo);
+      }
+      tmem_wait_st();
+    }
+    fence_before_sync();
+    __syncthreads();  // (A) G is in tensor memory: the MMA warp may start
+    float S = 0.f;    // g . (colour accumulated behind this pixel), see render_backward_generic_kernel
+    float* my_w = &sm.w[warp][0][lane];
+    const float gop = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
+    const float gob = Tf * (gop - bgdot);
+    float T = Tf;
+    const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
+
+    for (int b = 0; b < nb; b++) {
+      const int s = b & 1;
+      const uint32_t use = (uint32_t)(b >> 1);
+      const int hi = mc - b * BR;
+      const int lo = max(0, hi - BR);
+      const int cnt = hi - lo;
+      mbar_wait_wd(&sm.ready_f[s], use & 1);
+      mbar_wait_wd(&sm.ready_d[s], use & 1);
+      fence_after_sync();
+      uint32_t d[BR];
+      {
+        uint32_t d0[16], d1[16];
+        tmem_ld16(lane_addr + D_COL0 + s * 64 + mb * 32, d0);
+        tmem_ld16(lane_addr + D_COL0 + s * 64 + mb * 32 + 16, d1);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          d[i] = d0[i];
+          d[16 + i] = d1[i];
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.free_d[s]);
+      uint32_t touched = 0;
+#pragma unroll
+      for (int j = BR - 1; j >= 0; j--) {
+        if (j < cnt) {
+          const float4 a = reinterpret_cast<const float4*>(&sm.rec[s][j])[0];
+          const float4 bq = reinterpret_cast<const float4*>(&sm.rec[s][j])[1];
+          const float dx = a.x - fx, dy = a.y - fy;
+          const float power = a.z * dx * dx + bq.x * dy * dy + a.w * dx * dy;  // log2 domain (scaled conic)
+          const float G = ex2_approx_b(power);
+          const float alpha = fminf(0.99f, bq.y * G);
+          const bool ok = (int)__float_as_uint(bq.z) <= nc && power <= 0.0f && alpha >= 1.0f / 255.0f;
+          float rcp = 1.f, w = 0.f, al = 0.f;
+          if (ok) {
+            rcp = __fdividef(1.f, 1.f - alpha);
+            T *= rcp;
+            w = alpha * T;
+            al = alpha;
+          }
+          my_w[(j & (FB - 1)) * WP] = w;  // column `lane` of the warp's w^T tile (0 for a pixel that did not blend)
+          if (__any_sync(0xffffffffu, ok)) {
+            const float dot = __uint_as_float(d[j]) - S;
+            S = fmaf(al, dot, S);  // lanes that did not blend have al = 0
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (ok) {
+              const float dL_dalpha = dot * T + gob * rcp;
+              const float dL_dG = bq.y * dL_dalpha;
+              const float gdx = G * dx, gdy = G * dy;
+              // conic recovered from the scaled record: A = -2 ln2 qa, B = -ln2 qb, C = -2 ln2 qc
+              v[0] = dL_dG * (LN2 * (2.f * gdx * a.z + gdy * a.w)) * ddelx_dx;
+              v[1] = dL_dG * (LN2 * (2.f * gdy * bq.x + gdx * a.w)) * ddely_dy;
+              v[2] = -0.5f * gdx * dx * dL_dG;
+              v[3] = -0.5f * gdx * dy * dL_dG;
+              v[4] = -0.5f * gdy * dy * dL_dG;
+              v[5] = G * dL_dalpha;
+            }
+            const float r8 = butterfly8(v, lane);
+            if ((lane & 3) == 0) sm.acc[warp][j][lane >> 2] = r8;
+            touched |= 1u << j;
+          }
+          if ((j & (FB - 1)) == 0) {
+            // ---- records [j, j + FB) are complete in every warp: one reduction over the warps per channel ----
+            __syncwarp();
+            {  // this warp's partial dF[16 records][CP] = w^T[16 x 32 px] . g[32 px x CP] (3xTF32 mma.sync)
+              const int gid = lane >> 2, tig = lane & 3;
+              const float* wt = &sm.w[warp][0][0];
+              const float* gt = &sm.g[warp][0][0];
+              float cacc[CP / 8][4];
+#pragma unroll
+              for (int nt = 0; nt < CP / 8; nt++) cacc[nt][0] = cacc[nt][1] = cacc[nt][2] = cacc[nt][3] = 0.f;
+#pragma unroll
+              for (int ks = 0; ks < 4; ks++) {
+                uint32_t ahi[4], alo[4];
+                split_tf32(wt[gid * WP + 8 * ks + tig], ahi[0], alo[0]);
+                split_tf32(wt[(gid + 8) * WP + 8 * ks + tig], ahi[1], alo[1]);
+                split_tf32(wt[gid * WP + 8 * ks + tig + 4], ahi[2], alo[2]);
+                split_tf32(wt[(gid + 8) * WP + 8 * ks + tig + 4], ahi[3], alo[3]);
+#pragma unroll
+                for (int nt = 0; nt < CP / 8; nt++) {
+                  uint32_t bhi[2], blo[2];
+                  split_tf32(gt[(8 * ks + tig) * GP + 8 * nt + gid], bhi[0], blo[0]);
+                  split_tf32(gt[(8 * ks + tig + 4) * GP + 8 * nt + gid], bhi[1], blo[1]);
+                  mma_tf32_16x8x8(cacc[nt], alo, bhi);
+                  mma_tf32_16x8x8(cacc[nt], ahi, blo);
+                  mma_tf32_16x8x8(cacc[nt], ahi, bhi);
+                }
+              }
+              float* fo = &sm.facc[warp][0][0];
+#pragma unroll
+              for (int nt = 0; nt < CP / 8; nt++) {
+                *reinterpret_cast<float2*>(fo + gid * CP + 8 * nt + 2 * tig) = make_float2(cacc[nt][0], cacc[nt][1]);
+                *reinterpret_cast<float2*>(fo + (gid + 8) * CP + 8 * nt + 2 * tig) = make_float2(cacc[nt][2], cacc[nt][3]);
+              }
+            }
+            worker_bar();
+            for (int e = tid; e < FB * CP; e += TILE_PIX) {
+              const int jj = e / CP, ch = e - jj * CP;
+              const int rj = j + jj;
+              if (rj >= cnt || ch >= C) continue;  // (rows past the end of the block hold stale weights)
+              float tot = 0.f;
+#pragma unroll
+              for (int w2 = 0; w2 < NWW; w2++) tot += sm.facc[w2][jj][ch];
+              if (tot != 0.f) atomicAdd(gfbase + (size_t)sm.rec[s][rj].id * C + ch, tot);
+            }
+            worker_bar();
+          }
+        }
+      }
+      if (lane == 0) sm.touched[warp] = touched;
+      worker_bar();
+      if (tid < cnt) {
+        const int j = tid;
+        float q[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        bool hit = false;
+#pragma unroll
+        for (int w2 = 0; w2 < NWW; w2++)
+          if ((sm.touched[w2] >> j) & 1u) {
+            hit = true;
+            const float4 q0 = *reinterpret_cast<const float4*>(&sm.acc[w2][j][0]);
+            const float2 q1 = *reinterpret_cast<const float2*>(&sm.acc[w2][j][4]);
+            q[0] += q0.x; q[1] += q0.y; q[2] += q0.z; q[3] += q0.w; q[4] += q1.x; q[5] += q1.y;
+          }
+        if (hit) {
+          double* gg = ggrad + ((size_t)view * P + sm.rec[s][j].id) * OCRF_GGRAD_STRIDE;
+#pragma unroll
+          for (int e = 0; e < 6; e++) atomicAdd(gg + e, (double)q[e]);
+        }
+      }
+      worker_bar();  // acc / touched / rec[s] are free again
+      if (lane == 0) mbar_arrive(&sm.free_f[s]);
+    }
+  } else if (warp == NWW) {
+    // ------------------------------------------------ MMA issuer ------------------------------------------------
+    constexpr uint32_t IDESC = idesc_tf32(128, BR);
+    __syncthreads();  // (A)
+    fence_after_sync();
+    for (int b = 0; b < nb; b++) {
+      const int s = b & 1;
+      const uint32_t use = (uint32_t)(b >> 1);
+      mbar_wait_wd(&sm.ready_f[s], use & 1);
+      mbar_wait_wd(&sm.free_d[s], (use & 1) ^ 1);
+      fence_after_sync();
+      if (lane == 0) {
+        const uint32_t f_raw = smem_u32(&sm.f[s][0][0]), f_lo = smem_u32(&sm.f[s][1][0]);
+#pragma unroll
+        for (int mb = 0; mb < 2; mb++) {
+          const uint32_t dcol = tm + D_COL0 + s * 64 + mb * 32;
+          const uint32_t g_raw = tm + mb * 2 * CP, g_lo = g_raw + CP;
+#pragma unroll
+          for (int ks = 0; ks < CP / 8; ks++) {
+            const uint64_t b_raw = smem_desc(f_raw + ks * 2 * SM::LBO, SM::LBO, SM::SBO);
+            const uint64_t b_lo = smem_desc(f_lo + ks * 2 * SM::LBO, SM::LBO, SM::SBO);
+            mma_ts_tf32(dcol, g_raw + ks * 8, b_raw, IDESC, ks > 0);
+            mma_ts_tf32(dcol, g_lo + ks * 8, b_raw, IDESC, 1);
+            mma_ts_tf32(dcol, g_raw + ks * 8, b_lo, IDESC, 1);
+          }
+        }
+        mma_commit(&sm.ready_d[s]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ------------------------------------------------ loader ------------------------------------------------
+    const Record* src = records + range.x;
+    const float* fbase = feats + (size_t)s_idx * P * C;
+    auto issue = [&](int b) {
+      const int s = b & 1;
+      const uint32_t use = (uint32_t)(b >> 1);
+      const int hi = mc - b * BR;
+      const int lo = max(0, hi - BR);
+      const int cnt = hi - lo;
+      mbar_wait_wd(&sm.free_f[s], (use & 1) ^ 1);
+      if (lane < cnt) {
+        const uint32_t id = src[lo + lane].id;
+        unsigned char* dst = &sm.f[s][0][(lane & 7) * 16 + (lane >> 3) * SM::SBO];
+        const float* row = fbase + (size_t)id * C;
+#pragma unroll
+        for (int cc = 0; cc < SM::KC; cc++)
+          if (4 * cc < C) cp_async16(dst + cc * SM::LBO, row + 4 * cc);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        const int t = lane + 32 * i;
+        if (t < cnt * 3)
+          cp_async16(reinterpret_cast<char*>(&sm.rec[s][0]) + t * 16, reinterpret_cast<const char*>(src + lo) + t * 16);
+      }
+      cp_async_commit();
+    };
+    auto finalize = [&](int b) {  // this lane's record: the f_lo image (and the zero padding of the channels)
+      const int s = b & 1;
+      const int hi = mc - b * BR;
+      const int cnt = hi - max(0, hi - BR);
+      if (lane < cnt) {
+        unsigned char* raw = &sm.f[s][0][(lane & 7) * 16 + (lane >> 3) * SM::SBO];
+        unsigned char* lo = &sm.f[s][1][(lane & 7) * 16 + (lane >> 3) * SM::SBO];
+#pragma unroll
+        for (int cc = 0; cc < SM::KC; cc++) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (4 * cc < C) v = *reinterpret_cast<const float4*>(raw + cc * SM::LBO);
+          else *reinterpret_cast<float4*>(raw + cc * SM::LBO) = v;
+          *reinterpret_cast<float4*>(lo + cc * SM::LBO) = make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w));
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.ready_f[s]);
+    };
+    issue(0);
+    __syncthreads();  // (A)
+    for (int b = 0; b < nb; b++) {
+      if (b + 1 < nb) {
+        issue(b + 1);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      finalize(b);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == NWW) tmem_dealloc<BWD_TMEM_COLS>(tm);
+}
+
+template <int CP>
+static int launch_backward_tc_cp(cudaStream_t st, dim3 grid, const OcrfShape* sh, const uint2* ranges, const Record* rec,
+                                 const float* colors, const float* bg, const float* fT, const uint32_t* nc,
+                                 const uint32_t* mc, const float* dL_dcolor, const float* dL_dopa, double* ggrad,
+                                 float* dL_dcolors) {
+  const size_t dyn = sizeof(BwdSmem<CP>);
+  static int configured[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 64 && !configured[dev]) {
+    cudaError_t e = cudaFuncSetAttribute(render_backward_tc_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return (int)e;
+    configured[dev] = 1;
+  }
+  OCRF_LAUNCH(render_backward_tc_kernel<CP>, dim3(grid), dim3(BWD_THREADS), dyn, st, sh->W, sh->H, sh->C, sh->P,
+              sh->views_per_sample, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopa, ggrad, dL_dcolors);
+  return 0;
+}
+
+int launch_backward_tc(cudaStream_t st, dim3 grid, const OcrfShape* sh, const uint2* ranges, const Record* rec,
+                       const float* colors, const float* bg, const float* fT, const uint32_t* nc, const uint32_t* mc,
+                       const float* dL_dcolor, const float* dL_dopa, double* ggrad, float* dL_dcolors) {
+  if (sh->C <= 48) return launch_backward_tc_cp<48>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopa, ggrad, dL_dcolors);
+  if (sh->C <= 64) return launch_backward_tc_cp<64>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopa, ggrad, dL_dcolors);
+  return launch_backward_tc_cp<80>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopa, ggrad, dL_dcolors);
+}
+
+}  // namespace tc
+}  // namespace ocrf
