@@ -105,9 +105,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
     const int nc = inside ? (int)n_contrib[view * HW + pix] : 0;
     const int mb = warp >> 2;
     const uint32_t lane_addr = tm + ((uint32_t)((warp & 3) * 32) << 16);
-    // this pixel's upstream gradient: to tensor memory (g, g_lo) and to the shared tile the mma.sync product reads
+    // this pixel's upstream gradient: to tensor memory (g, g_lo) and to the shared tile the mma.sync product reads.
+    // All loads are issued before the first store: one memory round trip for the row instead of one per 16 channels.
     float bgdot = 0.f;
     {
+      float gv[CP];
+#pragma unroll
+      for (int k = 0; k < CP; k++) gv[k] = (inside && k < C) ? dL_dpix[((size_t)view * C + k) * HW + pix] : 0.f;
       float* grow = &sm.g[warp][lane][0];
 #pragma unroll
       for (int c0 = 0; c0 < CP; c0 += 16) {
@@ -115,15 +119,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
 #pragma unroll
         for (int i = 0; i < 16; i++) {
           const int k = c0 + i;
-          const float gv = (inside && k < C) ? dL_dpix[((size_t)view * C + k) * HW + pix] : 0.f;
-          bgdot += (k < C ? bg[k] : 0.f) * gv;
-          raw[i] = __float_as_uint(gv);
-          lo[i] = __float_as_uint(tf32_lo(gv));
+          bgdot += (k < C ? bg[k] : 0.f) * gv[k];
+          raw[i] = __float_as_uint(gv[k]);
+          lo[i] = __float_as_uint(tf32_lo(gv[k]));
         }
 #pragma unroll
         for (int i = 0; i < 16; i += 4)
-          *reinterpret_cast<float4*>(grow + c0 + i) = make_float4(__uint_as_float(raw[i]), __uint_as_float(raw[i + 1]),
-                                                                  __uint_as_float(raw[i + 2]), __uint_as_float(raw[i + 3]));
+          *reinterpret_cast<float4*>(grow + c0 + i) = make_float4(gv[c0 + i], gv[c0 + i + 1], gv[c0 + i + 2], gv[c0 + i + 3]);
         tmem_st16(lane_addr + mb * 2 * CP + c0, raw);
         tmem_st16(lane_addr + mb * 2 * CP + CP + c0, lo);
       }
@@ -147,107 +149,139 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
       mbar_wait_wd(&sm.ready_f[s], use & 1);
       mbar_wait_wd(&sm.ready_d[s], use & 1);
       fence_after_sync();
-      uint32_t d[BR];
-      {
-        uint32_t d0[16], d1[16];
-        tmem_ld16(lane_addr + D_COL0 + s * 64 + mb * 32, d0);
-        tmem_ld16(lane_addr + D_COL0 + s * 64 + mb * 32 + 16, d1);
-        tmem_wait_ld();
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          d[i] = d0[i];
-          d[16 + i] = d1[i];
-        }
-      }
-      fence_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.free_d[s]);
       uint32_t touched = 0;
+      // Two groups of 16 records, back to front.  Inside a group the work is laid out for instruction-level
+      // parallelism (one CTA per SM: there are only two warps per scheduler to hide latency with):
+      //   phase A  alpha, G, 1 / (1 - alpha) of eight records: independent of each other
+      //   phase B  the recurrences (T, the colour dot product accumulated behind): a short dependent chain
+      //   phase C  the geometry gradients of four records at a time, their four butterflies interleaved
+#pragma unroll 1
+      for (int grp = 1; grp >= 0; grp--) {
+        const int j0 = grp * FB;
+        if (j0 >= cnt) continue;  // (CTA-uniform)
+        uint32_t d[FB];
+        tmem_ld16(lane_addr + D_COL0 + s * 64 + mb * 32 + j0, d);
+        tmem_wait_ld();
+        if (grp == 0) {  // the last read of this D1 buffer: the MMA warp may overwrite it
+          fence_before_sync();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sm.free_d[s]);
+        }
 #pragma unroll
-      for (int j = BR - 1; j >= 0; j--) {
-        if (j < cnt) {
-          const float4 a = reinterpret_cast<const float4*>(&sm.rec[s][j])[0];
-          const float4 bq = reinterpret_cast<const float4*>(&sm.rec[s][j])[1];
-          const float dx = a.x - fx, dy = a.y - fy;
-          const float power = a.z * dx * dx + bq.x * dy * dy + a.w * dx * dy;  // log2 domain (scaled conic)
-          const float G = ex2_approx_b(power);
-          const float alpha = fminf(0.99f, bq.y * G);
-          const bool ok = (int)__float_as_uint(bq.z) <= nc && power <= 0.0f && alpha >= 1.0f / 255.0f;
-          float rcp = 1.f, w = 0.f, al = 0.f;
-          if (ok) {
-            rcp = __fdividef(1.f, 1.f - alpha);
-            T *= rcp;
-            w = alpha * T;
-            al = alpha;
+        for (int h = 1; h >= 0; h--) {
+          float Gv[8], al[8], rc[8], dxv[8], dyv[8], dLa[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const int j = j0 + h * 8 + i;
+            const float4 a = reinterpret_cast<const float4*>(&sm.rec[s][j])[0];
+            const float4 bq = reinterpret_cast<const float4*>(&sm.rec[s][j])[1];
+            const float dx = a.x - fx, dy = a.y - fy;
+            const float power = a.z * dx * dx + bq.x * dy * dy + a.w * dx * dy;  // log2 domain (scaled conic)
+            const float G = ex2_approx_b(power);
+            const float alpha = fminf(0.99f, bq.y * G);
+            const bool ok = j < cnt && (int)__float_as_uint(bq.z) <= nc && power <= 0.0f && alpha >= 1.0f / 255.0f;
+            const float r = __fdividef(1.f, 1.f - alpha);
+            Gv[i] = ok ? G : 0.f;  // (a garbage row past the end of the list must not put a NaN into the sums)
+            al[i] = ok ? alpha : 0.f;
+            rc[i] = ok ? r : 1.f;
+            dxv[i] = dx;
+            dyv[i] = dy;
           }
-          my_w[(j & (FB - 1)) * WP] = w;  // column `lane` of the warp's w^T tile (0 for a pixel that did not blend)
-          if (__any_sync(0xffffffffu, ok)) {
-            const float dot = __uint_as_float(d[j]) - S;
-            S = fmaf(al, dot, S);  // lanes that did not blend have al = 0
-            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-            if (ok) {
-              const float dL_dalpha = dot * T + gob * rcp;
+#pragma unroll
+          for (int i = 7; i >= 0; i--) {
+            T *= rc[i];
+            const float w = al[i] * T;
+            my_w[(h * 8 + i) * WP] = w;  // column `lane` of the warp's w^T tile (0 for a pixel that did not blend)
+            // (columns past the end of the list hold whatever the tensor core made of stale rows: never let them in)
+            const float dot = al[i] > 0.f ? __uint_as_float(d[h * 8 + i]) - S : 0.f;
+            S = fmaf(al[i], dot, S);
+            dLa[i] = dot * T + gob * rc[i];
+          }
+#pragma unroll
+          for (int qd = 1; qd >= 0; qd--) {
+            uint32_t m[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) m[e] = __ballot_sync(0xffffffffu, al[qd * 4 + e] > 0.f);
+            if ((m[0] | m[1] | m[2] | m[3]) == 0u) continue;  // nobody in the warp blended any of the four
+            float v[4][8];
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+              const int i = qd * 4 + e;
+              const int j = j0 + h * 8 + i;
+              const float4 a = reinterpret_cast<const float4*>(&sm.rec[s][j])[0];
+              const float2 bq = reinterpret_cast<const float2*>(&sm.rec[s][j])[2];  // qc, opacity
+              const bool ok = al[i] > 0.f;
+              const float dL_dalpha = ok ? dLa[i] : 0.f;
               const float dL_dG = bq.y * dL_dalpha;
-              const float gdx = G * dx, gdy = G * dy;
+              const float gdx = Gv[i] * dxv[i], gdy = Gv[i] * dyv[i];
               // conic recovered from the scaled record: A = -2 ln2 qa, B = -ln2 qb, C = -2 ln2 qc
-              v[0] = dL_dG * (LN2 * (2.f * gdx * a.z + gdy * a.w)) * ddelx_dx;
-              v[1] = dL_dG * (LN2 * (2.f * gdy * bq.x + gdx * a.w)) * ddely_dy;
-              v[2] = -0.5f * gdx * dx * dL_dG;
-              v[3] = -0.5f * gdx * dy * dL_dG;
-              v[4] = -0.5f * gdy * dy * dL_dG;
-              v[5] = G * dL_dalpha;
+              v[e][0] = dL_dG * (LN2 * (2.f * gdx * a.z + gdy * a.w)) * ddelx_dx;
+              v[e][1] = dL_dG * (LN2 * (2.f * gdy * bq.x + gdx * a.w)) * ddely_dy;
+              v[e][2] = -0.5f * gdx * dxv[i] * dL_dG;
+              v[e][3] = -0.5f * gdx * dyv[i] * dL_dG;
+              v[e][4] = -0.5f * gdy * dyv[i] * dL_dG;
+              v[e][5] = Gv[i] * dL_dalpha;
+              v[e][6] = 0.f;
+              v[e][7] = 0.f;
             }
-            const float r8 = butterfly8(v, lane);
-            if ((lane & 3) == 0) sm.acc[warp][j][lane >> 2] = r8;
-            touched |= 1u << j;
-          }
-          if ((j & (FB - 1)) == 0) {
-            // ---- records [j, j + FB) are complete in every warp: one reduction over the warps per channel ----
-            __syncwarp();
-            {  // this warp's partial dF[16 records][CP] = w^T[16 x 32 px] . g[32 px x CP] (3xTF32 mma.sync)
-              const int gid = lane >> 2, tig = lane & 3;
-              const float* wt = &sm.w[warp][0][0];
-              const float* gt = &sm.g[warp][0][0];
-              float cacc[CP / 8][4];
+            float r8[4];
 #pragma unroll
-              for (int nt = 0; nt < CP / 8; nt++) cacc[nt][0] = cacc[nt][1] = cacc[nt][2] = cacc[nt][3] = 0.f;
+            for (int e = 0; e < 4; e++) r8[e] = butterfly8(v[e], lane);
 #pragma unroll
-              for (int ks = 0; ks < 4; ks++) {
-                uint32_t ahi[4], alo[4];
-                split_tf32(wt[gid * WP + 8 * ks + tig], ahi[0], alo[0]);
-                split_tf32(wt[(gid + 8) * WP + 8 * ks + tig], ahi[1], alo[1]);
-                split_tf32(wt[gid * WP + 8 * ks + tig + 4], ahi[2], alo[2]);
-                split_tf32(wt[(gid + 8) * WP + 8 * ks + tig + 4], ahi[3], alo[3]);
-#pragma unroll
-                for (int nt = 0; nt < CP / 8; nt++) {
-                  uint32_t bhi[2], blo[2];
-                  split_tf32(gt[(8 * ks + tig) * GP + 8 * nt + gid], bhi[0], blo[0]);
-                  split_tf32(gt[(8 * ks + tig + 4) * GP + 8 * nt + gid], bhi[1], blo[1]);
-                  mma_tf32_16x8x8(cacc[nt], alo, bhi);
-                  mma_tf32_16x8x8(cacc[nt], ahi, blo);
-                  mma_tf32_16x8x8(cacc[nt], ahi, bhi);
-                }
-              }
-              float* fo = &sm.facc[warp][0][0];
-#pragma unroll
-              for (int nt = 0; nt < CP / 8; nt++) {
-                *reinterpret_cast<float2*>(fo + gid * CP + 8 * nt + 2 * tig) = make_float2(cacc[nt][0], cacc[nt][1]);
-                *reinterpret_cast<float2*>(fo + (gid + 8) * CP + 8 * nt + 2 * tig) = make_float2(cacc[nt][2], cacc[nt][3]);
+            for (int e = 0; e < 4; e++) {
+              const int jl = j0 + h * 8 + qd * 4 + e;
+              if (m[e]) {
+                if ((lane & 3) == 0) sm.acc[warp][jl][lane >> 2] = r8[e];
+                touched |= 1u << jl;
               }
             }
-            worker_bar();
-            for (int e = tid; e < FB * CP; e += TILE_PIX) {
-              const int jj = e / CP, ch = e - jj * CP;
-              const int rj = j + jj;
-              if (rj >= cnt || ch >= C) continue;  // (rows past the end of the block hold stale weights)
-              float tot = 0.f;
-#pragma unroll
-              for (int w2 = 0; w2 < NWW; w2++) tot += sm.facc[w2][jj][ch];
-              if (tot != 0.f) atomicAdd(gfbase + (size_t)sm.rec[s][rj].id * C + ch, tot);
-            }
-            worker_bar();
           }
         }
+        // ---- records [j0, j0 + FB) are complete in every warp: one reduction over the warps per channel ----
+        __syncwarp();
+        {  // this warp's partial dF[16 records][CP] = w^T[16 x 32 px] . g[32 px x CP] (3xTF32 mma.sync,
+           // operands rounded with cvt.rna: raw fp32 patterns as "hi" did not keep the 1e-4 bar on this path)
+          const int gid = lane >> 2, tig = lane & 3;
+          const float* wt = &sm.w[warp][0][0];
+          const float* gt = &sm.g[warp][0][0];
+          float cacc[CP / 8][4];
+#pragma unroll
+          for (int nt = 0; nt < CP / 8; nt++) cacc[nt][0] = cacc[nt][1] = cacc[nt][2] = cacc[nt][3] = 0.f;
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {
+            uint32_t ahi[4], alo[4];
+            split_tf32(wt[gid * WP + 8 * ks + tig], ahi[0], alo[0]);
+            split_tf32(wt[(gid + 8) * WP + 8 * ks + tig], ahi[1], alo[1]);
+            split_tf32(wt[gid * WP + 8 * ks + tig + 4], ahi[2], alo[2]);
+            split_tf32(wt[(gid + 8) * WP + 8 * ks + tig + 4], ahi[3], alo[3]);
+#pragma unroll
+            for (int nt = 0; nt < CP / 8; nt++) {
+              uint32_t bhi[2], blo[2];
+              split_tf32(gt[(8 * ks + tig) * GP + 8 * nt + gid], bhi[0], blo[0]);
+              split_tf32(gt[(8 * ks + tig + 4) * GP + 8 * nt + gid], bhi[1], blo[1]);
+              mma_tf32_16x8x8(cacc[nt], alo, bhi);
+              mma_tf32_16x8x8(cacc[nt], ahi, blo);
+              mma_tf32_16x8x8(cacc[nt], ahi, bhi);
+            }
+          }
+          float* fo = &sm.facc[warp][0][0];
+#pragma unroll
+          for (int nt = 0; nt < CP / 8; nt++) {
+            *reinterpret_cast<float2*>(fo + gid * CP + 8 * nt + 2 * tig) = make_float2(cacc[nt][0], cacc[nt][1]);
+            *reinterpret_cast<float2*>(fo + (gid + 8) * CP + 8 * nt + 2 * tig) = make_float2(cacc[nt][2], cacc[nt][3]);
+          }
+        }
+        worker_bar();
+        for (int e = tid; e < FB * CP; e += TILE_PIX) {
+          const int jj = e / CP, ch = e - jj * CP;
+          const int rj = j0 + jj;
+          if (rj >= cnt || ch >= C) continue;
+          float tot = 0.f;
+#pragma unroll
+          for (int w2 = 0; w2 < NWW; w2++) tot += sm.facc[w2][jj][ch];
+          if (tot != 0.f) atomicAdd(gfbase + (size_t)sm.rec[s][rj].id * C + ch, tot);
+        }
+        worker_bar();
       }
       if (lane == 0) sm.touched[warp] = touched;
       worker_bar();
