@@ -250,15 +250,15 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
 #pragma unroll
           for (int ks = 0; ks < 4; ks++) {
             uint32_t ahi[4], alo[4];
-            split_tf32(wt[gid * WP + 8 * ks + tig], ahi[0], alo[0]);
-            split_tf32(wt[(gid + 8) * WP + 8 * ks + tig], ahi[1], alo[1]);
-            split_tf32(wt[gid * WP + 8 * ks + tig + 4], ahi[2], alo[2]);
-            split_tf32(wt[(gid + 8) * WP + 8 * ks + tig + 4], ahi[3], alo[3]);
+            split_trunc(wt[gid * WP + 8 * ks + tig], ahi[0], alo[0]);
+            split_trunc(wt[(gid + 8) * WP + 8 * ks + tig], ahi[1], alo[1]);
+            split_trunc(wt[gid * WP + 8 * ks + tig + 4], ahi[2], alo[2]);
+            split_trunc(wt[(gid + 8) * WP + 8 * ks + tig + 4], ahi[3], alo[3]);
 #pragma unroll
             for (int nt = 0; nt < CP / 8; nt++) {
               uint32_t bhi[2], blo[2];
-              split_tf32(gt[(8 * ks + tig) * GP + 8 * nt + gid], bhi[0], blo[0]);
-              split_tf32(gt[(8 * ks + tig + 4) * GP + 8 * nt + gid], bhi[1], blo[1]);
+              split_trunc(gt[(8 * ks + tig) * GP + 8 * nt + gid], bhi[0], blo[0]);
+              split_trunc(gt[(8 * ks + tig + 4) * GP + 8 * nt + gid], bhi[1], blo[1]);
               mma_tf32_16x8x8(cacc[nt], alo, bhi);
               mma_tf32_16x8x8(cacc[nt], ahi, blo);
               mma_tf32_16x8x8(cacc[nt], ahi, bhi);
