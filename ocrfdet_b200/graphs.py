@@ -11,6 +11,9 @@ Usage:
     step = GraphedRenderStep(S=1, P=100_000, cams=cams, height=256, width=704, channels=3, pair_capacity=5_000_000)
     outs, grads = step(means3D=..., scales=..., rotations=..., opacities=..., colors=..., grad_color=..., grad_opacity=...)
     step.check_overflow()     # after any number of replays: raises if a replay needed more than pair_capacity pairs
+`pre` / `post` hooks are captured with the step (host <-> device copies of pinned buffers, a loss): `step.graph.replay()`
+is then a complete host-to-host step; two instances replayed on two streams overlap the copies of one step with the
+kernels of the other (bench.py's `e2e`).
 """
 import torch
 
@@ -20,7 +23,8 @@ INPUTS = ("means3D", "scales", "rotations", "opacities", "colors")
 
 
 class GraphedRenderStep:
-    def __init__(self, S, P, cams, height, width, channels=3, pair_capacity=None, bg=None, binning=None, device="cuda"):
+    def __init__(self, S, P, cams, height, width, channels=3, pair_capacity=None, bg=None, binning=None, device="cuda",
+                 pre=None, post=None):
         if pair_capacity is None:
             raise ValueError("a captured step needs a fixed pair_capacity (exact sizing reads the pair count on the host)")
         self.S, self.P, self.H, self.W, self.C = int(S), int(P), int(height), int(width), int(channels)
@@ -34,18 +38,29 @@ class GraphedRenderStep:
         self.static_in = {k: torch.zeros(v, device=dev).requires_grad_(True) for k, v in shapes.items()}
         self.static_gcolor = torch.zeros(self.V, self.C, self.H, self.W, device=dev)
         self.static_gopac = torch.zeros(self.V, 1, self.H, self.W, device=dev)
+        # optional hooks captured WITH the step: pre(step) runs before the forward (e.g. non-blocking copies of pinned
+        # host parameters into `static_in`), post(step, outs, grads) after the backward (e.g. the loss and non-blocking
+        # copies of the gradients into pinned host buffers): a whole host-to-host training step is then ONE launch
+        self.pre, self.post = pre, post
         self.graph = None
         self.outs = None
         self.grads = None
 
     def _step(self):
         t = self.static_in
+        if self.pre is not None:
+            with torch.no_grad():
+                self.pre(self)
         color, radii, depth, opac = R.render_batch(t["means3D"], t["opacities"], self.cams, self.H, self.W, self.bg,
                                                    colors_precomp=t["colors"], scales=t["scales"],
                                                    rotations=t["rotations"], pair_capacity=self.capacity,
                                                    binning=self.binning)
         grads = torch.autograd.grad([color, opac], [t[k] for k in INPUTS], [self.static_gcolor, self.static_gopac])
-        return (color, radii, depth, opac), dict(zip(INPUTS, grads))
+        outs, grads = (color, radii, depth, opac), dict(zip(INPUTS, grads))
+        if self.post is not None:
+            with torch.no_grad():
+                self.post(self, outs, grads)
+        return outs, grads
 
     def capture(self, **example):
         """Fill the static buffers with `example` (representative inputs: they only serve as warm-up), run the step a
