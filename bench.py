@@ -665,6 +665,20 @@ def run_ours(args, rank, world, device):
                               "kernels": "render_forward_tc_kernel<80> / render_backward_tc_kernel<80> (tcgen05.mma kind::tf32)"}
         except Exception as e:  # never lose the headline line to the extra measurement
             out["config4"] = {"error": repr(e)[:200]}
+        # stage 5 (the height-aware opacity lift and the voxel-to-BEV converter) per sample against a torch
+        # formulation of the same modules on this GPU (tools/hoa_bench.py: agreement checked first, then timed)
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import hoa_bench
+            torch.cuda.empty_cache()
+            r = hoa_bench.run(1)
+            out["hoa_lift"] = {"samples": 1, "unit": "ms per call (forward + backward)",
+                               "lift_ours": r["ms"]["lift_fwdbwd_ours"], "lift_torch": r["ms"]["lift_fwdbwd_torch"],
+                               "converter_ours": r["ms"]["conv_fwdbwd_ours"], "converter_torch": r["ms"]["conv_fwdbwd_torch"],
+                               "forward_only": {k: r["ms"][k] for k in ("lift_fwd_ours", "lift_fwd_torch", "conv_fwd_ours", "conv_fwd_torch")},
+                               "agreement": r["agreement"]}
+        except Exception as e:
+            out["hoa_lift"] = {"error": repr(e)[:200]}
     return out
 
 

@@ -159,15 +159,23 @@ __global__ void __cluster_dims__(VS_CLUSTER, 1, 1) __launch_bounds__(VS_THREADS)
 #pragma unroll
       for (int i = 0; i < VS_ITEMS; i++) {
         const uint32_t loc = warp_base + i * 32 + lane;
-        if (loc < n_valid) {
+        const bool valid = loc < n_valid;
+        uint32_t slot = 0xffff0000u + lane;  // (owner, next digit) of my key; unique for an invalid lane
+        if (valid) {
           const uint32_t d = (uint32_t)(key[i] >> shift) & 255u;
           const uint32_t pos = s_base[d] + my_hist[d] + rk[i];
           dst_k[pos] = key[i];
           dst_v[pos] = val[i];
-          if (pass < 3) {  // (3) the next pass's digit of this key, counted where the key now lives
-            const uint32_t owner = min((pos - seg_b) / per, (uint32_t)VS_CLUSTER - 1);
-            dsmem_add_u32(cluster.map_shared_rank(&hist_next[(uint32_t)(key[i] >> (shift + 8)) & 255u], owner), 1u);
-          }
+          const uint32_t owner = min((pos - seg_b) / per, (uint32_t)VS_CLUSTER - 1);
+          slot = (owner << 8) | ((uint32_t)(key[i] >> (shift + 8)) & 255u);
+        }
+        if (pass < 3) {
+          // (3) the next pass's digit of this key, counted where the key now lives.  The high bytes of a depth take a
+          // handful of values, so unaggregated every key of the view would hit the same few remote counters: the
+          // lanes of a warp that share (owner, digit) send ONE remote reduction
+          const uint32_t same = __match_any_sync(0xffffffffu, slot);
+          if (valid && (same & lt_mask) == 0)
+            dsmem_add_u32(cluster.map_shared_rank(&hist_next[slot & 255u], slot >> 8), (uint32_t)__popc(same));
         }
       }
       __syncthreads();

@@ -267,31 +267,50 @@ class OpacityVoxelToBEVConverter(_PackedModule):
             raise ValueError("the fused converter implements OcRFDet's 13 height planes")
         _, init = _converter_layout_and_init()
         self.packed = nn.Parameter(pack_parameters(init, CONVERTER_PARAMS))
-        for name, _cin, cout in BLOCKS:  # buffer names: "__" stands for "." (state_dict keys are the reference's)
-            self.register_buffer("%s__2__running_mean" % name, torch.zeros(cout))
-            self.register_buffer("%s__2__running_var" % name, torch.ones(cout))
-            self.register_buffer("%s__2__num_batches_tracked" % name, torch.tensor(0, dtype=torch.long))
+        # batch-norm buffers of the five blocks, packed [block, channel] as the kernels read them (one module call is
+        # one kernel chain plus a handful of vector ops, not fifty tiny launches); state_dict keys are the reference's
+        self.register_buffer("bn_mean", torch.zeros(5, 16), persistent=False)
+        self.register_buffer("bn_var", torch.ones(5, 16), persistent=False)
+        self.register_buffer("bn_batches", torch.zeros(5, dtype=torch.long), persistent=False)
+        mask = torch.zeros(5, 16)
+        for i, (_name, _cin, cout) in enumerate(BLOCKS):
+            mask[i, :cout] = 1.0
+        self.register_buffer("bn_mask", mask, persistent=False)
 
-    def _running(self):
-        mean = torch.zeros((5, 16), dtype=torch.float32, device=self.packed.device)
-        var = torch.ones((5, 16), dtype=torch.float32, device=self.packed.device)
+    def _save_to_state_dict(self, destination, prefix, keep_vars):
+        for name, t in self.reference_parameters().items():
+            destination[prefix + name] = t.clone()
         for i, (name, _cin, cout) in enumerate(BLOCKS):
-            mean[i, :cout] = getattr(self, "%s__2__running_mean" % name)
-            var[i, :cout] = getattr(self, "%s__2__running_var" % name)
-        return mean, var
+            destination[prefix + name + ".2.running_mean"] = self.bn_mean[i, :cout].clone()
+            destination[prefix + name + ".2.running_var"] = self.bn_var[i, :cout].clone()
+            destination[prefix + name + ".2.num_batches_tracked"] = self.bn_batches[i].clone()
+
+    def _load_from_state_dict(self, state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs):
+        saved, self._buffers = self._buffers, type(self._buffers)()  # the base class handles the parameters only
+        try:
+            super()._load_from_state_dict(state_dict, prefix, local_metadata, strict, missing_keys, unexpected_keys, error_msgs)
+        finally:
+            self._buffers = saved
+        for i, (name, _cin, cout) in enumerate(BLOCKS):
+            for key, dst in ((".2.running_mean", self.bn_mean[i, :cout]), (".2.running_var", self.bn_var[i, :cout]),
+                             (".2.num_batches_tracked", self.bn_batches[i])):
+                k = prefix + name + key
+                if k in state_dict:
+                    dst.copy_(state_dict[k])
+                elif strict:
+                    missing_keys.append(k)
 
     def forward(self, x, position):
-        mean, var = self._running()
+        # (training mode updates the buffers in place below; the autograd node keeps what the forward saw)
+        mean, var = (self.bn_mean.clone(), self.bn_var.clone()) if self.training else (self.bn_mean, self.bn_var)
         out, stats = _ConverterFn.apply(x, position, self.packed, mean, var, self.training)
         if self.training:
             with torch.no_grad():  # nn.BatchNorm2d: momentum 0.1, running_var from the unbiased batch variance
                 B, _, S, _ = x.shape
-                for i, (name, _cin, cout) in enumerate(BLOCKS):
-                    shift = (0, 1, 2, 1, 0)[i]
-                    n = float(B * (S >> shift) * (S >> shift))
-                    m = stats[i, :cout, 0] / n
-                    v = (stats[i, :cout, 1] / n - m * m).clamp_min(0.0) * (n / max(n - 1.0, 1.0))
-                    getattr(self, "%s__2__running_mean" % name).mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * m)
-                    getattr(self, "%s__2__running_var" % name).mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * v)
-                    getattr(self, "%s__2__num_batches_tracked" % name).add_(1)
+                n = torch.tensor([float(B * (S >> sh) * (S >> sh)) for sh in (0, 1, 2, 1, 0)], device=stats.device)[:, None]
+                m = stats[:, :, 0] / n
+                v = (stats[:, :, 1] / n - m * m).clamp_min_(0.0) * (n / (n - 1.0).clamp_min(1.0))
+                self.bn_mean.mul_(1 - BN_MOMENTUM).add_(BN_MOMENTUM * m * self.bn_mask)
+                self.bn_var.lerp_(torch.where(self.bn_mask > 0, v, self.bn_var), BN_MOMENTUM)
+                self.bn_batches.add_(1)
         return out

@@ -59,3 +59,42 @@ def test_graphed_step_reports_overflow():
         step.check_overflow()
     with pytest.raises(ValueError):
         GraphedRenderStep(S=1, P=P, cams=util.cams_tensor(cams), height=H, width=W)
+
+
+def test_graphed_step_with_captured_host_copies_is_a_host_to_host_step():
+    """`pre` / `post` hooks: pinned host parameters in, gradients out, ONE graph launch (what bench.py's `e2e` times)."""
+    from ocrfdet_b200 import rasterizer as R
+    from ocrfdet_b200.graphs import GraphedRenderStep, INPUTS
+    W, H, P, V = 176, 64, 6000, 3
+    g, cams = util.small_scene("ring", P=P, seed=43, W=W, H=H, n_views=V)
+    cam_t = util.cams_tensor(cams)
+    host = {k: torch.from_numpy(g[k]).unsqueeze(0).contiguous().pin_memory() for k in INPUTS}
+    ghost = {k: torch.zeros_like(host[k]).pin_memory() for k in INPUTS}
+    gcol = torch.randn(V, 3, H, W, device="cuda")
+    gop = torch.randn(V, 1, H, W, device="cuda")
+
+    def pre(st):
+        for k in INPUTS:
+            st.static_in[k].copy_(host[k], non_blocking=True)
+
+    def post(st, outs, grads):
+        for k in INPUTS:
+            ghost[k].copy_(grads[k], non_blocking=True)
+
+    step = GraphedRenderStep(S=1, P=P, cams=cam_t, height=H, width=W, channels=3, pair_capacity=600_000, pre=pre, post=post)
+    step.capture(grad_color=gcol, grad_opacity=gop)
+    # new host data AFTER the capture: the replay must pick it up from the same pinned buffers
+    g2, _ = util.small_scene("ring", P=P, seed=44, W=W, H=H, n_views=V)
+    for k in INPUTS:
+        host[k].copy_(torch.from_numpy(g2[k]).unsqueeze(0))
+        ghost[k].zero_()
+    step.graph.replay()
+    torch.cuda.synchronize()
+    step.check_overflow()
+    leaf = {k: host[k].cuda().requires_grad_(True) for k in INPUTS}
+    color, radii, depth, opac = R.render_batch(leaf["means3D"], leaf["opacities"], cam_t, H, W, torch.zeros(3, device="cuda"),
+                                               colors_precomp=leaf["colors"], scales=leaf["scales"], rotations=leaf["rotations"])
+    torch.autograd.backward([color, opac], [gcol, gop])
+    assert torch.equal(step.outs[0], color)
+    for k in INPUTS:
+        assert util.rel_err(ghost[k].numpy(), leaf[k].grad.cpu().numpy()) <= 1e-6, k
