@@ -38,12 +38,13 @@ struct BwdSmem {
   static constexpr int GP = CP + 8;             // g row pitch (== 8 mod 16: conflict-free B fragments)
   alignas(128) unsigned char f[2][2][PART];     // [stage][raw | lo]
   alignas(128) Record rec[2][BR];
-  alignas(16) float acc[NWW][BR][8];
+  alignas(16) float macc[NWW][FB][8];   // per-warp partial moments of a group of 16 records
+  alignas(16) float mom[BR][8];         // moments of the block's records, summed over the warps
   alignas(16) float facc[NWW][FB][CP];
   alignas(16) float g[NWW][32][GP];
   alignas(16) float w[NWW][FB][WP];
+  alignas(16) float t[NWW][FB][WP];     // t = G * dL/dalpha per (record, pixel): the operand of the moment product
   alignas(8) uint64_t ready_f[2], free_f[2], ready_d[2], free_d[2];
-  uint32_t touched[NWW];
   uint32_t tmem;
 };
 
@@ -135,6 +136,18 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
     __syncthreads();  // (A) G is in tensor memory: the MMA warp may start
     float S = 0.f;    // g . (colour accumulated behind this pixel), see render_backward_generic_kernel
     float* my_w = &sm.w[warp][0][lane];
+    float* my_t = &sm.t[warp][0][lane];
+    // B fragments of the moment product: monomial (lane >> 2) of the local coordinates of pixels 8 ks + (lane & 3) (+ 4)
+    float bmono[8];
+    {
+      const int gid = lane >> 2, tig = lane & 3;
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        const int q = 8 * (e >> 1) + tig + 4 * (e & 1);  // warp-local pixel = the lane that owns it
+        const float lx = (float)((warp & 1) * 8 + (q & 7)) - 7.5f, ly = (float)((warp >> 1) * 4 + (q >> 3)) - 7.5f;
+        bmono[e] = gid == 0 ? 1.f : gid == 1 ? lx : gid == 2 ? ly : gid == 3 ? lx * lx : gid == 4 ? lx * ly : gid == 5 ? ly * ly : 0.f;
+      }
+    }
     const float gop = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
     const float gob = Tf * (gop - bgdot);
     float T = Tf;
@@ -149,12 +162,12 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
       mbar_wait_wd(&sm.ready_f[s], use & 1);
       mbar_wait_wd(&sm.ready_d[s], use & 1);
       fence_after_sync();
-      uint32_t touched = 0;
       // Two groups of 16 records, back to front.  Inside a group the work is laid out for instruction-level
       // parallelism (one CTA per SM: there are only two warps per scheduler to hide latency with):
       //   phase A  alpha, G, 1 / (1 - alpha) of eight records: independent of each other
       //   phase B  the recurrences (T, the colour dot product accumulated behind): a short dependent chain
-      //   phase C  the geometry gradients of four records at a time, their four butterflies interleaved
+      //   phase C  t = G dL/dalpha per record; the geometry gradients are six MOMENTS of t over the tile's pixels
+      //            (sum t, t x, t y, t x^2, t x y, t y^2 about the tile centre), i.e. one more small product t^T . M
 #pragma unroll 1
       for (int grp = 1; grp >= 0; grp--) {
         const int j0 = grp * FB;
@@ -169,7 +182,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
         }
 #pragma unroll
         for (int h = 1; h >= 0; h--) {
-          float Gv[8], al[8], rc[8], dxv[8], dyv[8], dLa[8];
+          float Gv[8], al[8], rc[8], dLa[8];
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             const int j = j0 + h * 8 + i;
@@ -184,8 +197,6 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
             Gv[i] = ok ? G : 0.f;  // (a garbage row past the end of the list must not put a NaN into the sums)
             al[i] = ok ? alpha : 0.f;
             rc[i] = ok ? r : 1.f;
-            dxv[i] = dx;
-            dyv[i] = dy;
           }
 #pragma unroll
           for (int i = 7; i >= 0; i--) {
@@ -197,50 +208,13 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
             S = fmaf(al[i], dot, S);
             dLa[i] = dot * T + gob * rc[i];
           }
+          // phase C: t = G dL/dalpha, the one per-(pixel, record) scalar every geometry gradient is linear in
 #pragma unroll
-          for (int qd = 1; qd >= 0; qd--) {
-            uint32_t m[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) m[e] = __ballot_sync(0xffffffffu, al[qd * 4 + e] > 0.f);
-            if ((m[0] | m[1] | m[2] | m[3]) == 0u) continue;  // nobody in the warp blended any of the four
-            float v[4][8];
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const int i = qd * 4 + e;
-              const int j = j0 + h * 8 + i;
-              const float4 a = reinterpret_cast<const float4*>(&sm.rec[s][j])[0];
-              const float2 bq = reinterpret_cast<const float2*>(&sm.rec[s][j])[2];  // qc, opacity
-              const bool ok = al[i] > 0.f;
-              const float dL_dalpha = ok ? dLa[i] : 0.f;
-              const float dL_dG = bq.y * dL_dalpha;
-              const float gdx = Gv[i] * dxv[i], gdy = Gv[i] * dyv[i];
-              // conic recovered from the scaled record: A = -2 ln2 qa, B = -ln2 qb, C = -2 ln2 qc
-              v[e][0] = dL_dG * (LN2 * (2.f * gdx * a.z + gdy * a.w)) * ddelx_dx;
-              v[e][1] = dL_dG * (LN2 * (2.f * gdy * bq.x + gdx * a.w)) * ddely_dy;
-              v[e][2] = -0.5f * gdx * dxv[i] * dL_dG;
-              v[e][3] = -0.5f * gdx * dyv[i] * dL_dG;
-              v[e][4] = -0.5f * gdy * dyv[i] * dL_dG;
-              v[e][5] = Gv[i] * dL_dalpha;
-              v[e][6] = 0.f;
-              v[e][7] = 0.f;
-            }
-            float r8[4];
-#pragma unroll
-            for (int e = 0; e < 4; e++) r8[e] = butterfly8(v[e], lane);
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-              const int jl = j0 + h * 8 + qd * 4 + e;
-              if (m[e]) {
-                if ((lane & 3) == 0) sm.acc[warp][jl][lane >> 2] = r8[e];
-                touched |= 1u << jl;
-              }
-            }
-          }
+          for (int i = 0; i < 8; i++) my_t[(h * 8 + i) * WP] = al[i] > 0.f ? Gv[i] * dLa[i] : 0.f;
         }
         // ---- records [j0, j0 + FB) are complete in every warp: one reduction over the warps per channel ----
         __syncwarp();
-        {  // this warp's partial dF[16 records][CP] = w^T[16 x 32 px] . g[32 px x CP] (3xTF32 mma.sync,
-           // operands rounded with cvt.rna: raw fp32 patterns as "hi" did not keep the 1e-4 bar on this path)
+        {  // this warp's partial dF[16 records][CP] = w^T[16 x 32 px] . g[32 px x CP] (3xTF32 mma.sync)
           const int gid = lane >> 2, tig = lane & 3;
           const float* wt = &sm.w[warp][0][0];
           const float* gt = &sm.g[warp][0][0];
@@ -270,8 +244,32 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
             *reinterpret_cast<float2*>(fo + gid * CP + 8 * nt + 2 * tig) = make_float2(cacc[nt][0], cacc[nt][1]);
             *reinterpret_cast<float2*>(fo + (gid + 8) * CP + 8 * nt + 2 * tig) = make_float2(cacc[nt][2], cacc[nt][3]);
           }
+          // this warp's partial moments [16 records][8] = t^T[16 x 32 px] . M[32 px x 8]; the monomials of the local
+          // pixel coordinates (multiples of 0.5 below 64) are exact in tf32: two products per k-step
+          const float* tt = &sm.t[warp][0][0];
+          float macc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++) {
+            uint32_t ahi[4], alo[4];
+            split_trunc(tt[gid * WP + 8 * ks + tig], ahi[0], alo[0]);
+            split_trunc(tt[(gid + 8) * WP + 8 * ks + tig], ahi[1], alo[1]);
+            split_trunc(tt[gid * WP + 8 * ks + tig + 4], ahi[2], alo[2]);
+            split_trunc(tt[(gid + 8) * WP + 8 * ks + tig + 4], ahi[3], alo[3]);
+            const uint32_t bm[2] = {__float_as_uint(bmono[2 * ks]), __float_as_uint(bmono[2 * ks + 1])};
+            mma_tf32_16x8x8(macc, alo, bm);
+            mma_tf32_16x8x8(macc, ahi, bm);
+          }
+          *reinterpret_cast<float2*>(&sm.macc[warp][gid][2 * tig]) = make_float2(macc[0], macc[1]);
+          *reinterpret_cast<float2*>(&sm.macc[warp][gid + 8][2 * tig]) = make_float2(macc[2], macc[3]);
         }
         worker_bar();
+        if (tid < FB * 8) {  // moments of the group's records, summed over the warps
+          const int jj = tid >> 3, m = tid & 7;
+          float tot = 0.f;
+#pragma unroll
+          for (int w2 = 0; w2 < NWW; w2++) tot += sm.macc[w2][jj][m];
+          sm.mom[j0 + jj][m] = tot;
+        }
         for (int e = tid; e < FB * CP; e += TILE_PIX) {
           const int jj = e / CP, ch = e - jj * CP;
           const int rj = j0 + jj;
@@ -283,27 +281,35 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
         }
         worker_bar();
       }
-      if (lane == 0) sm.touched[warp] = touched;
       worker_bar();
       if (tid < cnt) {
+        // one thread per record: the six geometry gradients from the moments (fp64: the combination cancels when the
+        // Gaussian sits far from the tile), ONE set of global reductions per record per tile
         const int j = tid;
-        float q[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        bool hit = false;
+        const float4 m03 = *reinterpret_cast<const float4*>(&sm.mom[j][0]);
+        const float2 m45 = *reinterpret_cast<const float2*>(&sm.mom[j][4]);
+        if (m03.x != 0.f || m03.y != 0.f || m03.z != 0.f || m03.w != 0.f || m45.x != 0.f || m45.y != 0.f) {
+          const Record rc_ = sm.rec[s][j];
+          const double M0 = m03.x, Mx = m03.y, My = m03.z, Mxx = m03.w, Mxy = m45.x, Myy = m45.y;
+          const double a = (double)rc_.x - ((double)(blockIdx.x * TILE) + 7.5), bb = (double)rc_.y - ((double)(blockIdx.y * TILE) + 7.5);
+          const double sdx = a * M0 - Mx, sdy = bb * M0 - My;
+          const double sxx = a * a * M0 - 2.0 * a * Mx + Mxx;
+          const double sxy = a * bb * M0 - a * My - bb * Mx + Mxy;
+          const double syy = bb * bb * M0 - 2.0 * bb * My + Myy;
+          const double op = rc_.op, qa = rc_.qa, qb = rc_.qb, qc = rc_.qc;
+          double q[6];
+          q[0] = op * (double)LN2 * (double)ddelx_dx * (2.0 * qa * sdx + qb * sdy);
+          q[1] = op * (double)LN2 * (double)ddely_dy * (2.0 * qc * sdy + qb * sdx);
+          q[2] = -0.5 * op * sxx;
+          q[3] = -0.5 * op * sxy;
+          q[4] = -0.5 * op * syy;
+          q[5] = M0;
+          double* gg = ggrad + ((size_t)view * P + rc_.id) * OCRF_GGRAD_STRIDE;
 #pragma unroll
-        for (int w2 = 0; w2 < NWW; w2++)
-          if ((sm.touched[w2] >> j) & 1u) {
-            hit = true;
-            const float4 q0 = *reinterpret_cast<const float4*>(&sm.acc[w2][j][0]);
-            const float2 q1 = *reinterpret_cast<const float2*>(&sm.acc[w2][j][4]);
-            q[0] += q0.x; q[1] += q0.y; q[2] += q0.z; q[3] += q0.w; q[4] += q1.x; q[5] += q1.y;
-          }
-        if (hit) {
-          double* gg = ggrad + ((size_t)view * P + sm.rec[s][j].id) * OCRF_GGRAD_STRIDE;
-#pragma unroll
-          for (int e = 0; e < 6; e++) atomicAdd(gg + e, (double)q[e]);
+          for (int e = 0; e < 6; e++) atomicAdd(gg + e, q[e]);
         }
       }
-      worker_bar();  // acc / touched / rec[s] are free again
+      worker_bar();  // mom / rec[s] are free again
       if (lane == 0) mbar_arrive(&sm.free_f[s]);
     }
   } else if (warp == NWW) {
