@@ -100,9 +100,14 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
     const float fx = (float)px, fy = (float)py;
     const int mb = warp >> 2;
     const uint32_t lane_addr = tm + ((uint32_t)((warp & 3) * 32) << 16);
-    bool done = !inside, reported = false;
-    float T = 1.f, D = 15.f;
-    uint32_t last = 0, lastc = 0;
+    // a finished (or out-of-image) pixel is a NaN row coordinate: its power is NaN, every comparison on it is false,
+    // so it needs no predicate of its own in the loop
+    const float qnan = __int_as_float(0x7fc00000);
+    float fyn = inside ? fy : qnan;
+    bool reported = false;
+    float T = 1.f;
+    uint32_t last_idx = 0, cross_idx = 0;  // 1-based positions in the culled list: last blended record / the record
+                                           // that took T across 0.5 (their `orig` and depth are fetched once, at the end)
     int b = 0;
     for (;; b++) {
       const int s = b % STAGES;
@@ -113,15 +118,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
       uint32_t wv[16];
 #pragma unroll
       for (int j = 0; j < 16; j++) wv[j] = 0u;
-      const bool warp_done = __all_sync(0xffffffffu, done);
+      const bool warp_done = __all_sync(0xffffffffu, fyn != fyn);
       if (!warp_done) {
         float al[KB];
         // phase 1: the eight alphas, independent of each other
 #pragma unroll
         for (int j = 0; j < KB; j++) {
           const float4 a = reinterpret_cast<const float4*>(&sm.rec[s][j])[0];
-          const float4 c = reinterpret_cast<const float4*>(&sm.rec[s][j])[1];
-          const float dx = a.x - fx, dy = a.y - fy;
+          const float2 c = reinterpret_cast<const float2*>(&sm.rec[s][j])[2];  // qc, opacity
+          const float dx = a.x - fx, dy = a.y - fyn;
           const float power = a.z * dx * dx + c.x * dy * dy + a.w * dx * dy;  // log2 domain (scaled conic)
           const float alpha = fminf(0.99f, c.y * ex2_approx_t(power));
           al[j] = (j < cnt && power <= 0.0f && alpha >= 1.0f / 255.0f) ? alpha : 0.f;
@@ -129,19 +134,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
         // phase 2: the transmittance recurrence (forward.cu:343-358: stop BEFORE blending once T would drop below 1e-4)
 #pragma unroll
         for (int j = 0; j < KB; j++) {
-          const bool ok = !done && al[j] > 0.f;
+          const bool ok = al[j] > 0.f && fyn == fyn;
           const float test_T = T * (1.f - al[j]);
           const bool blend = ok && test_T >= 0.0001f;
           const float w = blend ? al[j] * T : 0.f;
           wv[j] = __float_as_uint(w);
           wv[KB + j] = __float_as_uint(tf32_lo(w));
-          if (blend) {
-            if (T > 0.5f && test_T < 0.5f) D = sm.rec[s][j].depth;
-            T = test_T;
-            last = sm.rec[s][j].orig;
-            lastc = (uint32_t)(b * KB + j + 1);
-          }
-          done = done || (ok && !blend);
+          const uint32_t idx = (uint32_t)(b * KB + j + 1);
+          cross_idx = (blend && T > 0.5f && test_T < 0.5f) ? idx : cross_idx;
+          last_idx = blend ? idx : last_idx;
+          T = blend ? test_T : T;
+          fyn = (ok && !blend) ? qnan : fyn;
         }
       } else if (!reported) {
         if (lane == 0) atomicAdd(&sm.done_warps, 1u);
@@ -180,11 +183,11 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
     }
     if (inside) {
       final_T[view * HW + pix] = T;
-      n_contrib[view * HW + pix] = last;
-      if (out_depth) out_depth[view * HW + pix] = D;
+      n_contrib[view * HW + pix] = last_idx ? records[range.x + last_idx - 1].orig : 0u;
+      if (out_depth) out_depth[view * HW + pix] = cross_idx ? records[range.x + cross_idx - 1].depth : 15.f;
       if (out_opacity) out_opacity[view * HW + pix] = 1.f - T;
     }
-    const uint32_t my_max = __reduce_max_sync(0xffffffffu, lastc);
+    const uint32_t my_max = __reduce_max_sync(0xffffffffu, last_idx);
     if (lane == 0 && my_max) atomicMax(&sm.max_contrib, my_max);
   } else if (warp == WORKER_WARPS) {
     // ------------------------------------------------ MMA issuer ------------------------------------------------
@@ -267,10 +270,17 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
         const int cc = q + 4 * i;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (valid && 4 * cc < C) v = *reinterpret_cast<const float4*>(&sm.land_f[slot][r][4 * cc]);
-        const float e[4] = {v.x, v.y, v.z, v.w};
+        // transposing store: element k of the chunk goes to channel row 4 cc + k.  Lanes that differ only in r >> 2 or
+        // q >> 1 would hit the same bank (their targets are 128 / 256 bytes apart), so every lane starts its four
+        // elements at a different k: rot = (r >> 2) + 2 (q >> 1) -> 32 distinct banks per store
+        const int rot = (r >> 2) + 2 * (q >> 1);
+        float e0 = v.x, e1 = v.y, e2 = v.z, e3 = v.w;
+        if (rot & 1) { const float t0 = e0; e0 = e1; e1 = e2; e2 = e3; e3 = t0; }
+        if (rot & 2) { const float t0 = e0, t1 = e1; e0 = e2; e1 = e3; e2 = t0; e3 = t1; }
+        const float e[4] = {e0, e1, e2, e3};
 #pragma unroll
         for (int k = 0; k < 4; k++) {
-          const int c = 4 * cc + k;
+          const int c = 4 * cc + ((k + rot) & 3);
           const uint32_t off = (uint32_t)((c & 7) * 16 + (c >> 3) * FwdSmem<CP>::SBO + (r & 3) * 4 + (r >> 2) * FwdSmem<CP>::LBO);
           *reinterpret_cast<float*>(&sm.f[s][0][off]) = e[k];
           *reinterpret_cast<float*>(&sm.f[s][1][off]) = tf32_lo(e[k]);
