@@ -28,13 +28,15 @@ namespace ocrf {
 namespace tc {
 
 constexpr int KB = 8;          // records per stage == K of one tf32 tcgen05.mma
-constexpr int STAGES = 3;
+constexpr int STAGES = 3;      // weight stages in tensor memory
+constexpr int FST = 6;         // feature / record stages in shared memory (the loader runs further ahead than the weights)
 constexpr int LOOKAHEAD = 3;   // blocks between the cp.async of a block and its use
 constexpr int RING = LOOKAHEAD + 1;
-constexpr int WORKER_WARPS = TILE_PIX / 32;
-constexpr int FWD_THREADS = TILE_PIX + 64;
-constexpr uint32_t FWD_TMEM_COLS = 256;
-constexpr uint32_t A_COL0 = 160;  // first column of the weight stages (D occupies [0, 2 CP) <= 160)
+// A CTA blends MB M-blocks of 128 pixels: MB = 2 is a whole 16x16 tile (256 tensor-memory columns, 2 CTAs per SM),
+// MB = 1 the upper or lower 16x8 half of one (128 columns, 4 CTAs per SM).  The lists of this path are short where
+// the scene is opaque (BASELINE config 4: a tile is finished after ~76 of its ~400 records), so a tile is mostly
+// start-up and drain latency; with half tiles twice as many of them are in flight per SM.  The loader work per tile
+// doubles (it is idle most of the time), the tensor-core and worker work does not.
 
 __device__ __forceinline__ float ex2_approx_t(float x) {
   float y;
@@ -48,17 +50,19 @@ struct FwdSmem {
   static constexpr uint32_t LBO = 128;              // the two 4-record chunks of a stage: adjacent core matrices
   static constexpr uint32_t SBO = 256;              // next group of 8 channels
   static constexpr uint32_t PART = NG * 256;        // bytes of one operand image (f or f_lo) of one stage
-  alignas(128) unsigned char f[STAGES][2][PART];    // [stage][raw | lo]
-  alignas(128) Record rec[STAGES][KB];
+  alignas(128) unsigned char f[FST][2][PART];       // [stage][raw | lo]
+  alignas(128) Record rec[FST][KB];
   alignas(128) float land_f[RING][KB][CP];          // cp.async landing zone (row = record)
   alignas(128) Record land_rec[RING][KB];
-  alignas(8) uint64_t ready_f[STAGES], ready_w[STAGES], free_[STAGES], final_;
-  int cnt[STAGES];
-  uint32_t tmem, done_warps, max_contrib;
+  alignas(8) uint64_t ready_f[FST], free_f[FST], ready_w[STAGES], free_[STAGES], final_, meta_;
+  int cnt[FST];
+  float bg[CP];
+  uint32_t nonzero[STAGES];  // worker warps whose weights of the stage's block are not all zero
+  uint32_t tmem, done_warps, max_contrib, started;
 };
 
-template <int CP>
-__global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
+template <int CP, int MB>
+__global__ void __launch_bounds__(MB * 128 + 64, 4 / MB) render_forward_tc_kernel(
     int W, int H, int C, int P, int views_per_sample, const uint2* __restrict__ ranges /* culled lists */,
     const Record* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
     float* __restrict__ final_T, uint32_t* __restrict__ n_contrib, uint32_t* __restrict__ max_contrib,
@@ -66,10 +70,15 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
   pdl_enter();
   extern __shared__ __align__(128) unsigned char smem_raw[];
   FwdSmem<CP>& sm = *reinterpret_cast<FwdSmem<CP>*>(smem_raw);
+  constexpr int WORKER_WARPS = MB * 4;
+  constexpr uint32_t FWD_TMEM_COLS = MB * 128;
+  constexpr uint32_t A_COL0 = MB * 80;  // first column of the weight stages (D occupies [0, MB CP) <= MB 80)
+  constexpr int HALVES = 2 / MB;        // CTAs per tile
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tiles_x = gridDim.x, tiles_per_view = gridDim.x * gridDim.y;
+  const int tiles_x = gridDim.x / HALVES, tiles_per_view = tiles_x * gridDim.y;
   const int view = blockIdx.z;
-  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  const int tile_x = blockIdx.x / HALVES, half = blockIdx.x % HALVES;
+  const int tile = blockIdx.y * tiles_x + tile_x;
   const uint2 range = ranges[(size_t)view * tiles_per_view + tile];
   const int n = (int)(range.y - range.x);
   const int nblocks = (n + KB - 1) / KB;
@@ -77,16 +86,24 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < STAGES; s++) {
-      mbar_init(&sm.ready_f[s], 1);
       mbar_init(&sm.ready_w[s], WORKER_WARPS);
       mbar_init(&sm.free_[s], 1);
     }
+#pragma unroll
+    for (int s = 0; s < FST; s++) {
+      mbar_init(&sm.ready_f[s], 1);
+      mbar_init(&sm.free_f[s], 1);
+    }
     mbar_init(&sm.final_, 1);
+    mbar_init(&sm.meta_, 1);
     mbar_fence_init();
     sm.done_warps = 0;
     sm.max_contrib = 0;
+#pragma unroll
+    for (int s = 0; s < STAGES; s++) sm.nonzero[s] = 0;
   }
   if (warp == WORKER_WARPS) tmem_alloc<FWD_TMEM_COLS>(&sm.tmem);
+  if (tid < CP) sm.bg[tid] = tid < C ? bg[tid] : 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -94,8 +111,9 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
 
   if (warp < WORKER_WARPS) {
     // ------------------------------------------------ workers ------------------------------------------------
-    const int px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = blockIdx.y * TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int wt = half * 4 + warp;  // warp of the tile: an 8 x 4 pixel block
+    const int px = tile_x * TILE + (wt & 1) * 8 + (lane & 7);
+    const int py = blockIdx.y * TILE + (wt >> 1) * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
     const float fx = (float)px, fy = (float)py;
     const int mb = warp >> 2;
@@ -110,27 +128,36 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
                                            // that took T across 0.5 (their `orig` and depth are fetched once, at the end)
     int b = 0;
     for (;; b++) {
-      const int s = b % STAGES;
-      const uint32_t use = (uint32_t)(b / STAGES);
-      mbar_wait_wd(&sm.ready_f[s], use & 1);
-      const int cnt = sm.cnt[s];
+      const int s = b % STAGES, sf = b % FST;
+      const uint32_t use = (uint32_t)(b / STAGES), usef = (uint32_t)(b / FST);
+      mbar_wait_wd(&sm.ready_f[sf], usef & 1);
+      const int cnt = sm.cnt[sf];
       if (cnt < 0) break;
       uint32_t wv[16];
 #pragma unroll
       for (int j = 0; j < 16; j++) wv[j] = 0u;
       const bool warp_done = __all_sync(0xffffffffu, fyn != fyn);
+      bool nonzero = false;
       if (!warp_done) {
         float al[KB];
         // phase 1: the eight alphas, independent of each other
 #pragma unroll
         for (int j = 0; j < KB; j++) {
-          const float4 a = reinterpret_cast<const float4*>(&sm.rec[s][j])[0];
-          const float2 c = reinterpret_cast<const float2*>(&sm.rec[s][j])[2];  // qc, opacity
+          const float4 a = reinterpret_cast<const float4*>(&sm.rec[sf][j])[0];
+          const float2 c = reinterpret_cast<const float2*>(&sm.rec[sf][j])[2];  // qc, opacity
           const float dx = a.x - fx, dy = a.y - fyn;
           const float power = a.z * dx * dx + c.x * dy * dy + a.w * dx * dy;  // log2 domain (scaled conic)
           const float alpha = fminf(0.99f, c.y * ex2_approx_t(power));
           al[j] = (j < cnt && power <= 0.0f && alpha >= 1.0f / 255.0f) ? alpha : 0.f;
         }
+        // Behind the last record that any pixel of the tile blends (position ~76 of ~400 in an opaque scene) the
+        // lists go on -- the exact tile cull knows the geometry, not the occlusion -- and nobody in the warp has a
+        // non-zero alpha any more: the recurrence is skipped for the whole block (the weights stay zero)
+        float amax = al[0];
+#pragma unroll
+        for (int j = 1; j < KB; j++) amax = fmaxf(amax, al[j]);
+        if (__any_sync(0xffffffffu, amax > 0.f)) {
+        nonzero = true;
         // phase 2: the transmittance recurrence (forward.cu:343-358: stop BEFORE blending once T would drop below 1e-4)
 #pragma unroll
         for (int j = 0; j < KB; j++) {
@@ -146,29 +173,34 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
           T = blend ? test_T : T;
           fyn = (ok && !blend) ? qnan : fyn;
         }
+        }
       } else if (!reported) {
         if (lane == 0) atomicAdd(&sm.done_warps, 1u);
         reported = true;
       }
       mbar_wait_wd(&sm.free_[s], (use & 1) ^ 1);  // the MMAs that read this stage's columns three blocks ago are done
       fence_after_sync();
-      tmem_st16(lane_addr + A_COL0 + s * 32 + mb * 16, wv);
+      tmem_st16(lane_addr + A_COL0 + s * (MB * 16) + mb * 16, wv);
       tmem_wait_st();
       fence_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.ready_w[s]);
+      if (lane == 0) {
+        if (nonzero) atomicAdd(&sm.nonzero[s], 1u);  // (ordered before the arrival: the MMA warp reads it after its wait)
+        mbar_arrive(&sm.ready_w[s]);
+      }
     }
     // ---- epilogue: D -> registers -> out_color
     const size_t HW = (size_t)H * W;
     const size_t pix = (size_t)py * W + px;
-    if (b > 0) {
-      mbar_wait_wd(&sm.final_, 0);
-      fence_after_sync();
-    }
+    mbar_wait_wd(&sm.meta_, 0);
+    mbar_wait_wd(&sm.final_, 0);  // every product has completed (the MMA warp commits even when it issued none)
+    fence_after_sync();
+    const bool have_d = *reinterpret_cast<volatile uint32_t*>(&sm.started) != 0u;
+    float* oc = out_color + (size_t)view * C * HW + pix;
 #pragma unroll
     for (int c0 = 0; c0 < CP; c0 += 16) {
       uint32_t v[16];
-      if (b > 0) {
+      if (have_d) {
         tmem_ld16(lane_addr + mb * CP + c0, v);
         tmem_wait_ld();
       } else {
@@ -177,8 +209,10 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
       }
       if (inside) {
 #pragma unroll
-        for (int i = 0; i < 16; i++)
-          if (c0 + i < C) out_color[((size_t)view * C + c0 + i) * HW + pix] = __uint_as_float(v[i]) + T * bg[c0 + i];
+        for (int i = 0; i < 16; i++) {
+          if (C == CP || c0 + i < C) *oc = fmaf(T, sm.bg[c0 + i], __uint_as_float(v[i]));
+          oc += HW;
+        }
       }
     }
     if (inside) {
@@ -193,29 +227,45 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
     // ------------------------------------------------ MMA issuer ------------------------------------------------
     constexpr uint32_t IDESC = idesc_tf32(128, CP);
     int b = 0;
+    uint32_t started = 0;  // D holds a product (the first one overwrites, the later ones accumulate)
+    uint32_t seen0 = 0, seen1 = 0, seen2 = 0;
+    static_assert(STAGES == 3, "three stage counters");
     for (;; b++) {
-      const int s = b % STAGES;
-      const uint32_t use = (uint32_t)(b / STAGES);
-      mbar_wait_wd(&sm.ready_f[s], use & 1);
-      if (sm.cnt[s] < 0) break;
+      const int s = b % STAGES, sf = b % FST;
+      const uint32_t use = (uint32_t)(b / STAGES), usef = (uint32_t)(b / FST);
+      mbar_wait_wd(&sm.ready_f[sf], usef & 1);
+      if (sm.cnt[sf] < 0) break;
       mbar_wait_wd(&sm.ready_w[s], use & 1);
       fence_after_sync();
+      // (the counters only grow: what this use of the stage added is the difference to what the last use left)
+      const uint32_t nz = *reinterpret_cast<volatile uint32_t*>(&sm.nonzero[s]);
+      const uint32_t before = s == 0 ? seen0 : s == 1 ? seen1 : seen2;
+      const bool any_w = nz != before;  // (warp-uniform)
+      if (s == 0) seen0 = nz; else if (s == 1) seen1 = nz; else seen2 = nz;
       if (lane == 0) {
-        const uint64_t d_raw = smem_desc(smem_u32(&sm.f[s][0][0]), FwdSmem<CP>::LBO, FwdSmem<CP>::SBO);
-        const uint64_t d_lo = smem_desc(smem_u32(&sm.f[s][1][0]), FwdSmem<CP>::LBO, FwdSmem<CP>::SBO);
+        if (any_w) {  // a block whose weights are all zero adds nothing: no product is issued for it
+          const uint64_t d_raw = smem_desc(smem_u32(&sm.f[sf][0][0]), FwdSmem<CP>::LBO, FwdSmem<CP>::SBO);
+          const uint64_t d_lo = smem_desc(smem_u32(&sm.f[sf][1][0]), FwdSmem<CP>::LBO, FwdSmem<CP>::SBO);
 #pragma unroll
-        for (int mb = 0; mb < 2; mb++) {
-          const uint32_t d = tm + mb * CP;
-          const uint32_t a = tm + A_COL0 + s * 32 + mb * 16;
-          mma_ts_tf32(d, a, d_raw, IDESC, b > 0);  // w . f
-          mma_ts_tf32(d, a + KB, d_raw, IDESC, 1);  // w_lo . f
-          mma_ts_tf32(d, a, d_lo, IDESC, 1);        // w . f_lo
+          for (int mb = 0; mb < MB; mb++) {
+            const uint32_t d = tm + mb * CP;
+            const uint32_t a = tm + A_COL0 + s * (MB * 16) + mb * 16;
+            mma_ts_tf32(d, a, d_raw, IDESC, started);  // w . f
+            mma_ts_tf32(d, a + KB, d_raw, IDESC, 1);    // w_lo . f
+            mma_ts_tf32(d, a, d_lo, IDESC, 1);          // w . f_lo
+          }
         }
-        mma_commit(&sm.free_[s]);
+        mma_commit(&sm.free_[s]);    // the weight columns of the stage
+        mma_commit(&sm.free_f[sf]);  // the feature / record stage
       }
+      started = started || any_w;
       __syncwarp();
     }
-    if (lane == 0 && b > 0) mma_commit(&sm.final_);
+    if (lane == 0) {
+      sm.started = started ? 1u : 0u;
+      mbar_arrive(&sm.meta_);     // (a generic arrival: releases the flag to the workers)
+      mma_commit(&sm.final_);     // every product issued so far has completed
+    }
     __syncwarp();
   } else {
     // ------------------------------------------------ loader ------------------------------------------------
@@ -250,12 +300,12 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
     };
     for (int bb = 0; bb < LOOKAHEAD; bb++) issue(bb);
     for (int b = 0;; b++) {
-      const int s = b % STAGES;
-      const uint32_t use = (uint32_t)(b / STAGES);
+      const int s = b % FST;
+      const uint32_t use = (uint32_t)(b / FST);
       issue(b + LOOKAHEAD);
       cp_async_wait<LOOKAHEAD>();  // block b has landed (this lane's own chunks)
       const bool stop = b >= nblocks || *reinterpret_cast<volatile uint32_t*>(&sm.done_warps) == WORKER_WARPS;
-      mbar_wait_wd(&sm.free_[s], (use & 1) ^ 1);
+      mbar_wait_wd(&sm.free_f[s], (use & 1) ^ 1);
       if (stop) {
         if (lane == 0) {
           sm.cnt[s] = -1;
@@ -300,26 +350,35 @@ __global__ void __launch_bounds__(FWD_THREADS, 2) render_forward_tc_kernel(
   }
   fence_before_sync();
   __syncthreads();
-  if (tid == 0) max_contrib[(size_t)view * tiles_per_view + tile] = sm.max_contrib;
+  if (tid == 0) {
+    if (MB == 2) max_contrib[(size_t)view * tiles_per_view + tile] = sm.max_contrib;
+    else atomicMax(&max_contrib[(size_t)view * tiles_per_view + tile], sm.max_contrib);  // (zeroed before the launch)
+  }
   if (warp == WORKER_WARPS) tmem_dealloc<FWD_TMEM_COLS>(tm);
 }
 
-template <int CP>
+template <int CP, int MB>
 static int launch_forward_tc_cp(cudaStream_t st, dim3 grid, const OcrfShape* sh, const uint2* ranges, const Record* rec,
                                 const float* colors, const float* bg, float* fT, uint32_t* nc, uint32_t* mc,
                                 float* out_color, float* out_depth, float* out_opacity) {
-  // tensor memory allows two CTAs per SM (2 x 256 columns); asking for just over a third of the shared memory
-  // keeps a third CTA from becoming resident and spinning in tcgen05.alloc
-  const size_t dyn = sizeof(FwdSmem<CP>) > 80 * 1024 ? sizeof(FwdSmem<CP>) : 80 * 1024;
+  // tensor memory allows 4 / MB CTAs per SM; asking for just over 1 / (4 / MB + 1) of the shared memory keeps one
+  // more from becoming resident and spinning in tcgen05.alloc
+  const size_t want = MB == 2 ? 80 * 1024 : 48 * 1024;
+  const size_t dyn = sizeof(FwdSmem<CP>) > want ? sizeof(FwdSmem<CP>) : want;
   static int configured[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(render_forward_tc_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaError_t e = cudaFuncSetAttribute(render_forward_tc_kernel<CP, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return (int)e;
     configured[dev] = 1;
   }
-  OCRF_LAUNCH(render_forward_tc_kernel<CP>, dim3(grid), dim3(FWD_THREADS), dyn, st, sh->W, sh->H, sh->C, sh->P,
+  if (MB == 1) {  // the two halves of a tile combine their last contributor with atomicMax
+    cudaError_t e = cudaMemsetAsync(mc, 0, (size_t)grid.x * grid.y * grid.z * sizeof(uint32_t), st);
+    if (e != cudaSuccess) return (int)e;
+    grid.x *= 2;
+  }
+  OCRF_LAUNCH(render_forward_tc_kernel<CP, MB>, dim3(grid), dim3(MB * 128 + 64), dyn, st, sh->W, sh->H, sh->C, sh->P,
               sh->views_per_sample, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
   return 0;
 }
@@ -332,9 +391,14 @@ bool forward_tc_supported(int C) {
 int launch_forward_tc(cudaStream_t st, dim3 grid, const OcrfShape* sh, const uint2* ranges, const Record* rec,
                       const float* colors, const float* bg, float* fT, uint32_t* nc, uint32_t* mc, float* out_color,
                       float* out_depth, float* out_opacity) {
-  if (sh->C <= 48) return launch_forward_tc_cp<48>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
-  if (sh->C <= 64) return launch_forward_tc_cp<64>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
-  return launch_forward_tc_cp<80>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity);
+  static const int mb = (getenv("OCRF_TC_FWD_MB") != nullptr && atoi(getenv("OCRF_TC_FWD_MB")) == 2) ? 2 : 1;
+#define OCRF_TCF(CPV)                                                                                                       \
+  return mb == 2 ? launch_forward_tc_cp<CPV, 2>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity) \
+                 : launch_forward_tc_cp<CPV, 1>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, out_color, out_depth, out_opacity)
+  if (sh->C <= 48) OCRF_TCF(48);
+  if (sh->C <= 64) OCRF_TCF(64);
+  OCRF_TCF(80);
+#undef OCRF_TCF
 }
 
 }  // namespace tc
