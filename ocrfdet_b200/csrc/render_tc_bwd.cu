@@ -22,15 +22,17 @@
 namespace ocrf {
 namespace tc {
 
-constexpr int BR = 32;  // records per block == N of the tcgen05.mma
-constexpr int BWD_THREADS = TILE_PIX + 64;
-constexpr uint32_t BWD_TMEM_COLS = 512;
 constexpr int FB = 16;  // records per cross-warp reduction of the feature gradients
 constexpr int WP = 36;  // pitch of a record's 32 pixel weights (== 4 mod 32: conflict-free A fragments)
-constexpr int NWW = TILE_PIX / 32;
 
-template <int CP>
+// A CTA owns MB M-blocks of 128 pixels: MB = 2 a whole 16x16 tile (448 tensor-memory columns: one CTA per SM), MB = 1
+// the upper or lower half of one (192 columns: TWO CTAs per SM, so the start-up of one half tile -- 40 KB of upstream
+// gradient, the first feature block, the first products -- runs under the traversal of the other).  Blocks are
+// BR = 16 MB records; the feature staging and the global reductions double with half tiles, the products do not.
+template <int CP, int MB>
 struct BwdSmem {
+  static constexpr int BR = 16 * MB;   // records per block == N of the tcgen05.mma
+  static constexpr int NWW = 4 * MB;   // worker warps
   static constexpr int KC = CP / 4;  // 16-byte chunks per feature row
   static constexpr uint32_t LBO = 128;          // next 4 channels of the same 8 records
   static constexpr uint32_t SBO = KC * 128;     // next 8 records
@@ -48,26 +50,31 @@ struct BwdSmem {
   uint32_t tmem;
 };
 
-__device__ __forceinline__ void worker_bar() { asm volatile("bar.sync 1, %0;" ::"n"(TILE_PIX) : "memory"); }
 
-template <int CP>
-__global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
+template <int CP, int MB>
+__global__ void __launch_bounds__(MB * 128 + 64, 2 / MB) render_backward_tc_kernel(
     int W, int H, int C, int P, int views_per_sample, const uint2* __restrict__ ranges /* culled lists */,
     const Record* __restrict__ records, const float* __restrict__ feats, const float* __restrict__ bg,
     const float* __restrict__ final_T, const uint32_t* __restrict__ n_contrib,
     const uint32_t* __restrict__ max_contrib, const float* __restrict__ dL_dpix, const float* __restrict__ dL_dopa,
     double* __restrict__ ggrad, float* __restrict__ dL_dfeats) {
   pdl_enter();
-  using SM = BwdSmem<CP>;
+  using SM = BwdSmem<CP, MB>;
   extern __shared__ __align__(128) unsigned char smem_raw_b[];
   SM& sm = *reinterpret_cast<SM*>(smem_raw_b);
   constexpr int GP = SM::GP;
-  constexpr uint32_t D_COL0 = 4 * CP;  // G occupies [0, 4 CP): per M-block g then g_lo
+  constexpr int BR = SM::BR, NWW = SM::NWW;
+  constexpr int WORKERS = NWW * 32;
+  constexpr uint32_t D_COL0 = MB * 2 * CP;  // G occupies [0, 2 MB CP): per M-block g then g_lo
+  constexpr uint32_t BWD_TMEM_COLS = MB == 2 ? 512 : 256;
+  constexpr int HALVES = 2 / MB;
+  auto worker_bar = [] { asm volatile("bar.sync 1, %0;" ::"n"(WORKERS) : "memory"); };
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int tiles_x = gridDim.x, tiles_per_view = gridDim.x * gridDim.y;
+  const int tiles_x = gridDim.x / HALVES, tiles_per_view = tiles_x * gridDim.y;
   const int view = blockIdx.z;
-  const int tile = blockIdx.y * tiles_x + blockIdx.x;
+  const int tile_x = blockIdx.x / HALVES, half = blockIdx.x % HALVES;
+  const int tile = blockIdx.y * tiles_x + tile_x;
   const size_t vt = (size_t)view * tiles_per_view + tile;
   const int mc = (int)max_contrib[vt];
   if (mc == 0) return;
@@ -97,8 +104,9 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
     (void)fbase;
     float* gfbase = dL_dfeats + (size_t)s_idx * P * C;
     const size_t HW = (size_t)H * W;
-    const int px = blockIdx.x * TILE + (warp & 1) * 8 + (lane & 7);
-    const int py = blockIdx.y * TILE + (warp >> 1) * 4 + (lane >> 3);
+    const int wt = half * 4 + warp;  // warp of the tile: an 8 x 4 pixel block
+    const int px = tile_x * TILE + (wt & 1) * 8 + (lane & 7);
+    const int py = blockIdx.y * TILE + (wt >> 1) * 4 + (lane >> 3);
     const bool inside = px < W && py < H;
     const size_t pix = (size_t)py * W + px;
     const float fx = (float)px, fy = (float)py;
@@ -144,7 +152,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
 #pragma unroll
       for (int e = 0; e < 8; e++) {
         const int q = 8 * (e >> 1) + tig + 4 * (e & 1);  // warp-local pixel = the lane that owns it
-        const float lx = (float)((warp & 1) * 8 + (q & 7)) - 7.5f, ly = (float)((warp >> 1) * 4 + (q >> 3)) - 7.5f;
+        const float lx = (float)((wt & 1) * 8 + (q & 7)) - 7.5f, ly = (float)((wt >> 1) * 4 + (q >> 3)) - 7.5f;
         bmono[e] = gid == 0 ? 1.f : gid == 1 ? lx : gid == 2 ? ly : gid == 3 ? lx * lx : gid == 4 ? lx * ly : gid == 5 ? ly * ly : 0.f;
       }
     }
@@ -169,11 +177,11 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
       //   phase C  t = G dL/dalpha per record; the geometry gradients are six MOMENTS of t over the tile's pixels
       //            (sum t, t x, t y, t x^2, t x y, t y^2 about the tile centre), i.e. one more small product t^T . M
 #pragma unroll 1
-      for (int grp = 1; grp >= 0; grp--) {
+      for (int grp = BR / FB - 1; grp >= 0; grp--) {
         const int j0 = grp * FB;
         if (j0 >= cnt) continue;  // (CTA-uniform)
         uint32_t d[FB];
-        tmem_ld16(lane_addr + D_COL0 + s * 64 + mb * 32 + j0, d);
+        tmem_ld16(lane_addr + D_COL0 + s * (MB * BR) + mb * BR + j0, d);
         tmem_wait_ld();
         if (grp == 0) {  // the last read of this D1 buffer: the MMA warp may overwrite it
           fence_before_sync();
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
           for (int w2 = 0; w2 < NWW; w2++) tot += sm.macc[w2][jj][m];
           sm.mom[j0 + jj][m] = tot;
         }
-        for (int e = tid; e < FB * CP; e += TILE_PIX) {
+        for (int e = tid; e < FB * CP; e += WORKERS) {
           const int jj = e / CP, ch = e - jj * CP;
           const int rj = j0 + jj;
           if (rj >= cnt || ch >= C) continue;
@@ -291,7 +299,7 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
         if (m03.x != 0.f || m03.y != 0.f || m03.z != 0.f || m03.w != 0.f || m45.x != 0.f || m45.y != 0.f) {
           const Record rc_ = sm.rec[s][j];
           const double M0 = m03.x, Mx = m03.y, My = m03.z, Mxx = m03.w, Mxy = m45.x, Myy = m45.y;
-          const double a = (double)rc_.x - ((double)(blockIdx.x * TILE) + 7.5), bb = (double)rc_.y - ((double)(blockIdx.y * TILE) + 7.5);
+          const double a = (double)rc_.x - ((double)(tile_x * TILE) + 7.5), bb = (double)rc_.y - ((double)(blockIdx.y * TILE) + 7.5);
           const double sdx = a * M0 - Mx, sdy = bb * M0 - My;
           const double sxx = a * a * M0 - 2.0 * a * Mx + Mxx;
           const double sxy = a * bb * M0 - a * My - bb * Mx + Mxy;
@@ -326,8 +334,8 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
       if (lane == 0) {
         const uint32_t f_raw = smem_u32(&sm.f[s][0][0]), f_lo = smem_u32(&sm.f[s][1][0]);
 #pragma unroll
-        for (int mb = 0; mb < 2; mb++) {
-          const uint32_t dcol = tm + D_COL0 + s * 64 + mb * 32;
+        for (int mb = 0; mb < MB; mb++) {
+          const uint32_t dcol = tm + D_COL0 + s * (MB * BR) + mb * BR;
           const uint32_t g_raw = tm + mb * 2 * CP, g_lo = g_raw + CP;
 #pragma unroll
           for (int ks = 0; ks < CP / 8; ks++) {
@@ -405,21 +413,22 @@ __global__ void __launch_bounds__(BWD_THREADS, 1) render_backward_tc_kernel(
   if (warp == NWW) tmem_dealloc<BWD_TMEM_COLS>(tm);
 }
 
-template <int CP>
+template <int CP, int MB>
 static int launch_backward_tc_cp(cudaStream_t st, dim3 grid, const OcrfShape* sh, const uint2* ranges, const Record* rec,
                                  const float* colors, const float* bg, const float* fT, const uint32_t* nc,
                                  const uint32_t* mc, const float* dL_dcolor, const float* dL_dopa, double* ggrad,
                                  float* dL_dcolors) {
-  const size_t dyn = sizeof(BwdSmem<CP>);
+  const size_t dyn = sizeof(BwdSmem<CP, MB>);
   static int configured[64] = {0};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev < 64 && !configured[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(render_backward_tc_kernel<CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaError_t e = cudaFuncSetAttribute(render_backward_tc_kernel<CP, MB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return (int)e;
     configured[dev] = 1;
   }
-  OCRF_LAUNCH(render_backward_tc_kernel<CP>, dim3(grid), dim3(BWD_THREADS), dyn, st, sh->W, sh->H, sh->C, sh->P,
+  grid.x *= 2 / MB;
+  OCRF_LAUNCH(render_backward_tc_kernel<CP, MB>, dim3(grid), dim3(MB * 128 + 64), dyn, st, sh->W, sh->H, sh->C, sh->P,
               sh->views_per_sample, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopa, ggrad, dL_dcolors);
   return 0;
 }
@@ -427,9 +436,16 @@ static int launch_backward_tc_cp(cudaStream_t st, dim3 grid, const OcrfShape* sh
 int launch_backward_tc(cudaStream_t st, dim3 grid, const OcrfShape* sh, const uint2* ranges, const Record* rec,
                        const float* colors, const float* bg, const float* fT, const uint32_t* nc, const uint32_t* mc,
                        const float* dL_dcolor, const float* dL_dopa, double* ggrad, float* dL_dcolors) {
-  if (sh->C <= 48) return launch_backward_tc_cp<48>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopa, ggrad, dL_dcolors);
-  if (sh->C <= 64) return launch_backward_tc_cp<64>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopa, ggrad, dL_dcolors);
-  return launch_backward_tc_cp<80>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopa, ggrad, dL_dcolors);
+  // whole tiles by default: half tiles (two CTAs per SM) measured 2.13 against 1.96 ms at BASELINE config 4 -- the
+  // kernel is bound by its instruction count (the per-warp mma.sync product is a third of it), not by start-up latency
+  static const int mb = (getenv("OCRF_TC_BWD_MB") != nullptr && atoi(getenv("OCRF_TC_BWD_MB")) == 1) ? 1 : 2;
+#define OCRF_TCB(CPV)                                                                                                     \
+  return mb == 2 ? launch_backward_tc_cp<CPV, 2>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopa, ggrad, dL_dcolors) \
+                 : launch_backward_tc_cp<CPV, 1>(st, grid, sh, ranges, rec, colors, bg, fT, nc, mc, dL_dcolor, dL_dopa, ggrad, dL_dcolors)
+  if (sh->C <= 48) OCRF_TCB(48);
+  if (sh->C <= 64) OCRF_TCB(64);
+  OCRF_TCB(80);
+#undef OCRF_TCB
 }
 
 }  // namespace tc
