@@ -328,7 +328,14 @@ def run_ours(args, rank, world, device):
     if world > 1:
         # settle: a few flushed steps with the collective, so that lazy NCCL channel setup and rank skew are not
         # inside the timed region (untimed, in addition to the --warmup steps above)
-        for _ in range(5):
+        # (an 8-GPU run on a fresh box showed ~25 slow steps -- 0.65-0.79 ms, one rank's launching thread still cold
+        # and every rank waiting for it in the gather -- before settling at 0.59: settle for longer than that)
+        for _ in range(60):
+            flush.fill_(1)
+            step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        for _ in range(10):
             flush.fill_(1)
             step()
         torch.cuda.synchronize()
