@@ -398,9 +398,8 @@ int multisplit_bin(cudaStream_t st, const OcrfShape* sh, uint64_t pair_capacity,
   const int tiles_v = tiles_x(*sh) * tiles_y(*sh);
   if (tiles_v > 8191) return OCRF_ECAPACITY;
   // chunk size: multiples of MS_ROUND pairs, at most ~2048 chunks for the whole capacity
-  uint64_t rounds = (pair_capacity + (uint64_t)MS_ROUND * 2048 - 1) / ((uint64_t)MS_ROUND * 2048);
-  if (rounds < 1) rounds = 1;
-  const uint32_t Q = (uint32_t)(rounds * MS_ROUND);
+  static_assert(MS_ROUND == 4096, "multisplit_chunk_pairs (common.cuh) sizes the chunk tables in rounds of 4096 pairs");
+  const uint32_t Q = multisplit_chunk_pairs(pair_capacity);
   const int chunks_max = (int)((pair_capacity + Q - 1) / Q) + 1;
   if ((size_t)2 * sh->V * chunks_max * tiles_v > table_words) return OCRF_ECAPACITY;
   uint32_t* cnt_full = tables;

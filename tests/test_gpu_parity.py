@@ -319,3 +319,53 @@ def test_colors_ready_event_late_binds_the_colour_upload():
                          colors_ready=ready, **kw)
     for a, b in zip(want, got):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("C,half", [(80, 0), (48, 0), (36, 0), (80, 1), (40, 1)])
+def test_tensor_core_blend_odd_image_batch_and_half_tiles(C, half):
+    """The tcgen05 blend kernels (32 < C <= 80, C % 4 == 0) on an image that is not a multiple of the tile, two samples
+    x two views in one call, channel counts that pad the MMA's N (36 -> 48), whole-tile and half-tile CTAs; a
+    subprocess per case because the CTA shape is read from the environment once."""
+    import os
+    import subprocess
+    import sys
+    code = r'''
+import numpy as np, torch
+from tests import util
+from ocrfdet_b200 import rasterizer as R
+C = %d
+W, H, V = 90, 50, 2
+gs = [util.small_scene("ring", P=1500, seed=20 + s, W=W, H=H, channels=C, n_views=V) for s in range(2)]
+cams = gs[0][1] + gs[1][1]
+names = ("means3D", "scales", "rotations", "opacities", "colors")
+t = {k: torch.from_numpy(np.stack([g[0][k] for g in gs])).cuda().requires_grad_(True) for k in names}
+bg = np.linspace(0.1, 0.9, C).astype(np.float32)
+rng = np.random.default_rng(9)
+gcol = rng.normal(size=(2 * V, C, H, W)).astype(np.float32)
+gop = rng.normal(size=(2 * V, 1, H, W)).astype(np.float32)
+outs = [util.oracle_forward(gs[i // V][0], cams[i], W, H, list(bg)) for i in range(2 * V)]
+amb = np.stack([np.asarray(w["ambiguous"]).astype(bool).reshape(H, W) for w, _ in outs])
+gcol, gop = gcol * ~amb[:, None], gop * ~amb[:, None]   # a borderline pixel may blend one Gaussian more or less
+color, radii, depth, opac = R.render_batch(t["means3D"], t["opacities"], util.cams_tensor(cams), H, W,
+                                           torch.from_numpy(bg).cuda(), colors_precomp=t["colors"], scales=t["scales"],
+                                           rotations=t["rotations"])
+torch.autograd.backward([color, opac], [torch.from_numpy(gcol).cuda(), torch.from_numpy(gop).cuda()])
+for s in range(2):
+    acc = {k: 0.0 for k in names}
+    for v in range(V):
+        i = s * V + v
+        want, wst = outs[i]
+        util.assert_image_close(color[i].detach().cpu().numpy(), want["color"], want["ambiguous"], 1e-5, "features")
+        util.assert_image_close(opac[i].detach().cpu().numpy(), want["opacity"], want["ambiguous"], 1e-5, "opacity")
+        gw = util.oracle_backward(gs[s][0], cams[i], W, H, list(bg), want, wst, gcol[i], gop[i])
+        for k in names:
+            acc[k] = acc[k] + np.asarray(gw[k], np.float64).reshape(gs[s][0][k].shape)
+    for k in names:
+        e = util.rel_err(t[k].grad[s].cpu().numpy(), acc[k])
+        assert e <= 1e-4, "%%s gradient of sample %%d: rel err %%.3g (C=%%d)" %% (k, s, e, C)
+print("PARITY_OK")
+''' % C
+    env = dict(os.environ, OCRF_TC_FWD_MB="1" if half else "2", OCRF_TC_BWD_MB="1" if half else "2",
+               PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert r.returncode == 0 and "PARITY_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
