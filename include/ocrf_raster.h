@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define OCRF_ABI_VERSION 4
+#define OCRF_ABI_VERSION 5
 
 #define OCRF_EINVAL (-1)    /* bad argument (null pointer, non-positive size, unsupported channel count) */
 #define OCRF_ECAPACITY (-2) /* workspace too small for the request */
@@ -130,6 +130,15 @@ int ocrf_preprocess_forward(void* stream, const OcrfShape* shape, const float* m
                             const float* rotations, const float* cov3D_precomp, const float* opacities,
                             const float* shs, const float* cams, float scale_modifier, int prefiltered,
                             int32_t* radii, void* geom_ws);
+/* The same with a foreground filter (OcRFDet turns every voxel of its 13 x 128 x 128 grid into a
+ * Gaussian, view_transformer_ocrf.py:1130-1153, most of them empty space): Gaussians with opacity < min_opacity are
+ * culled like out-of-frustum ones (radii 0, no pairs).  min_opacity is clamped to 1/255, below which a Gaussian can
+ * never pass the blend's `alpha < 1/255 -> continue` (forward.cu:345, backward.cu:478): images and gradients are
+ * unchanged, only radii / keys / pair counts shrink.  min_opacity <= 0 is ocrf_preprocess_forward. */
+int ocrf_preprocess_forward_filtered(void* stream, const OcrfShape* shape, const float* means3D, const float* scales,
+                                     const float* rotations, const float* cov3D_precomp, const float* opacities,
+                                     const float* shs, const float* cams, float scale_modifier, int prefiltered,
+                                     float min_opacity, int32_t* radii, void* geom_ws);
 
 /* Stage 2 (rasterizer_impl.cu:70-138,289-318): duplicateWithKeys + onesweep radix sort of the
  * 64-bit (view*tiles+tile | depth) keys + identifyTileRanges + record packing.

@@ -12,7 +12,7 @@ LIB_PATH = os.path.join(HERE, "libocrf_raster.so")
 OCRF_CAM_STRIDE = 40
 OCRF_RECORD_BYTES = 48
 OCRF_GGRAD_STRIDE = 6
-ABI_VERSION = 4
+ABI_VERSION = 5
 OCRF_EINVAL = -1
 OCRF_ECAPACITY = -2
 OCRF_BIN_PAIR_SORT = 1
@@ -20,7 +20,7 @@ OCRF_BIN_DEPTH_FIRST = 2
 
 EXPORTS = [
     "ocrf_abi_version", "ocrf_error_string", "ocrf_debug_sync", "ocrf_geom_layout", "ocrf_bin_layout", "ocrf_image_layout",
-    "ocrf_sort_end_bit", "ocrf_preprocess_forward", "ocrf_bin_forward", "ocrf_render_forward",
+    "ocrf_sort_end_bit", "ocrf_preprocess_forward", "ocrf_preprocess_forward_filtered", "ocrf_bin_forward", "ocrf_render_forward",
     "ocrf_render_backward", "ocrf_preprocess_backward", "ocrf_mark_visible", "ocrf_sort_workspace_bytes",
     "ocrf_sort_pairs", "ocrf_opacity_mask_forward", "ocrf_opacity_mask_backward",
     "ocrf_gaussian_heads_forward", "ocrf_gaussian_heads_backward", "ocrf_gaussian_heads_backward_workspace_bytes", "ocrf_clear_gradients",
@@ -80,6 +80,7 @@ def lib():
     L.ocrf_image_layout.argtypes = [shp, C.POINTER(OcrfImageLayout)]
     L.ocrf_sort_end_bit.argtypes = [shp]
     L.ocrf_preprocess_forward.argtypes = [vp, shp, vp, vp, vp, vp, vp, vp, vp, f32, C.c_int, vp, vp]
+    L.ocrf_preprocess_forward_filtered.argtypes = [vp, shp, vp, vp, vp, vp, vp, vp, vp, f32, C.c_int, f32, vp, vp]
     L.ocrf_bin_forward.argtypes = [vp, shp, u64, vp, vp, C.c_int, C.c_uint32, vp, vp, vp, vp]
     L.ocrf_debug_sync.argtypes = [vp]
     L.ocrf_render_forward.argtypes = [vp, shp, u64, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(PRE_THREADS, OCRF_PRE_MINB) preprocess_forward
     OcrfShape sh, int blocks_per_view, const float* __restrict__ means3D, const float* __restrict__ scales,
     const float* __restrict__ rotations, const float* __restrict__ cov3D_precomp, const float* __restrict__ opacities,
     const float* __restrict__ shs, const Camera* __restrict__ cams, float scale_modifier, int prefiltered,
-    int32_t* __restrict__ radii, uint32_t* __restrict__ header, float* __restrict__ depths, float2* __restrict__ xy,
+    float min_opacity, int32_t* __restrict__ radii, uint32_t* __restrict__ header, float* __restrict__ depths, float2* __restrict__ xy,
     float4* __restrict__ conic_opacity, uint32_t* __restrict__ tiles_touched, uint32_t* __restrict__ offsets,
     float* __restrict__ rgb, uint8_t* __restrict__ clamped, unsigned long long* __restrict__ scan_status,
     uint64_t* __restrict__ vis_keys, uint32_t* __restrict__ vis_vals, uint32_t* __restrict__ view_start) {
@@ -86,7 +86,11 @@ __global__ void __launch_bounds__(PRE_THREADS, OCRF_PRE_MINB) preprocess_forward
     const float* vm = s_cam.view;
     const float* pm = s_cam.proj;
     const float tz = xform_row(vm, 2, x, y, z);
-    if (tz > 0.2f) {
+    // Foreground filter (optional, min_opacity > 0): alpha = min(0.99, opacity * G) with G <= 1, so a Gaussian whose
+    // opacity is below the blend threshold 1/255 can never pass `alpha < 1/255 -> continue` (forward.cu:345,
+    // backward.cu:478): dropping it here changes no pixel and no gradient, only radii / the pair count.
+    const bool background = min_opacity > 0.f && __ldg(opacities + gbase + tid) < min_opacity;
+    if (tz > 0.2f && !background) {
       const float tx = xform_row(vm, 0, x, y, z), ty = xform_row(vm, 1, x, y, z);
       const float hx = xform_row(pm, 0, x, y, z), hy = xform_row(pm, 1, x, y, z), hw = xform_row(pm, 3, x, y, z);
       const float pw = __frcp_rn(__fadd_rn(hw, 0.0000001f));
@@ -147,7 +151,7 @@ __global__ void __launch_bounds__(PRE_THREADS, OCRF_PRE_MINB) preprocess_forward
           my_tiles = area;
         }
       }
-    } else if (prefiltered) {
+    } else if (prefiltered && !background) {
       atomicOr(&header[HDR_ERROR], ERR_PREFILTERED);  // the reference traps here (auxiliary.h:156-160)
     }
     radii[o] = rad_out;
@@ -237,6 +241,15 @@ extern "C" int ocrf_preprocess_forward(void* stream, const OcrfShape* sh, const 
                                        const float* rotations, const float* cov3D_precomp, const float* opacities,
                                        const float* shs, const float* cams, float scale_modifier, int prefiltered,
                                        int32_t* radii, void* geom_ws) {
+  return ocrf_preprocess_forward_filtered(stream, sh, means3D, scales, rotations, cov3D_precomp, opacities, shs, cams,
+                                          scale_modifier, prefiltered, 0.f, radii, geom_ws);
+}
+
+extern "C" int ocrf_preprocess_forward_filtered(void* stream, const OcrfShape* sh, const float* means3D,
+                                                const float* scales, const float* rotations, const float* cov3D_precomp,
+                                                const float* opacities, const float* shs, const float* cams,
+                                                float scale_modifier, int prefiltered, float min_opacity, int32_t* radii,
+                                                void* geom_ws) {
   if (!sh || !means3D || !opacities || !cams || !radii || !geom_ws) return OCRF_EINVAL;
   if (sh->V <= 0 || sh->P <= 0 || sh->W <= 0 || sh->H <= 0 || sh->views_per_sample <= 0 ||
       sh->V % sh->views_per_sample != 0 || sh->S * sh->views_per_sample != sh->V)
@@ -253,7 +266,8 @@ extern "C" int ocrf_preprocess_forward(void* stream, const OcrfShape* sh, const 
   cudaMemsetAsync(at<char>(geom_ws, L.header), 0, L.depths - L.header, st);
   OCRF_LAUNCH(preprocess_forward_kernel, dim3(blocks), dim3(PRE_THREADS), 0, st, 
       *sh, bpv, means3D, scales, rotations, cov3D_precomp, opacities, shs, reinterpret_cast<const Camera*>(cams),
-      scale_modifier, prefiltered, radii, at<uint32_t>(geom_ws, L.header), at<float>(geom_ws, L.depths),
+      scale_modifier, prefiltered, min_opacity > 1.0f / 255.0f ? 1.0f / 255.0f : min_opacity, radii,
+      at<uint32_t>(geom_ws, L.header), at<float>(geom_ws, L.depths),
       at<float2>(geom_ws, L.xy), at<float4>(geom_ws, L.conic_opacity), at<uint32_t>(geom_ws, L.tiles_touched),
       at<uint32_t>(geom_ws, L.offsets), at<float>(geom_ws, L.rgb), at<uint8_t>(geom_ws, L.clamped),
       at<unsigned long long>(geom_ws, L.scan_status),

@@ -188,10 +188,11 @@ class _RasterizeBatch(torch.autograd.Function):
         depth = torch.empty((V, 1, H, W), dtype=torch.float32, device=dev)
         opac = torch.empty((V, 1, H, W), dtype=torch.float32, device=dev)
 
-        check(L.ocrf_preprocess_forward(stream, C.byref(shape), ptr(means3D), ptr(scales), ptr(rotations),
-                                        ptr(cov3D_precomp), ptr(opacities), ptr(shs), ptr(cams),
-                                        C.c_float(cfg["scale_modifier"]), int(cfg["prefiltered"]), ptr(radii),
-                                        ptr(geom)), "ocrf_preprocess_forward")
+        check(L.ocrf_preprocess_forward_filtered(stream, C.byref(shape), ptr(means3D), ptr(scales), ptr(rotations),
+                                                 ptr(cov3D_precomp), ptr(opacities), ptr(shs), ptr(cams),
+                                                 C.c_float(cfg["scale_modifier"]), int(cfg["prefiltered"]),
+                                                 C.c_float(cfg.get("min_opacity", 0.0)), ptr(radii), ptr(geom)),
+              "ocrf_preprocess_forward")
         _stage("preprocess")
         if debug:
             _debug_sync("preprocess")
@@ -391,7 +392,7 @@ def last_state(reference_lists=False):
 def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors_precomp=None, shs=None, scales=None,
                  rotations=None, cov3D_precomp=None, means2D=None, scale_modifier=1.0, sh_degree=0, prefiltered=False,
                  pair_capacity=None, binning: Optional[str] = None, colors_ready=None, debug: bool = False,
-                 sample_chunk: Optional[int] = None):
+                 sample_chunk: Optional[int] = None, min_opacity: float = 0.0):
     """Render V = cams.shape[0] views of S = means3D.shape[0] samples in one launch sequence.
 
     means3D [S,P,3]; opacities [S,P,1]; colors_precomp [S,P,C] or shs [S,P,M,3]; scales [S,P,3] and
@@ -412,6 +413,10 @@ def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors
     other, and concatenate: bounds the transient workspaces -- the binning workspace is 56 bytes per (tile, Gaussian)
     pair -- for shapes like BASELINE config 5 (8 samples x 6 views at 512x1408 with a million Gaussians each: 134 M
     pairs per sample).  Every chunk is its own autograd node; `pair_capacity` may then be a sequence, one per chunk.
+    `min_opacity`: foreground filter (OcRFDet renders every voxel of its 13 x 128 x 128 grid,
+    view_transformer_ocrf.py:1130-1153).  Gaussians with opacity < min(min_opacity, 1/255) are culled in the preprocess
+    like out-of-frustum ones: they could never pass the blend's alpha >= 1/255 test, so images and gradients are
+    unchanged while radii (0 for them), keys and pair counts shrink.  0 (default) keeps the reference's radii.
     `debug`: the reference's debug mode (PKG:83-90,132-139; CR/auxiliary.h:166-173): synchronise and check for CUDA
     errors after every stage, and on any failure save the CPU copy of the arguments as `snapshot_fw.dump` /
     `snapshot_bw.dump` before re-raising.
@@ -432,7 +437,8 @@ def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors
                 colors_precomp=cut(colors_precomp, s0, s1), shs=cut(shs, s0, s1), scales=cut(scales, s0, s1),
                 rotations=cut(rotations, s0, s1), cov3D_precomp=cut(cov3D_precomp, s0, s1),
                 means2D=cut(means2D, s0 * vps, s1 * vps), scale_modifier=scale_modifier, sh_degree=sh_degree,
-                prefiltered=prefiltered, pair_capacity=cap, binning=binning, colors_ready=colors_ready, debug=debug))
+                prefiltered=prefiltered, pair_capacity=cap, binning=binning, colors_ready=colors_ready, debug=debug,
+                min_opacity=min_opacity))
         return tuple(torch.cat(parts, 0) for parts in zip(*outs))
     if isinstance(pair_capacity, (list, tuple)):
         pair_capacity = pair_capacity[0]
@@ -472,6 +478,7 @@ def render_batch(means3D, opacities, cams, image_height, image_width, bg, colors
         means2D = torch.empty((V, P, 3), dtype=torch.float32, device=means3D.device)
     cfg = dict(W=int(image_width), H=int(image_height), scale_modifier=float(scale_modifier), sh_degree=int(sh_degree),
                prefiltered=bool(prefiltered), pair_capacity=pair_capacity, colors_ready=colors_ready, debug=bool(debug),
+               min_opacity=float(min_opacity),
                binning=binning if binning is not None else os.environ.get("OCRF_BINNING", "split"))
     if P == 0:
         z = lambda c: torch.zeros((V, c, cfg["H"], cfg["W"]), dtype=torch.float32, device=means3D.device)  # noqa

@@ -369,3 +369,35 @@ print("PARITY_OK")
                PYTHONPATH=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
     assert r.returncode == 0 and "PARITY_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_foreground_filter_changes_pair_counts_not_results():
+    """render_batch(min_opacity=...): Gaussians below the blend threshold are culled before projection (SURVEY 8 f-1);
+    images and gradients are the unfiltered ones, radii of the culled Gaussians are 0 and the pair count shrinks."""
+    W, H, V = 176, 64, 3
+    g, cams = util.small_scene("ring", P=6000, seed=51, W=W, H=H, n_views=V)
+    rng = np.random.default_rng(2)
+    g["opacities"] = np.where(rng.random(g["opacities"].shape) < 0.6, np.float32(0.003) * rng.random(g["opacities"].shape),
+                              g["opacities"]).astype(np.float32)   # 60 % "empty space" voxels
+    names = ("means3D", "scales", "rotations", "opacities", "colors")
+    gcol = torch.randn(V, 3, H, W, device="cuda")
+    gop = torch.randn(V, 1, H, W, device="cuda")
+    res = []
+    for thr in (0.0, 1.0):  # (values above 1/255 are clamped to it)
+        t = {k: torch.from_numpy(g[k]).unsqueeze(0).cuda().requires_grad_(True) for k in names}
+        R.KEEP_STATE = True
+        color, radii, depth, opac = R.render_batch(t["means3D"], t["opacities"], util.cams_tensor(cams), H, W,
+                                                   torch.zeros(3, device="cuda"), colors_precomp=t["colors"],
+                                                   scales=t["scales"], rotations=t["rotations"], min_opacity=thr)
+        n_pairs = int(R.last_state()["num_pairs"])
+        R.KEEP_STATE = False
+        torch.autograd.backward([color, opac], [gcol, gop])
+        res.append((color.detach(), depth, opac.detach(), radii, n_pairs, {k: t[k].grad for k in names}))
+    (c0, d0, o0, r0, n0, g0), (c1, d1, o1, r1, n1, g1) = res
+    assert torch.equal(c0, c1) and torch.equal(d0, d1) and torch.equal(o0, o1)
+    low = torch.from_numpy(g["opacities"].reshape(-1) < 1.0 / 255.0).cuda()
+    assert int(r1[:, low].abs().max()) == 0 and torch.equal(r0[:, ~low], r1[:, ~low])
+    assert n1 < 0.6 * n0, (n0, n1)
+    for k in names:
+        assert util.rel_err(g1[k].cpu().numpy(), g0[k].cpu().numpy()) <= 1e-6, k
+    assert float(g0["opacities"].reshape(-1)[low].abs().max()) == 0.0   # they never blended
