@@ -119,8 +119,12 @@ __global__ void __launch_bounds__(MB * 128 + 64, 2 / MB) render_backward_tc_kern
     float bgdot = 0.f;
     {
       float gv[CP];
+      const float* gp = dL_dpix + (size_t)view * C * HW + (inside ? pix : 0);  // one pointer, stepped by a channel plane
 #pragma unroll
-      for (int k = 0; k < CP; k++) gv[k] = (inside && k < C) ? dL_dpix[((size_t)view * C + k) * HW + pix] : 0.f;
+      for (int k = 0; k < CP; k++) {
+        gv[k] = (inside && (C == CP || k < C)) ? __ldg(gp) : 0.f;
+        if (C == CP || k + 1 < C) gp += HW;
+      }
       float* grow = &sm.g[warp][lane][0];
 #pragma unroll
       for (int c0 = 0; c0 < CP; c0 += 16) {
@@ -201,7 +205,7 @@ __global__ void __launch_bounds__(MB * 128 + 64, 2 / MB) render_backward_tc_kern
             const float G = ex2_approx_b(power);
             const float alpha = fminf(0.99f, bq.y * G);
             const bool ok = j < cnt && (int)__float_as_uint(bq.z) <= nc && power <= 0.0f && alpha >= 1.0f / 255.0f;
-            const float r = __fdividef(1.f, 1.f - alpha);
+            const float r = rcp_approx(1.f - alpha);  // 1 - alpha in [0.01, 1]: one MUFU.RCP
             Gv[i] = ok ? G : 0.f;  // (a garbage row past the end of the list must not put a NaN into the sums)
             al[i] = ok ? alpha : 0.f;
             rc[i] = ok ? r : 1.f;
