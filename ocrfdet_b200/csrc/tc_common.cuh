@@ -103,7 +103,7 @@ __device__ __forceinline__ void mbar_wait_wd(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
     __nanosleep(spins < 8 ? 20u : 100u);
-    if (++spins > (1u << 22)) __trap();
+    if (++spins > (1u << 26)) __trap();  // ~7 s of back-off: a protocol error, not a slow peer
   }
 }
 
