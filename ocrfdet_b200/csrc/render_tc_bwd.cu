@@ -46,7 +46,7 @@ struct BwdSmem {
   alignas(16) float g[NWW][32][GP];
   alignas(16) float w[NWW][FB][WP];
   alignas(16) float t[NWW][FB][WP];     // t = G * dL/dalpha per (record, pixel): the operand of the moment product
-  alignas(8) uint64_t ready_f[2], free_f[2], ready_d[2], free_d[2];
+  alignas(8) uint64_t ready_f[2], free_f[2], ready_d[2], free_d[2], g_ready;
   uint32_t tmem;
 };
 
@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(MB * 128 + 64, 2 / MB) render_backward_tc_kern
       mbar_init(&sm.ready_d[s], 1);
       mbar_init(&sm.free_d[s], NWW);
     }
+    mbar_init(&sm.g_ready, NWW);
     mbar_fence_init();
   }
   if (warp == NWW) tmem_alloc<BWD_TMEM_COLS>(&sm.tmem);
@@ -145,7 +146,8 @@ __global__ void __launch_bounds__(MB * 128 + 64, 2 / MB) render_backward_tc_kern
       tmem_wait_st();
     }
     fence_before_sync();
-    __syncthreads();  // (A) G is in tensor memory: the MMA warp may start
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&sm.g_ready);  // this warp's rows of G are in tensor memory (the MMA warp waits for all)
     float S = 0.f;    // g . (colour accumulated behind this pixel), see render_backward_generic_kernel
     float* my_w = &sm.w[warp][0][lane];
     float* my_t = &sm.t[warp][0][lane];
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(MB * 128 + 64, 2 / MB) render_backward_tc_kern
   } else if (warp == NWW) {
     // ------------------------------------------------ MMA issuer ------------------------------------------------
     constexpr uint32_t IDESC = idesc_tf32(128, BR);
-    __syncthreads();  // (A)
+    mbar_wait_wd(&sm.g_ready, 0);
     fence_after_sync();
     for (int b = 0; b < nb; b++) {
       const int s = b & 1;
@@ -401,7 +403,6 @@ __global__ void __launch_bounds__(MB * 128 + 64, 2 / MB) render_backward_tc_kern
       if (lane == 0) mbar_arrive(&sm.ready_f[s]);
     };
     issue(0);
-    __syncthreads();  // (A)
     for (int b = 0; b < nb; b++) {
       if (b + 1 < nb) {
         issue(b + 1);
