@@ -98,3 +98,34 @@ def test_graphed_step_with_captured_host_copies_is_a_host_to_host_step():
     assert torch.equal(step.outs[0], color)
     for k in INPUTS:
         assert util.rel_err(ghost[k].numpy(), leaf[k].grad.cpu().numpy()) <= 1e-6, k
+
+
+def test_graphed_step_with_80_channels_runs_the_tensor_core_kernels_and_survives_overflow():
+    """The tcgen05 blend kernels under CUDA-graph capture (tensor-memory allocation, mbarrier pipelines and the
+    dependent-launch edges are all inside the graph), equal to the eager step; and with a capacity far below the pair
+    count they render background (empty lists: no product is ever issued) and the overflow is reported."""
+    from ocrfdet_b200 import _lib, rasterizer as R
+    from ocrfdet_b200.graphs import GraphedRenderStep, INPUTS
+    W, H, P, V, C = 176, 64, 4000, 2, 80
+    g, cams = util.small_scene("ring", P=P, seed=61, W=W, H=H, n_views=V, channels=C)
+    cam_t = util.cams_tensor(cams)
+    gc = util.to_cuda(g)
+    bg = torch.linspace(0.0, 1.0, C, device="cuda")
+    gcol = torch.randn(V, C, H, W, device="cuda")
+    gop = torch.randn(V, 1, H, W, device="cuda")
+    leaf = {k: gc[k].clone().unsqueeze(0).requires_grad_(True) for k in INPUTS}
+    color, radii, depth, opac = R.render_batch(leaf["means3D"], leaf["opacities"], cam_t, H, W, bg,
+                                               colors_precomp=leaf["colors"], scales=leaf["scales"], rotations=leaf["rotations"])
+    torch.autograd.backward([color, opac], [gcol, gop])
+    step = GraphedRenderStep(S=1, P=P, cams=cam_t, height=H, width=W, channels=C, pair_capacity=400_000, bg=bg)
+    (c1, r1, d1, o1), g1 = step(grad_color=gcol, grad_opacity=gop, **{k: gc[k].unsqueeze(0) for k in INPUTS})
+    step.check_overflow()
+    assert torch.equal(color, c1) and torch.equal(depth, d1) and torch.equal(opac, o1)
+    for k in INPUTS:
+        assert util.rel_err(g1[k].cpu().numpy(), leaf[k].grad.cpu().numpy()) <= 2e-6, k
+    small = GraphedRenderStep(S=1, P=P, cams=cam_t, height=H, width=W, channels=C, pair_capacity=500, bg=bg)
+    (c2, _, _, o2), g2 = small(grad_color=gcol, grad_opacity=gop, **{k: gc[k].unsqueeze(0) for k in INPUTS})
+    assert torch.equal(c2, bg.view(1, C, 1, 1).expand(V, C, H, W)) and float(o2.abs().max()) == 0.0
+    assert all(float(g2[k].abs().max()) == 0.0 for k in INPUTS)
+    with pytest.raises(_lib.OcrfError):
+        small.check_overflow()
