@@ -26,7 +26,10 @@ namespace hoaconv {
 constexpr int NLEV = 5;
 constexpr int MAXC = 16;
 constexpr float BN_EPS = 1e-5f;
-constexpr int THREADS = 256;
+#ifndef OCRF_HOAC_THREADS
+#define OCRF_HOAC_THREADS 256
+#endif
+constexpr int THREADS = OCRF_HOAC_THREADS;
 
 // parameter offsets inside the packed vector (= named_parameters() order of the reference module)
 struct LevelDef {

@@ -68,13 +68,54 @@ class _PeerBuffers:
     def all_gather(self, send):
         """Runs on the CURRENT stream.  Returns this rank's buffer [world, vmax, 1, H, W]; it is overwritten by the
         next gather of the same shape (the opening barrier of that call waits until every rank got there, i.e. is
-        done with the previous contents in stream order)."""
+        done with the previous contents in stream order).
+
+        Ten stream operations per step (two barriers, `world` copies) cost the launching thread ~0.1 ms at 8 ranks --
+        with eight processes on one host that showed up as jitter that every rank then waits for.  The exchange
+        [barrier, pushes of my slot to the peers, barrier] has fixed addresses, so it is captured once as a CUDA graph:
+        a gather is the local copy into my slot plus ONE graph launch.  OCRF_GATHER_GRAPH=0 keeps the eager sequence."""
+        mine = self.views[self.rank][self.rank]
+        if self._graph is None and self._graph_ok:
+            try:
+                self._capture()
+            except Exception as e:  # noqa: BLE001  (capture of the signal-pad barrier not supported: stay eager)
+                self._graph_ok = False
+                warnings.warn("opacity-map gather: CUDA-graph capture of the peer exchange failed (%s); issuing it "
+                              "eagerly" % (e,))
+        if self._graph is not None:
+            mine.copy_(send)
+            self._graph.replay()
+            return self.views[self.rank]
         self.hdl.barrier(channel=0)
         for i in range(self.world):  # start with myself, then ring order: no two ranks push to the same peer first
             peer = (self.rank + i) % self.world
             self.views[peer][self.rank].copy_(send)  # contiguous same-dtype copy: cudaMemcpyAsync -> copy engine
         self.hdl.barrier(channel=1)  # every rank's pushes are complete and visible
         return self.views[self.rank]
+
+    _graph = None
+    _graph_ok = os.environ.get("OCRF_GATHER_GRAPH", "1") != "0"
+
+    def _exchange(self):
+        mine = self.views[self.rank][self.rank]
+        self.hdl.barrier(channel=0)  # every peer is done with the previous contents of ITS buffer
+        for i in range(1, self.world):
+            peer = (self.rank + i) % self.world
+            self.views[peer][self.rank].copy_(mine)
+        self.hdl.barrier(channel=1)
+
+    def _capture(self):
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            self._exchange()  # warm-up outside the capture (collective: every rank does the same)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._exchange()
+        self._graph = g
 
 
 def _nccl_all_gather(send, world, vmax, group):

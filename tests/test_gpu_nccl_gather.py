@@ -40,6 +40,7 @@ def _worker(rank, world, port, q):
                     res[(transport, num_samples, rep)] = ok
         res["peer_used"] = _PeerBuffers._failed is None and len(_PeerBuffers._cache) > 0
         res["peer_error"] = str(_PeerBuffers._failed)
+        res["graphed"] = all(pb._graph is not None for pb in _PeerBuffers._cache.values())
         q.put((rank, res))
         dist.barrier()
         dist.destroy_process_group()
@@ -64,4 +65,5 @@ def test_opacity_map_gather_content_on_gpus():
         bad = [k for k, v in r.items() if isinstance(k, tuple) and not v]
         assert not bad, "rank %d: wrong gather content / gradient for %s" % (rank, bad)
         assert r["peer_used"], "the copy-engine transport was not used: %s" % r["peer_error"]
+        assert r["graphed"], "the peer exchange was not captured as a CUDA graph"
     assert all(p.exitcode == 0 for p in procs)
