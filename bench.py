@@ -341,6 +341,38 @@ def run_ours(args, rank, world, device):
         torch.cuda.synchronize()
         dist.barrier()
     torch.cuda.synchronize()
+    uncoupled = None
+    if world > 1:
+        # every rank renders its OWN scene (seed 1234 + 1000 rank): the per-step exchange makes all ranks advance at the
+        # pace of the slowest one.  Time each rank alone (same step, no exchange) so that the line shows how much of
+        # the N-GPU step is that imbalance and how much is the exchange itself.
+        def step_alone():
+            for k in names:
+                dev[k].grad = None
+            color, radii, depth, opac = render(dev)
+            torch.autograd.backward([color, opac], [gcol, gop])
+        for _ in range(5):
+            flush.fill_(1)
+            step_alone()
+        torch.cuda.synchronize()
+        ua = []
+        for _ in range(20):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            step_alone()
+            e1.record()
+            ua.append((e0, e1))
+        torch.cuda.synchronize()
+        mine = torch.tensor([sum(a.elapsed_time(b) for a, b in ua) / len(ua)], device=device)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        uncoupled = [round(float(t[0]), 4) for t in allr]
+        for _ in range(10):  # back in step with the exchange
+            flush.fill_(1)
+            step()
+        torch.cuda.synchronize()
+        dist.barrier()
     sampler.sm, sampler.bits = [], 0  # keep only the samples of the timed region
     evs = []
     for _ in range(8):
@@ -650,6 +682,7 @@ def run_ours(args, rank, world, device):
            "warmup": args.warmup, "ms_per_step": ms_per_step, "ms_per_step_median_rank0": median_ms,
            "ms_per_step_max_rank0": per_step[-1], "ms_steps_rank0": [round(x, 3) for x in step_ms],
            "ms_per_render": ms_per_step / VIEWS,
+           "ms_per_step_each_rank_alone": uncoupled,  # (N > 1) the same step without the exchange, per rank's own scene
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": "BASELINE config 2: 1 sample x 6 views 256x704, 100k voxel-grid Gaussians, "
                                   "colour+depth+opacity fwd+bwd, per GPU", "views_per_step_per_gpu": VIEWS,
