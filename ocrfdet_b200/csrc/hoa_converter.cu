@@ -59,7 +59,10 @@ struct Net {
   const float* run_var;
   float* t[NLEV];         // pre-norm block outputs [B,cout,h,w]
   float* e[NLEV];         // activations after ReLU (+ position at level 0), before the gate
-  float* bnsum;           // [NLEV][MAXC][2] sum, sum of squares (training)
+  double* bnsum;          // [NLEV][MAXC][2] sum, sum of squares (training).  fp64: the sums of the blocks arrive in any
+                          // order, and in fp32 their last bits -- hence the batch statistics, the activations and,
+                          // through near-equal maxima, the ARG-MAX of a gate -- differed from run to run
+  float* stats_out;       // optional [NLEV][MAXC][2] copy for the caller (running statistics)
   unsigned long long* maxkey;  // [NLEV][B][MAXC] (ordered value << 32 | ~index)
 };
 
@@ -76,9 +79,10 @@ __device__ __forceinline__ void bn_stats(const Net& n, int l, int c, float& mean
   if (n.train) {
     const int hw = (n.S >> LEVELS[l].shift) * (n.S >> LEVELS[l].shift);
     const float cnt = (float)n.B * (float)hw;
-    const float s = n.bnsum[(l * MAXC + c) * 2], s2 = n.bnsum[(l * MAXC + c) * 2 + 1];
-    mean = s / cnt;
-    const float var = fmaxf(s2 / cnt - mean * mean, 0.f);
+    const double s = n.bnsum[(l * MAXC + c) * 2], s2 = n.bnsum[(l * MAXC + c) * 2 + 1];
+    const double m = s / (double)cnt;
+    mean = (float)m;
+    const float var = (float)fmax(s2 / (double)cnt - m * m, 0.0);
     inv = rsqrtf(var + BN_EPS);
   } else {
     mean = n.run_mean[l * MAXC + c];
@@ -166,6 +170,23 @@ __device__ void block_sums_to(const float* vals, int count, float* scratch, floa
   }
 }
 
+// the same with an fp64 destination (a block's own sum is computed in a fixed order; only the order of the blocks varies)
+__device__ void block_sums_to_f64(const float* vals, int count, float* scratch, double* dst) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  __syncthreads();
+  for (int k = 0; k < count; k++) {
+    const float v = warp_sum_c(vals[k]);
+    if (lane == 0) scratch[warp * count + k] = v;
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < count; k += THREADS) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < THREADS / 32; w++) t += scratch[w * count + k];
+    if (t != 0.f) atomicAdd(dst + k, (double)t);
+  }
+}
+
 // ---- forward ---------------------------------------------------------------------------------------------------------
 // conv: thread = pixel of block l; grid (ceil(h*w / THREADS), B)
 __global__ void __launch_bounds__(THREADS) conv_kernel(Net n, int l) {
@@ -213,7 +234,7 @@ __global__ void __launch_bounds__(THREADS) conv_kernel(Net n, int l) {
       v[2 * o] = tv;
       v[2 * o + 1] = tv * tv;
     }
-    block_sums_to(v, 2 * L.cout, s_red, n.bnsum + (size_t)l * MAXC * 2);
+    block_sums_to_f64(v, 2 * L.cout, s_red, n.bnsum + (size_t)l * MAXC * 2);
   }
 }
 
@@ -254,6 +275,8 @@ __global__ void __launch_bounds__(THREADS) out_kernel(Net n, float* __restrict__
   __shared__ float s_g[MAXC];
   const int b = blockIdx.y;
   if (threadIdx.x == 0) gate_values(n, NLEV - 1, b, s_g, nullptr, nullptr);
+  if (n.stats_out != nullptr && blockIdx.x == 0 && b == 0)  // the batch statistics for the caller (every block is done)
+    for (int i = threadIdx.x; i < NLEV * MAXC * 2; i += THREADS) n.stats_out[i] = (float)n.bnsum[i];
   __syncthreads();
   const int pix = blockIdx.x * THREADS + threadIdx.x, hw = n.S;
   if (pix >= hw * hw) return;
@@ -618,8 +641,8 @@ static WsLayout ws_layout(int B, int S) {
     w.gin[l] = off; off += (size_t)B * H_CIN[l] * hw;
   }
   off = (off + 31) & ~size_t(31);
-  w.small = off;  // bnsum [5][16][2] | bsum [5][16][2] | gsum [5][B][16] | maxkey u64 [5][B][16]
-  off += 2 * NLEV * MAXC * 2 + (size_t)NLEV * B * MAXC + 2 * (size_t)NLEV * B * MAXC;
+  w.small = off;  // bnsum f64 [5][16][2] | bsum [5][16][2] | gsum [5][B][16] | maxkey u64 [5][B][16]
+  off += 3 * NLEV * MAXC * 2 + (size_t)NLEV * B * MAXC + 2 * (size_t)NLEV * B * MAXC;
   w.total = off + 32;
   return w;
 }
@@ -631,8 +654,8 @@ static void bind(Net& n, Grad* g, const WsLayout& w, float* ws, int B) {
     if (g) { g->genc[l] = ws + w.genc[l]; g->gin[l] = ws + w.gin[l]; }
   }
   float* sm = ws + w.small;
-  n.bnsum = sm;
-  float* bsum = sm + NLEV * MAXC * 2;
+  n.bnsum = reinterpret_cast<double*>(sm);
+  float* bsum = sm + 2 * NLEV * MAXC * 2;
   float* gsum = bsum + NLEV * MAXC * 2;
   n.maxkey = reinterpret_cast<unsigned long long*>(gsum + (size_t)NLEV * B * MAXC);
   if (g) { g->bsum = bsum; g->gsum = gsum; }
@@ -655,6 +678,8 @@ extern "C" int ocrf_hoa_converter_forward(void* stream, int32_t B, int32_t S, in
   n.B = B; n.S = S; n.train = train ? 1 : 0; n.pos_batched = position_batched ? 1 : 0;
   n.x = x; n.pos = position; n.p = params; n.run_mean = running_mean; n.run_var = running_var;
   bind(n, nullptr, w, workspace, B);
+  n.stats_out = (train && batch_stats) ? batch_stats : nullptr;  // sum / sum of squares per level and channel: the host
+                                                                 // derives mean, var (running statistics); out_kernel writes it
   cudaError_t e = cudaMemsetAsync(workspace + w.small, 0, (w.total - 32 - w.small) * sizeof(float), st);
   if (e != cudaSuccess) return (int)e;
   for (int l = 0; l < NLEV; l++) {
@@ -664,10 +689,6 @@ extern "C" int ocrf_hoa_converter_forward(void* stream, int32_t B, int32_t S, in
     OCRF_LAUNCH(act_kernel, dim3(gx, H_COUT[l], B), dim3(THREADS), 0, st, n, l);
   }
   OCRF_LAUNCH(out_kernel, dim3((unsigned)((S * S + THREADS - 1) / THREADS), B), dim3(THREADS), 0, st, n, out);
-  if (train && batch_stats) {  // sum / sum of squares per level and channel: the host derives mean, var (running stats)
-    e = cudaMemcpyAsync(batch_stats, n.bnsum, NLEV * MAXC * 2 * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    if (e != cudaSuccess) return (int)e;
-  }
   OCRF_CHECK_LAST();
   return 0;
 }
