@@ -82,6 +82,29 @@ __global__ void __launch_bounds__(MB * 128 + 64, 2 / MB) render_backward_tc_kern
   const int nb = (mc + BR - 1) / BR;
   const int s_idx = view / views_per_sample;
 
+  // The workers put their global loads (80 KB of upstream gradient per tile) in flight BEFORE the CTA's set-up barrier:
+  // with one CTA per SM nothing else overlaps a tile's start-up.
+  const size_t HW = (size_t)H * W;
+  const int wt = half * 4 + (warp < NWW ? warp : 0);  // warp of the tile: an 8 x 4 pixel block
+  const int px = tile_x * TILE + (wt & 1) * 8 + (lane & 7);
+  const int py = blockIdx.y * TILE + (wt >> 1) * 4 + (lane >> 3);
+  const bool inside = warp < NWW && px < W && py < H;
+  const size_t pix = (size_t)py * W + px;
+  float gv[CP];
+  float bgdot = 0.f, Tf = 0.f, gop = 0.f;
+  int nc = 0;
+  if (warp < NWW) {
+    const float* gp = dL_dpix + (size_t)view * C * HW + (inside ? pix : 0);  // one pointer, stepped by a channel plane
+#pragma unroll
+    for (int k = 0; k < CP; k++) {
+      gv[k] = (inside && (C == CP || k < C)) ? __ldg(gp) : 0.f;
+      if (C == CP || k + 1 < C) gp += HW;
+    }
+    Tf = inside ? final_T[view * HW + pix] : 0.f;
+    nc = inside ? (int)n_contrib[view * HW + pix] : 0;
+    gop = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
+  }
+
   if (tid == 0) {
 #pragma unroll
     for (int s = 0; s < 2; s++) {
@@ -104,28 +127,11 @@ __global__ void __launch_bounds__(MB * 128 + 64, 2 / MB) render_backward_tc_kern
     const float* fbase = feats + (size_t)s_idx * P * C;
     (void)fbase;
     float* gfbase = dL_dfeats + (size_t)s_idx * P * C;
-    const size_t HW = (size_t)H * W;
-    const int wt = half * 4 + warp;  // warp of the tile: an 8 x 4 pixel block
-    const int px = tile_x * TILE + (wt & 1) * 8 + (lane & 7);
-    const int py = blockIdx.y * TILE + (wt >> 1) * 4 + (lane >> 3);
-    const bool inside = px < W && py < H;
-    const size_t pix = (size_t)py * W + px;
     const float fx = (float)px, fy = (float)py;
-    const float Tf = inside ? final_T[view * HW + pix] : 0.f;
-    const int nc = inside ? (int)n_contrib[view * HW + pix] : 0;
     const int mb = warp >> 2;
     const uint32_t lane_addr = tm + ((uint32_t)((warp & 3) * 32) << 16);
-    // this pixel's upstream gradient: to tensor memory (g, g_lo) and to the shared tile the mma.sync product reads.
-    // All loads are issued before the first store: one memory round trip for the row instead of one per 16 channels.
-    float bgdot = 0.f;
+    // this pixel's upstream gradient: to tensor memory (g, g_lo) and to the shared tile the mma.sync product reads
     {
-      float gv[CP];
-      const float* gp = dL_dpix + (size_t)view * C * HW + (inside ? pix : 0);  // one pointer, stepped by a channel plane
-#pragma unroll
-      for (int k = 0; k < CP; k++) {
-        gv[k] = (inside && (C == CP || k < C)) ? __ldg(gp) : 0.f;
-        if (C == CP || k + 1 < C) gp += HW;
-      }
       float* grow = &sm.g[warp][lane][0];
 #pragma unroll
       for (int c0 = 0; c0 < CP; c0 += 16) {
@@ -159,10 +165,11 @@ __global__ void __launch_bounds__(MB * 128 + 64, 2 / MB) render_backward_tc_kern
       for (int e = 0; e < 8; e++) {
         const int q = 8 * (e >> 1) + tig + 4 * (e & 1);  // warp-local pixel = the lane that owns it
         const float lx = (float)((wt & 1) * 8 + (q & 7)) - 7.5f, ly = (float)((wt >> 1) * 4 + (q >> 3)) - 7.5f;
-        bmono[e] = gid == 0 ? 1.f : gid == 1 ? lx : gid == 2 ? ly : gid == 3 ? lx * lx : gid == 4 ? lx * ly : gid == 5 ? ly * ly : 0.f;
+        const float xm = (gid == 1 || gid == 4) ? lx : gid == 3 ? lx * lx : 1.f;  // (selects, no branches)
+        const float ym = (gid == 2 || gid == 4) ? ly : gid == 5 ? ly * ly : 1.f;
+        bmono[e] = gid < 6 ? xm * ym : 0.f;
       }
     }
-    const float gop = (inside && dL_dopa) ? dL_dopa[view * HW + pix] : 0.f;
     const float gob = Tf * (gop - bgdot);
     float T = Tf;
     const float ddelx_dx = 0.5f * W, ddely_dy = 0.5f * H;
