@@ -610,8 +610,8 @@ def run_ours(args, rank, world, device):
         # the results that came back are the step's: same gradients as the eager step (bit-exact is not expected:
         # atomics), loss equal to the eager loss
         ref_loss = float(torch.dot(insts[0][0].outs[0].detach().reshape(-1), gcol_flat) + torch.dot(insts[0][0].outs[3].detach().reshape(-1), gop_flat))
-        assert abs(float(insts[0][2][0]) - ref_loss) <= 1e-3 * (1 + abs(ref_loss)), "graphed e2e step returned a stale loss"
-        assert all(bool(torch.isfinite(insts[0][1][k]).all()) and float(insts[0][1][k].abs().max()) > 0 for k in names)
+        verified = bool(abs(float(insts[0][2][0]) - ref_loss) <= 1e-3 * (1 + abs(ref_loss))) and all(
+            bool(torch.isfinite(insts[0][1][k]).all()) and float(insts[0][1][k].abs().max()) > 0 for k in names)
         if world > 1:
             tt = torch.tensor([t_tot], device=device)
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -620,6 +620,7 @@ def run_ours(args, rank, world, device):
         return {"value": world * VIEWS / (t_tot / K / 1e3), "unit": "views/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": t_tot / K, "steps": K,
                 "d2h": "loss + all parameter gradients", "host_issue_ms_per_step": host_ms,
+                "results_on_host_verified": verified,  # the loss that came back equals the step's, the gradients are finite and non-zero
                 "mode": ("GraphedRenderStep with captured host<->device copies (L2 flush, H2D, forward, loss, backward, "
                          "D2H = one graph launch per step), %d instances replayed in turn on their own streams; "
                          "`e2e_serial` is the same step issued eagerly with a host synchronisation per step") % n_inst}
@@ -631,6 +632,11 @@ def run_ours(args, rank, world, device):
     # why config 3 (8 samples per call) reaches 13 k views/s
     e2e = time_e2e_graphed(int(os.environ.get("OCRF_E2E_STREAMS", "2"))) if cap["n"] is not None else e2e_serial
     e2e_streams4 = time_e2e_graphed(4) if (cap["n"] is not None and world == 1) else None
+    # a graphed run whose results did not check out on the host is not a measurement: report the eagerly issued one
+    if not e2e.get("results_on_host_verified", True):
+        e2e = dict(e2e_serial, note="graphed e2e failed its host-side result check; this is the eagerly issued step")
+    if e2e_streams4 is not None and not e2e_streams4["results_on_host_verified"]:
+        e2e_streams4 = None
 
     # ---- the UNMODIFIED caller: one GaussianRasterizer call per view through the reference's import name ----
     # (GR:39-70 as called from VT:1153: settings tuple per view, a zeros means2D leaf, exact sizing with its 8-byte
