@@ -20,6 +20,8 @@
 // eight partial sums.  Any segment size works (a CTA loops over sub-tiles of 4096 keys).
 #include <cooperative_groups.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace cg = cooperative_groups;
@@ -59,8 +61,10 @@ __device__ __forceinline__ void dsmem_add_u32(uint32_t* remote, uint32_t v) {
 __global__ void __cluster_dims__(VS_CLUSTER, 1, 1) __launch_bounds__(VS_THREADS) visible_sort_kernel(
     int P, const uint32_t* __restrict__ view_start, uint64_t* keys0, uint32_t* vals0, uint64_t* keys1, uint32_t* vals1,
     const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ offsets,
-    uint32_t* __restrict__ sorted_offsets) {
+    uint32_t* __restrict__ sorted_offsets, uint32_t skip_upto) {
   pdl_enter();
+  // (views of at most skip_upto keys were sorted by visible_sort_cta_kernel; the whole cluster sees the same count)
+  if (view_start[blockIdx.y + 1] - view_start[blockIdx.y] <= skip_upto) return;
   cg::cluster_group cluster = cg::this_cluster();
   // digit counts of MY part of the segment, three buffers in rotation: pass p reads [p % 3] (all CTAs, remotely), fills
   // [(p + 1) % 3] for the next pass (remote reductions of whoever writes into my part) and clears [(p + 2) % 3], which
@@ -231,13 +235,234 @@ __global__ void __cluster_dims__(VS_CLUSTER, 1, 1) __launch_bounds__(VS_THREADS)
   cluster.sync();  // no CTA leaves while a peer may still read its shared memory
 }
 
+// ---- the same sort with the keys in REGISTERS: the kernel that runs for up to 131 072 visible Gaussians per view ----
+// What the kernel above pays per pass (measured: ~12 us at 17 % issue-active for 2.4 k keys per CTA) is not arithmetic:
+// every key sends a remote shared-memory reduction for the next histogram, the scatter goes through L2, a
+// __threadfence and a cluster barrier close the pass, and the next pass starts with an L2 round trip for its keys.
+// Here a cluster of 8 CTAs holds the view's keys as (depth, position in the segment) in registers -- R = ceil(n / 8192)
+// rows of 32 per warp -- and a pass is: rank inside the warp, per-CTA digit totals, ONE cluster barrier, read the eight
+// totals through distributed shared memory, scatter every key with one 8-byte remote shared-memory store to the CTA
+// that owns its destination slot, a second cluster barrier, read the own slots back.  Nothing touches global memory
+// between the first load and the result; the Gaussian indices are gathered once, after the last pass.
+//
+// Ranking: tools/probe/match_probe.cu measured MATCH.ANY on this part at ~2 cycles per DISTINCT value per SM (64 cycles
+// for 32 distinct digits, 4 for one), against 31 cycles flat for eight ballots.  The three low digit places of a depth
+// are noise (32 distinct digits per warp): eight ballots; the top byte (sign + 7 exponent bits) takes a handful of
+// values: match.  (A first version with ONE CTA per view and 20 rows per warp was correct and 2x SLOWER than the
+// kernel above -- 115 vs 60 us: 768 matches per pass on one SM's match unit.)
+constexpr int VR_CLUSTER = 8;
+constexpr int VR_THREADS = 1024;
+constexpr int VR_WARPS = VR_THREADS / 32;
+constexpr int VR_ITEMS = 16;
+constexpr uint32_t VR_CAP = (uint32_t)VR_CLUSTER * VR_THREADS * VR_ITEMS;  // 131 072 keys per view
+constexpr uint32_t VR_IDX_MASK = 0x3ffffu;                                  // position in the segment (< 2^17), rank above
+
+struct alignas(16) VrFixed {  // fixed part of the dynamic shared memory; the (depth, position) slots of the CTA follow
+  uint16_t warp_hist[VR_WARPS][256];  // per-warp digit counts (<= 512), then the exclusive prefix over the warps
+  uint32_t cta_cnt[256];              // digit counts of this CTA's slots (read by the whole cluster)
+  uint32_t base[256];                 // first destination of this CTA's keys of every digit
+  uint32_t scan[VR_WARPS];
+  uint32_t total;
+};
+
+__device__ __forceinline__ uint32_t vr_peers(uint32_t d, bool few_values) {  // lanes of the warp holding my digit
+  if (few_values) return __match_any_sync(0xffffffffu, d);
+  uint32_t peers = 0xffffffffu;
+#pragma unroll
+  for (int b = 0; b < 8; b++) {
+    const bool bit = (d >> b) & 1u;
+    const uint32_t vote = __ballot_sync(0xffffffffu, bit);
+    peers &= bit ? vote : ~vote;
+  }
+  return peers;
+}
+
+__global__ void __cluster_dims__(VR_CLUSTER, 1, 1) __launch_bounds__(VR_THREADS, 1) visible_sort_reg_kernel(
+    int P, const uint32_t* __restrict__ view_start, uint64_t* keys0, uint32_t* vals0,
+    const uint32_t* __restrict__ tiles_touched, const uint32_t* __restrict__ offsets,
+    uint32_t* __restrict__ sorted_offsets) {
+  pdl_enter();
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(16) unsigned char vr_raw[];
+  VrFixed& sm = *reinterpret_cast<VrFixed*>(vr_raw);
+  uint2* buf = reinterpret_cast<uint2*>(vr_raw + sizeof(VrFixed));  // [1024 R] slots of this CTA
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t rank = cluster.block_rank();
+  const int v = blockIdx.y;
+  const uint32_t seg_b = view_start[v], n = view_start[v + 1] - seg_b;
+  if (n == 0 || n > VR_CAP) return;  // (the whole cluster; larger views are sorted by visible_sort_kernel)
+  // R rows of 32 consecutive slots per warp, 1024 R slots per CTA, CTA-major: slots past n hold the largest key
+  const uint32_t R = (n + VR_CLUSTER * VR_THREADS - 1) / (VR_CLUSTER * VR_THREADS);
+  const uint32_t per = (uint32_t)VR_THREADS * R;
+  const uint32_t inv_R = (65536u + R - 1) / R;  // (x * inv_R) >> 16 == x / R for x < 8 R <= 128
+  const uint32_t local_base = (uint32_t)warp * 32u * R;
+  const uint32_t glob_base = rank * per + local_base;
+  const uint32_t lt_mask = (1u << lane) - 1;
+  uint16_t* my_hist = sm.warp_hist[warp];
+
+  uint32_t k[VR_ITEMS], m[VR_ITEMS];  // depth bits; position in the segment | rank of the pass << 18
+  {
+    const uint32_t* lo = reinterpret_cast<const uint32_t*>(keys0 + seg_b);  // low word of (view << 32 | depth)
+#pragma unroll
+    for (int i = 0; i < VR_ITEMS; i++) {
+      k[i] = 0xffffffffu;
+      m[i] = 0u;
+      if (i < R) {
+        const uint32_t loc = glob_base + i * 32 + lane;
+        if (loc < n) k[i] = lo[2 * (size_t)loc];
+        m[i] = loc;
+      }
+    }
+  }
+
+#pragma unroll 1
+  for (int pass = 0; pass < 4; pass++) {
+    const int shift = 8 * pass;
+    const bool few_values = pass == 3;
+    for (int e = tid; e < VR_WARPS * 128; e += VR_THREADS) reinterpret_cast<uint32_t*>(sm.warp_hist)[e] = 0u;
+    __syncthreads();
+    // stable rank inside the warp, row by row (the padding keys are ordinary keys: they sort behind everything)
+#pragma unroll
+    for (int i = 0; i < VR_ITEMS; i++) {
+      if (i < R) {
+        const uint32_t d = (k[i] >> shift) & 255u;
+        const uint32_t peers = vr_peers(d, few_values);
+        const uint32_t b4 = my_hist[d];
+        __syncwarp();
+        if ((peers & lt_mask) == 0) my_hist[d] = (uint16_t)(b4 + __popc(peers));
+        __syncwarp();
+        m[i] = (m[i] & VR_IDX_MASK) | ((b4 + __popc(peers & lt_mask)) << 18);
+      }
+    }
+    __syncthreads();
+    if (tid < 256) {
+      uint32_t total = 0;
+#pragma unroll 8
+      for (int w = 0; w < VR_WARPS; w++) {  // thread d: exclusive prefix over the warps
+        const uint32_t c = sm.warp_hist[w][tid];
+        sm.warp_hist[w][tid] = (uint16_t)total;
+        total += c;
+      }
+      sm.cta_cnt[tid] = total;
+    }
+    cluster.sync();  // every CTA's digit counts are in place (and every CTA has read back the previous pass)
+    uint32_t total = 0, before = 0;
+    if (tid < 256) {
+#pragma unroll
+      for (uint32_t r = 0; r < VR_CLUSTER; r++) {
+        const uint32_t c = *cluster.map_shared_rank(&sm.cta_cnt[tid], r);
+        total += c;
+        before += r < rank ? c : 0u;
+      }
+    }
+    const uint32_t excl = vs_exclusive_scan_256(total, sm.scan);
+    if (tid < 256) sm.base[tid] = excl + before;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < VR_ITEMS; i++) {
+      if (i < R) {
+        const uint32_t d = (k[i] >> shift) & 255u;
+        const uint32_t pos = sm.base[d] + my_hist[d] + (m[i] >> 18);
+        const uint32_t owner = ((pos >> 10) * inv_R) >> 16;
+        *cluster.map_shared_rank(&buf[pos - owner * per], owner) = make_uint2(k[i], m[i] & VR_IDX_MASK);
+      }
+    }
+    cluster.sync();  // every key of the pass sits in its owner's shared memory
+#pragma unroll
+    for (int i = 0; i < VR_ITEMS; i++) {
+      if (i < R) {
+        const uint2 kv = buf[local_base + i * 32 + lane];
+        k[i] = kv.x;
+        m[i] = kv.y;
+      }
+    }
+  }
+
+  // ---- the Gaussian of every sorted slot (gathered once), the result, and the scan of tiles_touched in that order ----
+#pragma unroll
+  for (int i = 0; i < VR_ITEMS; i++) {
+    if (i < R) {
+      const uint32_t loc = glob_base + i * 32 + lane;
+      m[i] = loc < n ? vals0[seg_b + m[i]] : 0u;
+    }
+  }
+  cluster.sync();  // every read of the unsorted vals0 (by any CTA) precedes the first write of the sorted one
+  uint32_t carry = 0;
+#pragma unroll
+  for (int i = 0; i < VR_ITEMS; i++) {
+    if (i < R) {
+      const uint32_t loc = glob_base + i * 32 + lane;
+      uint32_t x = 0;
+      if (loc < n) {
+        keys0[seg_b + loc] = ((uint64_t)(uint32_t)v << 32) | k[i];
+        vals0[seg_b + loc] = m[i];
+        x = tiles_touched[m[i]];
+      }
+      uint32_t incl = x;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+      }
+      k[i] = carry + incl;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
+  }
+  if (lane == 0) sm.scan[warp] = carry;
+  __syncthreads();
+  if (tid == 0) {
+    uint32_t t = 0;
+#pragma unroll
+    for (int w = 0; w < VR_WARPS; w++) t += sm.scan[w];
+    sm.total = t;
+  }
+  cluster.sync();
+  uint32_t run = v ? offsets[(size_t)v * P - 1] : 0u;  // pairs of the views before mine (preprocess's scan)
+  for (uint32_t r = 0; r < rank; r++) run += *cluster.map_shared_rank(&sm.total, r);
+#pragma unroll 8
+  for (int w = 0; w < VR_WARPS; w++) run += w < warp ? sm.scan[w] : 0u;
+#pragma unroll
+  for (int i = 0; i < VR_ITEMS; i++) {
+    if (i < R) {
+      const uint32_t loc = glob_base + i * 32 + lane;
+      if (loc < n) sorted_offsets[seg_b + loc] = run + k[i];
+    }
+  }
+  cluster.sync();  // no CTA leaves while a peer may still read its shared memory
+}
+
+inline bool vis_sort_registers_enabled() {  // OCRF_VIS_SORT_REG=0: every view through visible_sort_kernel (A/B measurements)
+  static const bool on = !(getenv("OCRF_VIS_SORT_REG") != nullptr && atoi(getenv("OCRF_VIS_SORT_REG")) == 0);
+  return on;
+}
+
 // keys0 / vals0: where the preprocess compacted the visible Gaussians AND where the sorted result lands (4 passes);
 // keys1 / vals1: the other half of the ping-pong.
 int visible_sort(cudaStream_t st, const OcrfShape* sh, const uint32_t* view_start, uint64_t* keys0, uint32_t* vals0,
                  uint64_t* keys1, uint32_t* vals1, const uint32_t* tiles_touched, const uint32_t* offsets,
                  uint32_t* sorted_offsets) {
+  uint32_t skip_upto = 0;
+  if (vis_sort_registers_enabled()) {
+    static int configured[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || !configured[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(visible_sort_reg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)(sizeof(VrFixed) + (size_t)VR_ITEMS * VR_THREADS * sizeof(uint2)));
+      if (e != cudaSuccess) return (int)e;
+      if (dev >= 0 && dev < 64) configured[dev] = 1;
+    }
+    // no view has more visible Gaussians than the sample has Gaussians: size the slots for that
+    const size_t per_row = (size_t)VR_CLUSTER * VR_THREADS;
+    const size_t rows = std::min<size_t>(VR_ITEMS, ((size_t)std::max(sh->P, 1) + per_row - 1) / per_row);
+    OCRF_LAUNCH(visible_sort_reg_kernel, dim3(VR_CLUSTER, sh->V), dim3(VR_THREADS),
+                sizeof(VrFixed) + rows * VR_THREADS * sizeof(uint2), st, sh->P, view_start, keys0, vals0, tiles_touched,
+                offsets, sorted_offsets);
+    if ((uint32_t)sh->P <= VR_CAP) return 0;
+    skip_upto = VR_CAP;
+  }
   OCRF_LAUNCH(visible_sort_kernel, dim3(VS_CLUSTER, sh->V), dim3(VS_THREADS), 0, st, sh->P, view_start, keys0, vals0, keys1,
-              vals1, tiles_touched, offsets, sorted_offsets);
+              vals1, tiles_touched, offsets, sorted_offsets, skip_upto);
   return 0;
 }
 

@@ -84,6 +84,37 @@ def test_preprocess_and_binning_bit_exact(kind, kw, binning, monkeypatch):
             assert np.array_equal(rec[lo:hi, 10], b["point_list"][flo:fhi][orig - 1].astype(np.int32))
 
 
+@pytest.mark.parametrize("P", [1, 31, 1023, 1025, 4097, 24576, 25900, 25910, 40000])  # 25 900 -> 24 551 visible, 25 910 -> 24 587
+def test_visible_sort_segment_sizes_and_depth_ties(P):
+    # The depth sort of the visible Gaussians (visible_sort.cu) has two kernels: one CTA per view up to 24 576 visible
+    # Gaussians (keys in registers, R = ceil(n / 1024) rows per warp), the 8-CTA cluster above that.  Segment sizes on
+    # both sides of every boundary, depths quantised to half metres so that thousands of keys tie (ties must stay in
+    # Gaussian-index order, rasterizer_impl.cu:303-308 sorts stably); lists and ranges bit-exact against the oracle.
+    W, H = 96, 64
+    g, cams = util.small_scene("frustum", P=P, seed=11, W=W, H=H)
+    g["means3D"][:, 2] = np.maximum(1.0, np.round(g["means3D"][:, 2] * 2.0) / 2.0)
+    g["scales"] *= 0.3
+    cam, bg = cams[0], [0.0, 0.0, 0.0]
+    _render_single(g, cam, bg)
+    st = R.last_state(reference_lists=True)
+    _want, wst = util.oracle_forward(g, cam, W, H, bg)
+    b = wst["bin"]
+    assert st["num_pairs"] == b["N"]
+    keys = st["keys"] if "keys" in st else st["keys_ref"]
+    point_list = st["point_list"] if "point_list" in st else st["point_list_ref"]
+    if "point_list_ref" in st and "point_list" in st:
+        assert torch.equal(st["point_list"], st["point_list_ref"])
+    assert np.array_equal(keys.cpu().numpy().view(np.uint64), b["keys"])
+    assert np.array_equal(point_list.cpu().numpy().view(np.uint32), b["point_list"])
+    assert np.array_equal(st["ranges"][0].cpu().numpy().view(np.uint32), b["ranges"])
+    # the culled records index the tile's reference list: this is what the multi-split derives from the depth order
+    rr, full = st["ranges_render"][0].cpu().numpy(), st["ranges"][0].cpu().numpy()
+    rec = st["records"].cpu().numpy()
+    for (lo, hi), (flo, fhi) in zip(rr, full):
+        orig = rec[lo:hi, 6]
+        assert np.array_equal(rec[lo:hi, 10], b["point_list"][flo:fhi][orig - 1].astype(np.int32))
+
+
 @pytest.mark.parametrize("kind,kw", SCENES)
 def test_forward_outputs(kind, kw):
     g, cams = util.small_scene(kind, **kw)
