@@ -265,6 +265,16 @@ struct alignas(16) VrFixed {  // fixed part of the dynamic shared memory; the (d
   uint32_t total;
 };
 
+#ifdef OCRF_VS_STAMPS  // tools/probe/vsort_probe.cu: clock64 of thread 0 of every CTA at the phases of the kernel
+__device__ long long* g_vs_stamps = nullptr;
+#define VR_STAMP(id)                                                                                          \
+  do {                                                                                                        \
+    if (threadIdx.x == 0 && g_vs_stamps) g_vs_stamps[(blockIdx.y * VR_CLUSTER + blockIdx.x) * 64 + (id)] = clock64(); \
+  } while (0)
+#else
+#define VR_STAMP(id) do { } while (0)
+#endif
+
 __device__ __forceinline__ uint32_t vr_peers(uint32_t d, bool few_values) {  // lanes of the warp holding my digit
   if (few_values) return __match_any_sync(0xffffffffu, d);
   uint32_t peers = 0xffffffffu;
@@ -299,6 +309,10 @@ __global__ void __cluster_dims__(VR_CLUSTER, 1, 1) __launch_bounds__(VR_THREADS,
   const uint32_t glob_base = rank * per + local_base;
   const uint32_t lt_mask = (1u << lane) - 1;
   uint16_t* my_hist = sm.warp_hist[warp];
+  VR_STAMP(0);
+#pragma unroll
+  for (int e = 0; e < 4; e++) reinterpret_cast<uint32_t*>(my_hist)[e * 32 + lane] = 0u;
+  __syncwarp();
 
   uint32_t k[VR_ITEMS], m[VR_ITEMS];  // depth bits; position in the segment | rank of the pass << 18
   {
@@ -319,9 +333,9 @@ __global__ void __cluster_dims__(VR_CLUSTER, 1, 1) __launch_bounds__(VR_THREADS,
   for (int pass = 0; pass < 4; pass++) {
     const int shift = 8 * pass;
     const bool few_values = pass == 3;
-    for (int e = tid; e < VR_WARPS * 128; e += VR_THREADS) reinterpret_cast<uint32_t*>(sm.warp_hist)[e] = 0u;
-    __syncthreads();
-    // stable rank inside the warp, row by row (the padding keys are ordinary keys: they sort behind everything)
+    VR_STAMP(1 + 8 * pass);  // keys in registers
+    // stable rank inside the warp, row by row (the padding keys are ordinary keys: they sort behind everything);
+    // a warp's counters are zeroed by the warp itself (below): no CTA barrier in front of the ranking
 #pragma unroll
     for (int i = 0; i < VR_ITEMS; i++) {
       if (i < R) {
@@ -335,6 +349,7 @@ __global__ void __cluster_dims__(VR_CLUSTER, 1, 1) __launch_bounds__(VR_THREADS,
       }
     }
     __syncthreads();
+    VR_STAMP(2 + 8 * pass);  // ranked
     if (tid < 256) {
       uint32_t total = 0;
 #pragma unroll 8
@@ -345,7 +360,9 @@ __global__ void __cluster_dims__(VR_CLUSTER, 1, 1) __launch_bounds__(VR_THREADS,
       }
       sm.cta_cnt[tid] = total;
     }
+    VR_STAMP(3 + 8 * pass);  // own digit counts written
     cluster.sync();  // every CTA's digit counts are in place (and every CTA has read back the previous pass)
+    VR_STAMP(4 + 8 * pass);  // first cluster barrier passed
     uint32_t total = 0, before = 0;
     if (tid < 256) {
 #pragma unroll
@@ -355,9 +372,25 @@ __global__ void __cluster_dims__(VR_CLUSTER, 1, 1) __launch_bounds__(VR_THREADS,
         before += r < rank ? c : 0u;
       }
     }
-    const uint32_t excl = vs_exclusive_scan_256(total, sm.scan);
-    if (tid < 256) sm.base[tid] = excl + before;
+    // exclusive scan over the 256 digits (warps 0-7; sm.scan was last read before the cluster barrier)
+    uint32_t incl = total;
+    if (warp < 8) {
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += y;
+      }
+      if (lane == 31) sm.scan[warp] = incl;
+    }
     __syncthreads();
+    if (tid < 256) {
+      uint32_t off = 0;
+#pragma unroll
+      for (int w = 0; w < 8; w++) off += w < warp ? sm.scan[w] : 0u;
+      sm.base[tid] = off + incl - total + before;
+    }
+    __syncthreads();
+    VR_STAMP(5 + 8 * pass);  // destinations known
 #pragma unroll
     for (int i = 0; i < VR_ITEMS; i++) {
       if (i < R) {
@@ -367,7 +400,12 @@ __global__ void __cluster_dims__(VR_CLUSTER, 1, 1) __launch_bounds__(VR_THREADS,
         *cluster.map_shared_rank(&buf[pos - owner * per], owner) = make_uint2(k[i], m[i] & VR_IDX_MASK);
       }
     }
+    __syncwarp();  // the warp has read its prefixes: clear its counters for the next pass
+#pragma unroll
+    for (int e = 0; e < 4; e++) reinterpret_cast<uint32_t*>(my_hist)[e * 32 + lane] = 0u;
+    VR_STAMP(6 + 8 * pass);  // scattered
     cluster.sync();  // every key of the pass sits in its owner's shared memory
+    VR_STAMP(7 + 8 * pass);  // second cluster barrier passed
 #pragma unroll
     for (int i = 0; i < VR_ITEMS; i++) {
       if (i < R) {
@@ -379,6 +417,8 @@ __global__ void __cluster_dims__(VR_CLUSTER, 1, 1) __launch_bounds__(VR_THREADS,
   }
 
   // ---- the Gaussian of every sorted slot (gathered once), the result, and the scan of tiles_touched in that order ----
+  // (keys0 was last read in the load phase, many cluster barriers ago: it can be overwritten now; the tile counts are
+  // read-only: both global round trips of the gather chain run before the barrier, not after it)
 #pragma unroll
   for (int i = 0; i < VR_ITEMS; i++) {
     if (i < R) {
@@ -386,19 +426,24 @@ __global__ void __cluster_dims__(VR_CLUSTER, 1, 1) __launch_bounds__(VR_THREADS,
       m[i] = loc < n ? vals0[seg_b + m[i]] : 0u;
     }
   }
-  cluster.sync();  // every read of the unsorted vals0 (by any CTA) precedes the first write of the sorted one
-  uint32_t carry = 0;
 #pragma unroll
   for (int i = 0; i < VR_ITEMS; i++) {
     if (i < R) {
       const uint32_t loc = glob_base + i * 32 + lane;
-      uint32_t x = 0;
       if (loc < n) {
         keys0[seg_b + loc] = ((uint64_t)(uint32_t)v << 32) | k[i];
-        vals0[seg_b + loc] = m[i];
-        x = tiles_touched[m[i]];
+        k[i] = tiles_touched[m[i]];
+      } else {
+        k[i] = 0u;
       }
-      uint32_t incl = x;
+    }
+  }
+  VR_STAMP(33);  // passes done, Gaussian indices and tile counts gathered
+  uint32_t carry = 0;
+#pragma unroll
+  for (int i = 0; i < VR_ITEMS; i++) {
+    if (i < R) {
+      uint32_t incl = k[i];
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
@@ -410,13 +455,17 @@ __global__ void __cluster_dims__(VR_CLUSTER, 1, 1) __launch_bounds__(VR_THREADS,
   }
   if (lane == 0) sm.scan[warp] = carry;
   __syncthreads();
-  if (tid == 0) {
-    uint32_t t = 0;
+  if (warp == 0) {
+    uint32_t t = sm.scan[lane];
 #pragma unroll
-    for (int w = 0; w < VR_WARPS; w++) t += sm.scan[w];
-    sm.total = t;
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) sm.total = t;
   }
+  VR_STAMP(34);  // tile counts scanned inside the CTA
+  // ONE barrier: every read of the unsorted vals0 (by any CTA) precedes the first write of the sorted one, and every
+  // CTA's total is in place
   cluster.sync();
+  VR_STAMP(35);
   uint32_t run = v ? offsets[(size_t)v * P - 1] : 0u;  // pairs of the views before mine (preprocess's scan)
   for (uint32_t r = 0; r < rank; r++) run += *cluster.map_shared_rank(&sm.total, r);
 #pragma unroll 8
@@ -425,10 +474,15 @@ __global__ void __cluster_dims__(VR_CLUSTER, 1, 1) __launch_bounds__(VR_THREADS,
   for (int i = 0; i < VR_ITEMS; i++) {
     if (i < R) {
       const uint32_t loc = glob_base + i * 32 + lane;
-      if (loc < n) sorted_offsets[seg_b + loc] = run + k[i];
+      if (loc < n) {
+        vals0[seg_b + loc] = m[i];
+        sorted_offsets[seg_b + loc] = run + k[i];
+      }
     }
   }
+  VR_STAMP(36);
   cluster.sync();  // no CTA leaves while a peer may still read its shared memory
+  VR_STAMP(37);
 }
 
 inline bool vis_sort_registers_enabled() {  // OCRF_VIS_SORT_REG=0: every view through visible_sort_kernel (A/B measurements)
