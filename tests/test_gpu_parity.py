@@ -84,12 +84,13 @@ def test_preprocess_and_binning_bit_exact(kind, kw, binning, monkeypatch):
             assert np.array_equal(rec[lo:hi, 10], b["point_list"][flo:fhi][orig - 1].astype(np.int32))
 
 
-@pytest.mark.parametrize("P", [1, 31, 1023, 1025, 4097, 24576, 25900, 25910, 40000])  # 25 900 -> 24 551 visible, 25 910 -> 24 587
+@pytest.mark.parametrize("P", [1, 31, 1023, 1025, 4097, 24576, 40000, 138000, 138200])  # 138 000 -> 130 950 visible (16 rows), 138 200 -> 131 120
 def test_visible_sort_segment_sizes_and_depth_ties(P):
-    # The depth sort of the visible Gaussians (visible_sort.cu) has two kernels: one CTA per view up to 24 576 visible
-    # Gaussians (keys in registers, R = ceil(n / 1024) rows per warp), the 8-CTA cluster above that.  Segment sizes on
-    # both sides of every boundary, depths quantised to half metres so that thousands of keys tie (ties must stay in
-    # Gaussian-index order, rasterizer_impl.cu:303-308 sorts stably); lists and ranges bit-exact against the oracle.
+    # The depth sort of the visible Gaussians (visible_sort.cu) has two kernels: keys in registers up to 131 072 visible
+    # Gaussians per view (R = ceil(n / 8192) rows of 32 per warp, 1 .. 16), keys through global memory above that.
+    # Segment sizes on both sides of every boundary, depths quantised to half metres so that thousands of keys tie (ties
+    # must stay in Gaussian-index order, rasterizer_impl.cu:303-308 sorts stably); lists and ranges bit-exact against
+    # the oracle.
     W, H = 96, 64
     g, cams = util.small_scene("frustum", P=P, seed=11, W=W, H=H)
     g["means3D"][:, 2] = np.maximum(1.0, np.round(g["means3D"][:, 2] * 2.0) / 2.0)

@@ -12,8 +12,10 @@
 #include "../../ocrfdet_b200/csrc/visible_sort.cu"
 
 int main(int argc, char** argv) {
-  const int V = 6, P = 100000;
+  const int V = 6;
   const int n_per = argc > 1 ? atoi(argv[1]) : 19000;
+  const int P = std::max(100000, n_per);  // a view never has more visible Gaussians than its sample has Gaussians:
+                                          // the host sizes the kernel's shared memory from P
   std::mt19937 rng(1);
   std::vector<uint32_t> view_start(V + 1);
   for (int v = 0; v <= V; v++) view_start[v] = (uint32_t)v * n_per;
