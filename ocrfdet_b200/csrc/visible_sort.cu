@@ -5,8 +5,15 @@
 // is then split stably by tile (multisplit.cu).  Round 1 pushed these 114 k keys through the global onesweep sort: a
 // histogram kernel and five chained passes, 77 us for 1.4 MB -- a fixed chain of launches and L2 round trips.
 //
-// One thread-block CLUSTER of 8 CTAs owns a view (the views are already segments of the compacted key array, so the
-// view bits need no pass).  Per 8-bit digit place, CTA r of the cluster
+// Two kernels, both with one thread-block CLUSTER of 8 CTAs per view (the views are already segments of the compacted
+// key array, so the view bits need no pass) and four 8-bit passes over the depth bits:
+//   visible_sort_reg_kernel  (below, second in this file) holds the keys in REGISTERS and exchanges them through
+//                            distributed shared memory: up to 131 072 visible Gaussians per view -- the one that runs;
+//   visible_sort_kernel      (first in this file, the round's first version) keeps them in an L2-resident ping-pong:
+//                            any segment size; takes the views above that bound, or all of them with OCRF_VIS_SORT_REG=0.
+// Both end with the same epilogue (see below) and write the same bits.
+//
+// visible_sort_kernel: per 8-bit digit place, CTA r of the cluster
 //   (1) reads the eight digit histograms of the pass through distributed shared memory and derives, per digit, the
 //       global base + the keys of lower-ranked CTAs: the stable destination of its own keys,
 //   (2) ranks its eighth of the segment (warp match_any multi-split, the ranking of radix_sort.cu; 1024 threads x 4
