@@ -190,6 +190,30 @@ def test_every_dependent_launch_kernel_waits_for_its_predecessor():
             assert body.lstrip().startswith("pdl_enter();"), "%s is launched with PDL but does not wait first" % name
 
 
+def test_visible_sort_slot_arithmetic_is_exact_for_every_row_count():
+    """visible_sort_reg_kernel (csrc/visible_sort.cu) finds the CTA that owns a destination slot with a multiply by a
+    16-bit reciprocal instead of a division, and packs (position in the segment | rank of the pass) into one word.
+    Both are exact only within bounds set by the kernel's constants: read the constants from the source and check the
+    arithmetic for every row count the kernel can run with."""
+    import re
+    src = open(os.path.join(ROOT, "ocrfdet_b200", "csrc", "visible_sort.cu")).read()
+    const = {k: int(v) for k, v in re.findall(r"constexpr int (VR_[A-Z]+) = (\d+);", src)}
+    cluster, threads, items = const["VR_CLUSTER"], const["VR_THREADS"], const["VR_ITEMS"]
+    idx_mask = int(re.search(r"VR_IDX_MASK = (0x[0-9a-f]+)u", src).group(1), 16)
+    shift = int(re.search(r"<< (\d+)\);\n\s+}\n\s+}\n\s+__syncthreads\(\);\n\s+VR_STAMP\(2", src).group(1))
+    assert threads == 1024 and "(pos >> 10) * inv_R" in src          # the owner is found from pos / 1024
+    assert idx_mask + 1 == 1 << shift                                 # rank sits right above the position
+    assert cluster * threads * items <= idx_mask + 1                  # every position in the segment fits
+    assert (32 * items) << shift < 1 << 32                            # largest rank inside a warp (32 * rows) fits above it
+    assert 32 * items * (threads // 32) < 1 << 16                     # u16 per-warp counters and their prefix over the warps
+    for rows in range(1, items + 1):
+        inv = (65536 + rows - 1) // rows
+        per = threads * rows
+        for pos in range(0, cluster * per, 97):
+            assert ((pos >> 10) * inv) >> 16 == pos // per
+        assert (((cluster * per - 1) >> 10) * inv) >> 16 == cluster - 1
+
+
 def test_ctypes_signatures_match_the_header_arity():
     """Every entry point declared in include/ocrf_raster.h is bound in _lib.py with as many arguments as the header
     declares (ctypes would silently pass too few or too many)."""
